@@ -1,0 +1,31 @@
+# Builds the product library (sm_100a only) and the CPU oracle (test infrastructure).
+NVCC      ?= /usr/local/cuda/bin/nvcc
+CC        ?= gcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC      := recs_b200/csrc
+LIB       := recs_b200/librecs_gpu.so
+CU        := $(CSRC)/gravity.cu $(CSRC)/streaming.cu $(CSRC)/context.cu
+HOSTCPP   := $(wildcard $(CSRC)/host/*.cpp)
+OBJ       := $(CU:.cu=.o) $(HOSTCPP:.cpp=.o)
+HDR       := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/host/*.h) include/recs_gpu.h include/recs_ecs.h
+
+all: $(LIB) oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
+	$(NVCC) $(NVCCFLAGS) -c $< -o $@
+
+$(CSRC)/host/%.o: $(CSRC)/host/%.cpp $(HDR)
+	g++ -O2 -std=c++17 -fPIC -Wall -Iinclude -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl -lpthread
+
+oracle:
+	$(MAKE) -C oracle
+
+clean:
+	rm -f $(OBJ) $(LIB)
+	$(MAKE) -C oracle clean
+
+.PHONY: all oracle clean

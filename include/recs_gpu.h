@@ -1,0 +1,234 @@
+/*
+ * recs_gpu.h -- C ABI of librecs_gpu.so: the B200 (sm_100a) data-parallel hot path of the
+ * recs ECS engine (n-body systems, rain streaming systems, plain query iteration) behind the
+ * reference's own System / Schedule / Executor plugin contract.
+ *
+ * The reference (martinjonsson01/recs) has no FFI of its own; every entry point below cites the
+ * Rust interface (file:line under the reference checkout) that a thin `impl System` shim on
+ * the Rust side would forward to.  INTEGRATION.md shows that shim.
+ *
+ * Conventions
+ *   - every function returns an int32 status (RECS_OK == 0); nothing throws or aborts across
+ *     the ABI.  Errors are sticky per context until recs_gpu_clear_error().
+ *   - every function may be called from any host thread (the reference runs a system on an
+ *     arbitrary worker thread each tick, crates/scheduler/src/executor/worker.rs:143-154); the
+ *     context serialises calls internally and selects its device on every call.
+ *   - plain pointers and sizes only; component columns are described as (archetype index,
+ *     component id, element size, element count) exactly like the reference's
+ *     `Archetype::component_typeid_to_component_vec` (crates/ecs/src/archetypes.rs:178-182).
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *     RECS_ERR_NO_DEVICE.
+ */
+#ifndef RECS_GPU_H
+#define RECS_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RECS_GPU_ABI_VERSION 1
+
+/* ------------------------------------------------------------------------------------------
+ * Status codes.  Mirrors SystemError / ExecutionError
+ * (crates/ecs/src/systems/mod.rs:28-45, crates/ecs/src/lib.rs:419-432).
+ * ---------------------------------------------------------------------------------------- */
+enum {
+    RECS_OK = 0,
+    RECS_ERR_INVALID_ARGUMENT = 1,  /* null pointer, bad enum, bad handle                      */
+    RECS_ERR_NO_DEVICE = 2,         /* no CUDA device / driver: there is no CPU fallback       */
+    RECS_ERR_CUDA = 3,              /* a CUDA runtime call failed (sticky)                     */
+    RECS_ERR_NCCL = 4,              /* an NCCL call failed (sticky)                            */
+    RECS_ERR_MISSING_PARAMETER = 5, /* SystemError::MissingParameter: a column the system needs
+                                       is not bound for a matched archetype                    */
+    RECS_ERR_STALE_BINDING = 6,     /* column bound before recs_gpu_invalidate() and not rebound*/
+    RECS_ERR_SIZE_MISMATCH = 7,     /* element size / count disagree between columns           */
+    RECS_ERR_BORROW_CONFLICT = 8,   /* "Lock of ComponentVec<T> is already taken!"
+                                       (crates/ecs/src/archetypes.rs:145-151)                  */
+    RECS_ERR_SCHEDULE = 9,          /* ScheduleError (crates/ecs/src/lib.rs:470-493)           */
+    RECS_ERR_WORLD = 10,            /* WorldError (crates/ecs/src/lib.rs:600-645)              */
+    RECS_ERR_UNSUPPORTED = 11
+};
+
+typedef struct recs_gpu_ctx recs_gpu_ctx;
+
+/* Context creation parameters.  Replaces the compile-time constants of the reference:
+ * FIXED_TIME_STEP (crates/n-body/src/lib.rs:14), GRAVITATIONAL_CONSTANT (:123), f32::EPSILON
+ * (:118), rain's FIXED_TIME_STEP / GRAVITY_ACCELERATION / TERMINAL_VELOCITY / WIND_ACCELERATION
+ * (crates/rain-simulation/src/lib.rs:15,59-60,72).  recs_gpu_default_config() fills in exactly
+ * those values. */
+typedef struct recs_gpu_config {
+    int32_t device;            /* CUDA device ordinal                                          */
+    int32_t rank;              /* this process' shard index (0 when single GPU)                */
+    int32_t world_size;        /* number of shards (1 when single GPU)                         */
+    int32_t use_cuda_graph;    /* capture recs_gpu_tick chains into a CUDA graph               */
+    float nbody_dt;            /* 1/20000                                                      */
+    float nbody_g;             /* 6.67e-11                                                     */
+    float nbody_epsilon;       /* f32::EPSILON = 1.1920929e-7                                  */
+    float rain_dt;             /* 1/20                                                         */
+    float rain_gravity;        /* 9.82                                                         */
+    float rain_terminal;       /* 9.0                                                          */
+    float rain_wind_accel;     /* 10.0                                                         */
+    float rain_wind_deg_per_s; /* 10.0 (WIND_ROTATION_SPEED)                                   */
+} recs_gpu_config;
+
+void recs_gpu_default_config(recs_gpu_config* cfg);
+
+int32_t recs_gpu_abi_version(void);
+
+/* Lifecycle.  Replaces `E::default()` / `Drop for WorkerPool`
+ * (crates/ecs/src/lib.rs:386-400, crates/scheduler/src/executor/mod.rs:84-124). */
+int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx);
+int32_t recs_gpu_destroy(recs_gpu_ctx* ctx);
+const char* recs_gpu_last_error(recs_gpu_ctx* ctx); /* never NULL; "" when no error           */
+int32_t recs_gpu_clear_error(recs_gpu_ctx* ctx);
+int32_t recs_gpu_synchronize(recs_gpu_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Component columns: device-resident mirrors of `RwLock<Vec<T>>`
+ * (crates/ecs/src/archetypes.rs:15, 208-263; World::borrow_component_vecs(_mut),
+ * crates/ecs/src/lib.rs:807-833).
+ *
+ * The host keeps ownership of `host_ptr`; it must stay valid until the next bind / invalidate
+ * for that column (the Rust shim holds the column's write guard for that long).  The device
+ * copy has the SAME byte layout as the host Vec<T> (Position = 3 x f32, 12 bytes).
+ * ---------------------------------------------------------------------------------------- */
+int32_t recs_gpu_bind_column(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id,
+                             void* host_ptr, uint32_t elem_size, uint64_t count);
+/* host -> device / device -> host for one bound column (async on the context stream unless
+ * RECS_GPU_SYNC is passed to the system call that follows; download always completes before it
+ * returns). */
+int32_t recs_gpu_upload(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id);
+int32_t recs_gpu_download(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id);
+/* Structural change happened on the host (command-buffer playback,
+ * crates/ecs/src/lib.rs:321-323): all bindings of that archetype become stale. */
+int32_t recs_gpu_invalidate(recs_gpu_ctx* ctx, uint32_t archetype_index);
+/* Raw device pointer of a column (for zero-copy interop, e.g. torch / NCCL plumbing). */
+int32_t recs_gpu_column_device_ptr(recs_gpu_ctx* ctx, uint32_t archetype_index,
+                                   uint64_t component_id, void** out_dev_ptr, uint64_t* out_count);
+
+/* ------------------------------------------------------------------------------------------
+ * GPU systems.  A GPU system is the device-side body of one reference system function plus the
+ * `System` trait data the schedule needs (crates/ecs/src/systems/mod.rs:48-62).
+ * ---------------------------------------------------------------------------------------- */
+typedef enum recs_gpu_system_kind {
+    /* crates/n-body/src/lib.rs:104-135 -- gravity(Read<Position>, Write<Acceleration>,
+     *                                             Query<(Read<Position>, Read<Mass>)>)
+     * components = {Position, Acceleration, Mass}                                            */
+    RECS_SYS_NBODY_GRAVITY = 1,
+    /* crates/n-body/src/lib.rs:87-93 -- movement(Write<Position>, Read<Velocity>)
+     * components = {Position, Velocity}                                                      */
+    RECS_SYS_NBODY_MOVEMENT = 2,
+    /* crates/n-body/src/lib.rs:95-102 -- acceleration(Write<Velocity>, Read<Acceleration>)
+     * components = {Velocity, Acceleration}                                                  */
+    RECS_SYS_NBODY_ACCELERATION = 3,
+    /* crates/rain-simulation/src/lib.rs:65-70 -- gravity(Write<Velocity>); components = {Velocity} */
+    RECS_SYS_RAIN_GRAVITY = 4,
+    /* crates/rain-simulation/src/lib.rs:86-92 -- wind(Write<Velocity>); components = {Velocity}    */
+    RECS_SYS_RAIN_WIND = 5,
+    /* crates/rain-simulation/src/lib.rs:94-96 -- movement(Write<Position>, Read<Velocity>)          */
+    RECS_SYS_RAIN_MOVEMENT = 6,
+    /* crates/rain-simulation/src/lib.rs:78-84 -- wind_direction(): no component access; rotates
+     * the context's wind direction (host side, passed to the wind kernel as an argument)     */
+    RECS_SYS_RAIN_WIND_DIRECTION = 7,
+    /* crates/ecs_bench_suite/src/recs/simple_iter.rs:47-49 -- |Write<Position>, Read<Velocity>|
+     * position.0 += velocity.0; also the generic (Write<A>, Read<B>) f32-vector par-iter query.
+     * components = {A (written), B (read)}                                                   */
+    RECS_SYS_QUERY_ADD = 8
+} recs_gpu_system_kind;
+
+/* One entry of `System::component_accesses()` (crates/ecs/src/systems/mod.rs:88-94). */
+typedef struct recs_gpu_access {
+    uint64_t component_id;
+    uint8_t is_write;
+} recs_gpu_access;
+
+#define RECS_GPU_MAX_ACCESSES 8
+/* What the schedule needs to know about a system: `System::name()` and
+ * `System::component_accesses()` in parameter order (crates/ecs/src/systems/mod.rs:973-978). */
+typedef struct recs_gpu_system_desc {
+    const char* name; /* owned by the context */
+    uint32_t n_access;
+    recs_gpu_access access[RECS_GPU_MAX_ACCESSES];
+} recs_gpu_system_desc;
+
+/* Registers a GPU system.  `component_ids` are the host's ids (TypeId stand-ins) for the
+ * components listed next to the kind above, in that order. */
+int32_t recs_gpu_system_create(recs_gpu_ctx* ctx, recs_gpu_system_kind kind,
+                               const uint64_t* component_ids, uint32_t n_component_ids,
+                               uint32_t* out_system_id);
+int32_t recs_gpu_system_describe(recs_gpu_ctx* ctx, uint32_t system_id, recs_gpu_system_desc* out);
+/* Result of `SystemParameters::get_archetype_indices` (crates/ecs/src/systems/mod.rs:986-1000)
+ * computed by the host for the system's outer parameters, in iteration order. */
+int32_t recs_gpu_system_set_archetypes(recs_gpu_ctx* ctx, uint32_t system_id,
+                                       const uint32_t* archetype_indices, uint32_t n);
+/* Same for the nested `Query<...>` parameter of gravity (its own archetype match,
+ * crates/ecs/src/systems/mod.rs:1042). */
+int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* ctx, uint32_t system_id,
+                                             const uint32_t* archetype_indices, uint32_t n);
+
+#define RECS_GPU_ASYNC 0u /* enqueue only: every dependent is a GPU system of this context    */
+#define RECS_GPU_SYNC 1u  /* return after the system's writes are visible to the host thread  */
+/* `SequentiallyIterable::run(&self, world)` (crates/ecs/src/systems/iteration.rs:9-14) for a
+ * GPU system: launches its kernels on the context stream.  Completion in the reference is the
+ * drop of `SystemExecutionGuard::finished_sender` after `run` returns
+ * (crates/ecs/src/lib.rs:525-557); with RECS_GPU_SYNC the shim may drop it on return. */
+int32_t recs_gpu_run_system(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t flags);
+
+/* The per-tick order produced by the schedule (PrecedenceGraph batches flattened,
+ * crates/scheduler/src/schedule/mod.rs:205-333) for the GPU systems of this context. */
+int32_t recs_gpu_set_tick_order(recs_gpu_ctx* ctx, const uint32_t* system_ids, uint32_t n);
+/* `Executor::execute_once` x n_ticks (crates/scheduler/src/executor/mod.rs:191-236) for a chain
+ * made only of GPU systems: one stream-ordered chain (a CUDA graph when enabled). */
+int32_t recs_gpu_tick(recs_gpu_ctx* ctx, uint32_t n_ticks);
+
+/* Rain: current wind direction (the reference's `static WIND_DIRECTION`,
+ * crates/rain-simulation/src/lib.rs:75). */
+int32_t recs_gpu_set_wind_direction(recs_gpu_ctx* ctx, const float xyz[3]);
+int32_t recs_gpu_get_wind_direction(recs_gpu_ctx* ctx, float xyz[3]);
+
+/* ------------------------------------------------------------------------------------------
+ * Index-sharded multi-GPU n-body (one process per GPU).  Rank r owns rows
+ * [r*N/R, (r+1)*N/R) of the body archetype; positions are exchanged every step with an NCCL
+ * all-gather on a second stream, overlapped with the local j-tiles of gravity.
+ * ---------------------------------------------------------------------------------------- */
+#define RECS_GPU_NCCL_ID_BYTES 128
+int32_t recs_gpu_comm_get_unique_id(recs_gpu_ctx* ctx, uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]);
+int32_t recs_gpu_comm_init(recs_gpu_ctx* ctx, const uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]);
+/* Rows [row_begin, row_end) of gravity / movement / acceleration that this rank computes. */
+int32_t recs_gpu_shard_rows(recs_gpu_ctx* ctx, uint64_t n_rows, uint64_t* row_begin,
+                            uint64_t* row_end);
+
+/* ------------------------------------------------------------------------------------------
+ * Measurement hooks (used by bench.py; all times are CUDA-event times on the context stream).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct recs_gpu_timing {
+    float last_tick_chain_ms;    /* whole recs_gpu_tick call                                  */
+    float gravity_ms;            /* sum over launches of the interaction kernel               */
+    float gravity_reduce_ms;
+    float movement_ms;
+    float acceleration_ms;
+    float pack_ms;
+    float other_ms;
+    uint64_t kernel_launches;    /* kernels launched by this library since create / reset     */
+    uint64_t gravity_launches;
+} recs_gpu_timing;
+int32_t recs_gpu_enable_timing(recs_gpu_ctx* ctx, int32_t enabled);
+int32_t recs_gpu_get_timing(recs_gpu_ctx* ctx, recs_gpu_timing* out);
+int32_t recs_gpu_reset_timing(recs_gpu_ctx* ctx);
+/* Issue rate of the FP32 FMA pipe measured on this GPU with a register-resident FFMA2 loop:
+ * out_tflops = 2 * FMAs / s; out_sm_mhz = the SM clock derived from clock64 over the run. */
+int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* ctx, int32_t packed, float* out_tflops,
+                                   float* out_sm_mhz);
+/* Writes a buffer larger than L2 (timing hygiene between iterations). */
+int32_t recs_gpu_flush_l2(recs_gpu_ctx* ctx);
+/* Pinned host memory for the end-to-end path. */
+int32_t recs_gpu_host_alloc(recs_gpu_ctx* ctx, size_t bytes, void** out_ptr);
+int32_t recs_gpu_host_free(recs_gpu_ctx* ctx, void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECS_GPU_H */

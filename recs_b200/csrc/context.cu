@@ -1,0 +1,1024 @@
+// librecs_gpu.so -- context, device column mirrors, GPU systems and the C ABI (include/recs_gpu.h).
+//
+// Host-side logic only; the kernels are in gravity.cu / streaming.cu.  A context owns one CUDA
+// stream (plus a communication stream when sharded), the device mirrors of the bound component
+// columns and the workspace of the gravity system (pair-interleaved posm mirror, fragments).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/recs_gpu.h"
+#include "kernels.cuh"
+#include "nccl_dyn.h"
+
+namespace recs {
+namespace {
+
+struct Column {
+    void* host = nullptr;
+    void* dev = nullptr;
+    uint32_t elem = 0;
+    uint64_t count = 0;
+    size_t cap = 0;  // bytes allocated at dev
+    bool stale = false;
+    uint64_t version = 0;  // bumped on every write (upload or system)
+};
+
+struct System {
+    recs_gpu_system_kind kind;
+    uint64_t comp[3] = {0, 0, 0};
+    uint32_t n_comp = 0;
+    std::string name;
+    std::vector<recs_gpu_access> access;
+    std::vector<uint32_t> archs;   // outer parameters' archetypes, iteration order
+    std::vector<uint32_t> qarchs;  // nested Query archetypes (gravity)
+};
+
+enum TimeSlot { T_GRAVITY = 0, T_REDUCE, T_MOVEMENT, T_ACCEL, T_PACK, T_OTHER, T_CHAIN, T_COUNT };
+
+struct TimedSpan {
+    cudaEvent_t a, b;
+    int slot;
+};
+
+typedef std::pair<uint32_t, uint64_t> ColKey;
+
+}  // namespace
+}  // namespace recs
+
+using namespace recs;
+
+struct recs_gpu_ctx {
+    std::mutex mu;
+    recs_gpu_config cfg;
+    int32_t status = RECS_OK;
+    std::string error;
+    cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
+    int sm_count = 148;
+    int grav_ctas_per_sm = 2;
+
+    std::map<ColKey, Column> columns;
+    std::vector<System> systems;
+    std::vector<uint32_t> order;
+    uint64_t epoch = 0;  // bumped whenever bindings / archetype lists / order change
+
+    // gravity workspace
+    float* posm = nullptr;
+    size_t posm_cap = 0;
+    uint64_t posm_bodies = 0;  // padded body count currently laid out
+    std::vector<std::pair<ColKey, uint64_t>> posm_sources;  // (column, version) the mirror was packed from
+    float4* frags = nullptr;
+    size_t frags_cap = 0;
+
+    // rain
+    float wind[3] = {1.f, 0.f, 0.f};
+
+    // CUDA graph of one tick
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_epoch = ~0ull;
+    bool capturing = false;
+
+    // timing
+    bool timing = false;
+    std::vector<TimedSpan> spans;
+    std::vector<cudaEvent_t> event_pool;
+    uint64_t kernel_launches = 0;
+    uint64_t gravity_launches = 0;
+    float chain_ms = 0.f;
+
+    // NCCL
+    NcclApi nccl;
+    NcclApi::comm_t comm = nullptr;
+
+    // misc
+    float* l2_flush = nullptr;
+    size_t l2_flush_bytes = 0;
+};
+
+namespace {
+
+int32_t fail(recs_gpu_ctx* c, int32_t code, const std::string& msg) {
+    if (c->status == RECS_OK) {
+        c->status = code;
+        c->error = msg;
+    }
+    return code;
+}
+
+#define RECS_CUDA(c, expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t e__ = (expr);                                                                \
+        if (e__ != cudaSuccess)                                                                  \
+            return fail((c), RECS_ERR_CUDA,                                                      \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+    } while (0)
+
+#define RECS_ENTER(c)                                                                            \
+    if (!(c)) return RECS_ERR_INVALID_ARGUMENT;                                                  \
+    std::lock_guard<std::mutex> lock__((c)->mu);                                                 \
+    if ((c)->status != RECS_OK) return (c)->status;                                              \
+    {                                                                                            \
+        cudaError_t e__ = cudaSetDevice((c)->cfg.device);                                        \
+        if (e__ != cudaSuccess) return fail((c), RECS_ERR_CUDA, cudaGetErrorString(e__));        \
+    }
+
+cudaEvent_t get_event(recs_gpu_ctx* c) {
+    if (!c->event_pool.empty()) {
+        cudaEvent_t e = c->event_pool.back();
+        c->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// RAII bracket of one kernel category with CUDA events on the context stream.
+struct Timed {
+    recs_gpu_ctx* c;
+    TimedSpan s;
+    bool on;
+    Timed(recs_gpu_ctx* ctx, int slot) : c(ctx), on(ctx->timing && !ctx->capturing) {
+        if (on) {
+            s.a = get_event(c);
+            s.b = get_event(c);
+            s.slot = slot;
+            cudaEventRecord(s.a, c->stream);
+        }
+    }
+    ~Timed() {
+        if (on) {
+            cudaEventRecord(s.b, c->stream);
+            c->spans.push_back(s);
+        }
+    }
+};
+
+Column* find_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
+    auto it = c->columns.find(ColKey(arch, comp));
+    return it == c->columns.end() ? nullptr : &it->second;
+}
+
+int32_t need_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, uint32_t elem, Column** out) {
+    Column* col = find_column(c, arch, comp);
+    char buf[160];
+    if (!col || !col->dev) {
+        snprintf(buf, sizeof buf, "could not execute system due to missing parameter: archetype %u component %llu is not bound",
+                 arch, (unsigned long long)comp);
+        return fail(c, RECS_ERR_MISSING_PARAMETER, buf);
+    }
+    if (col->stale) {
+        snprintf(buf, sizeof buf, "archetype %u component %llu was invalidated and not rebound", arch,
+                 (unsigned long long)comp);
+        return fail(c, RECS_ERR_STALE_BINDING, buf);
+    }
+    if (col->elem != elem) {
+        snprintf(buf, sizeof buf, "archetype %u component %llu has element size %u, system expects %u", arch,
+                 (unsigned long long)comp, col->elem, elem);
+        return fail(c, RECS_ERR_SIZE_MISMATCH, buf);
+    }
+    *out = col;
+    return RECS_OK;
+}
+
+int32_t same_count(recs_gpu_ctx* c, const Column* a, const Column* b) {
+    if (a->count != b->count) return fail(c, RECS_ERR_SIZE_MISMATCH, "columns of one archetype differ in length");
+    return RECS_OK;
+}
+
+template <typename T>
+int32_t ensure(recs_gpu_ctx* c, T** p, size_t* cap, size_t bytes) {
+    if (*cap >= bytes && *p) return RECS_OK;
+    if (c->capturing) return fail(c, RECS_ERR_CUDA, "workspace growth during graph capture");
+    if (*p) RECS_CUDA(c, cudaFree(*p));
+    *p = nullptr;
+    *cap = 0;
+    RECS_CUDA(c, cudaMalloc(reinterpret_cast<void**>(p), bytes));
+    *cap = bytes;
+    return RECS_OK;
+}
+
+// Equal slices of the tile-padded body range, one per rank.
+void shard_rows(const recs_gpu_config& cfg, uint64_t n, uint64_t* slice, uint64_t* rb, uint64_t* re) {
+    const uint64_t R = cfg.world_size > 0 ? (uint64_t)cfg.world_size : 1;
+    const uint64_t quantum = (uint64_t)kGravTile * R;
+    const uint64_t padded = (n + quantum - 1) / quantum * quantum;
+    const uint64_t s = padded / R;
+    *slice = s;
+    uint64_t b = s * (uint64_t)cfg.rank, e = b + s;
+    if (b > n) b = n;
+    if (e > n) e = n;
+    *rb = b;
+    *re = e;
+}
+
+// ---- systems -----------------------------------------------------------------------------------
+int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
+    const uint64_t POS = sys.comp[0], ACC = sys.comp[1], MASS = sys.comp[2];
+    const bool sharded = c->cfg.world_size > 1;
+    // 1. the nested Query<(Read<Position>, Read<Mass>)>: concatenation of its archetypes
+    std::vector<std::pair<Column*, Column*>> q;
+    uint64_t total_j = 0;
+    std::vector<std::pair<ColKey, uint64_t>> sources;
+    for (uint32_t a : sys.qarchs) {
+        Column *p, *m;
+        int32_t st;
+        if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
+        if ((st = need_column(c, a, MASS, 4, &m)) != RECS_OK) return st;
+        if ((st = same_count(c, p, m)) != RECS_OK) return st;
+        q.push_back(std::make_pair(p, m));
+        total_j += p->count;
+        sources.push_back(std::make_pair(ColKey(a, POS), p->version));
+        sources.push_back(std::make_pair(ColKey(a, MASS), m->version));
+    }
+    if (sharded && (sys.qarchs.size() != 1 || sys.archs.size() != 1 || sys.qarchs[0] != sys.archs[0]))
+        return fail(c, RECS_ERR_UNSUPPORTED, "sharded gravity needs exactly one body archetype");
+    if (total_j >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 bodies");
+
+    uint64_t slice = 0, rb = 0, re = 0;
+    shard_rows(c->cfg, total_j, &slice, &rb, &re);
+    const uint64_t n_jpad = sharded ? slice * (uint64_t)c->cfg.world_size
+                                    : (total_j + kGravTile - 1) / kGravTile * kGravTile;
+    const uint32_t n_tiles = (uint32_t)(n_jpad / kGravTile);
+
+    int32_t st = ensure(c, &c->posm, &c->posm_cap, std::max<size_t>(n_jpad, kGravTile) * 16);
+    if (st != RECS_OK) return st;
+
+    // 2. refresh the posm mirror if any source column changed since it was packed
+    const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad || c->capturing;
+    if (dirty || sharded) {
+        Timed t(c, T_PACK);
+        if (!sharded) {
+            uint64_t off = 0;
+            for (auto& pm : q) {
+                RECS_CUDA(c, launch_pack_posm((const float*)pm.first->dev, (const float*)pm.second->dev,
+                                              c->cfg.nbody_g, c->posm, 0, pm.first->count, off, c->stream));
+                off += pm.first->count;
+                c->kernel_launches += pm.first->count ? 1 : 0;
+            }
+            RECS_CUDA(c, launch_pad_posm(c->posm, total_j, n_jpad, c->stream));
+            c->kernel_launches += n_jpad > total_j ? 1 : 0;
+        } else {
+            // own rows only; the other slices arrive through the all-gather below
+            RECS_CUDA(c, launch_pack_posm((const float*)q[0].first->dev, (const float*)q[0].second->dev,
+                                          c->cfg.nbody_g, c->posm, rb, re - rb, rb, c->stream));
+            const uint64_t own_end = slice * ((uint64_t)c->cfg.rank + 1);
+            RECS_CUDA(c, launch_pad_posm(c->posm, re, own_end, c->stream));
+            c->kernel_launches += (re > rb ? 1 : 0) + (own_end > re ? 1 : 0);
+        }
+        c->posm_sources = sources;
+        c->posm_bodies = n_jpad;
+    }
+    if (sharded) {
+        if (!c->comm) return fail(c, RECS_ERR_NCCL, "world_size > 1 but recs_gpu_comm_init was not called");
+        RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));
+        RECS_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
+        float* send = c->posm + (size_t)slice * (uint64_t)c->cfg.rank * 4;
+        int r = c->nccl.AllGather(send, c->posm, (size_t)slice * 4, /*ncclFloat32*/ 7, c->comm, c->comm_stream);
+        if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclAllGather: ") + c->nccl.GetErrorString(r));
+        RECS_CUDA(c, cudaEventRecord(c->ev_gather, c->comm_stream));
+    }
+
+    // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
+    const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm);
+    for (uint32_t a : sys.archs) {
+        Column *p, *acc;
+        if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
+        if ((st = need_column(c, a, ACC, 12, &acc)) != RECS_OK) return st;
+        if ((st = same_count(c, p, acc)) != RECS_OK) return st;
+        uint64_t row_begin = 0, row_count = p->count;
+        if (sharded) {
+            row_begin = rb;
+            row_count = re - rb;
+        }
+        if (row_count == 0) continue;
+        if (row_count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
+        const uint32_t n_iblocks = (uint32_t)((row_count + kGravRows - 1) / kGravRows);
+        if ((uint64_t)n_iblocks * n_tiles >= (1ull << 32))
+            return fail(c, RECS_ERR_UNSUPPORTED, "work-unit count overflows 32 bits");
+
+        GravityReduceArgs ra;
+        memset(&ra, 0, sizeof ra);
+        ra.acc = (float*)acc->dev;
+        ra.row_begin = (uint32_t)row_begin;
+        ra.row_count = (uint32_t)row_count;
+        // launch A: local tiles (all tiles when not sharded); launch B: the other ranks' tiles
+        const uint32_t own_tiles = sharded ? (uint32_t)(slice / kGravTile) : n_tiles;
+        const uint32_t own_off = sharded ? own_tiles * (uint32_t)c->cfg.rank : 0;
+        uint32_t frag_base = 0;
+        for (int l = 0; l < (sharded ? 2 : 1); ++l) {
+            GravityLaunch L;
+            L.n_iblocks = n_iblocks;
+            L.n_vtiles = l == 0 ? own_tiles : n_tiles - own_tiles;
+            L.tile_offset = l == 0 ? own_off : (own_off + own_tiles) % n_tiles;
+            const uint64_t units = (uint64_t)L.n_iblocks * L.n_vtiles;
+            L.grid = (uint32_t)std::min<uint64_t>(slots, std::max<uint64_t>(units, 1));
+            L.frag_base = frag_base;
+            frag_base += gravity_frag_slots(L);
+            ra.launch[l] = L;
+        }
+        ra.n_launches = sharded ? 2 : 1;
+        st = ensure(c, &c->frags, &c->frags_cap, (size_t)frag_base * kGravRows * sizeof(float4));
+        if (st != RECS_OK) return st;
+        ra.frags = c->frags;
+
+        for (uint32_t l = 0; l < ra.n_launches; ++l) {
+            if (l == 1) RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+            GravityArgs ga;
+            ga.posm = reinterpret_cast<const float4*>(c->posm);
+            ga.ipos = (const float*)p->dev;
+            ga.frags = c->frags;
+            ga.row_begin = (uint32_t)row_begin;
+            ga.row_count = (uint32_t)row_count;
+            ga.n_tiles_total = n_tiles;
+            ga.eps = c->cfg.nbody_epsilon;
+            ga.launch = ra.launch[l];
+            if (ga.launch.n_vtiles == 0) continue;
+            Timed t(c, T_GRAVITY);
+            RECS_CUDA(c, launch_gravity(ga, c->stream));
+            c->kernel_launches++;
+            c->gravity_launches++;
+        }
+        {
+            Timed t(c, T_REDUCE);
+            RECS_CUDA(c, launch_gravity_reduce(ra, c->stream));
+            c->kernel_launches++;
+        }
+        acc->version++;
+    }
+    if (sharded && sys.archs.empty()) RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+    return RECS_OK;
+}
+
+// (Write<Y>, Read<X>) with y += x * a over each matched archetype's rows.
+int32_t run_axpy(recs_gpu_ctx* c, System& sys, uint64_t Y, uint64_t X, float a, int slot, bool shard) {
+    for (uint32_t arch : sys.archs) {
+        Column *y, *x;
+        int32_t st;
+        if ((st = need_column(c, arch, Y, 12, &y)) != RECS_OK) return st;
+        if ((st = need_column(c, arch, X, 12, &x)) != RECS_OK) return st;
+        if ((st = same_count(c, y, x)) != RECS_OK) return st;
+        uint64_t rb = 0, re = y->count, slice;
+        if (shard && c->cfg.world_size > 1) shard_rows(c->cfg, y->count, &slice, &rb, &re);
+        if (re == rb) continue;
+        Timed t(c, slot);
+        RECS_CUDA(c, launch_axpy_rn((float*)y->dev + 3 * rb, (const float*)x->dev + 3 * rb, a, 3 * (re - rb),
+                                    c->stream));
+        c->kernel_launches++;
+        y->version++;
+    }
+    return RECS_OK;
+}
+
+void rotate_wind(recs_gpu_ctx* c) {
+    // crates/rain-simulation/src/lib.rs:78-84 with cgmath 0.18 semantics:
+    // Quaternion::from_axis_angle(unit_y, Deg(10) * dt).rotate_vector(dir)
+    const float deg = c->cfg.rain_wind_deg_per_s * c->cfg.rain_dt;
+    const float rad = deg * (float)(3.14159265358979323846 / 180.0);
+    const float half = rad * 0.5f;
+    const float s = sinf(half), qs = cosf(half);
+    const float qv[3] = {0.f * s, 1.f * s, 0.f * s};
+    const float* v = c->wind;
+    // tmp = qv x v + v * qs
+    const float t[3] = {(qv[1] * v[2] - qv[2] * v[1]) + v[0] * qs, (qv[2] * v[0] - qv[0] * v[2]) + v[1] * qs,
+                        (qv[0] * v[1] - qv[1] * v[0]) + v[2] * qs};
+    // (qv x tmp) * 2 + v
+    const float r[3] = {(qv[1] * t[2] - qv[2] * t[1]) * 2.f + v[0], (qv[2] * t[0] - qv[0] * t[2]) * 2.f + v[1],
+                        (qv[0] * t[1] - qv[1] * t[0]) * 2.f + v[2]};
+    c->wind[0] = r[0];
+    c->wind[1] = r[1];
+    c->wind[2] = r[2];
+}
+
+int32_t run_rain_vel(recs_gpu_ctx* c, System& sys, bool wind) {
+    const float k_gravity = (-c->cfg.rain_gravity) * c->cfg.rain_dt;
+    const float cw = c->cfg.rain_wind_accel * c->cfg.rain_dt;
+    for (uint32_t arch : sys.archs) {
+        Column* v;
+        int32_t st;
+        if ((st = need_column(c, arch, sys.comp[0], 12, &v)) != RECS_OK) return st;
+        if (v->count == 0) continue;
+        Timed t(c, T_OTHER);
+        if (wind)
+            RECS_CUDA(c, launch_rain_wind((float*)v->dev, v->count, cw * c->wind[0], cw * c->wind[1],
+                                          cw * c->wind[2], c->cfg.rain_terminal, c->stream));
+        else
+            RECS_CUDA(c, launch_rain_gravity((float*)v->dev, v->count, k_gravity, c->cfg.rain_terminal, c->stream));
+        c->kernel_launches++;
+        v->version++;
+    }
+    return RECS_OK;
+}
+
+int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
+    if (id >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system id");
+    System& s = c->systems[id];
+    switch (s.kind) {
+        case RECS_SYS_NBODY_GRAVITY:
+            return run_gravity(c, s);
+        case RECS_SYS_NBODY_MOVEMENT:
+            return run_axpy(c, s, s.comp[0], s.comp[1], c->cfg.nbody_dt, T_MOVEMENT, true);
+        case RECS_SYS_NBODY_ACCELERATION:
+            return run_axpy(c, s, s.comp[0], s.comp[1], c->cfg.nbody_dt, T_ACCEL, true);
+        case RECS_SYS_RAIN_GRAVITY:
+            return run_rain_vel(c, s, false);
+        case RECS_SYS_RAIN_WIND:
+            return run_rain_vel(c, s, true);
+        case RECS_SYS_RAIN_MOVEMENT:
+            return run_axpy(c, s, s.comp[0], s.comp[1], c->cfg.rain_dt, T_OTHER, false);
+        case RECS_SYS_RAIN_WIND_DIRECTION:
+            if (c->capturing) return fail(c, RECS_ERR_UNSUPPORTED, "wind_direction inside a captured tick");
+            rotate_wind(c);
+            return RECS_OK;
+        case RECS_SYS_QUERY_ADD:
+            return run_axpy(c, s, s.comp[0], s.comp[1], 1.0f, T_OTHER, false);
+    }
+    return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system kind");
+}
+
+// wind -> gravity -> movement adjacent in the tick order and over the same archetypes: one pass.
+bool try_fused_rain(recs_gpu_ctx* c, size_t i, int32_t* st) {
+    if (i + 2 >= c->order.size()) return false;
+    System& w = c->systems[c->order[i]];
+    System& g = c->systems[c->order[i + 1]];
+    System& m = c->systems[c->order[i + 2]];
+    if (w.kind != RECS_SYS_RAIN_WIND || g.kind != RECS_SYS_RAIN_GRAVITY || m.kind != RECS_SYS_RAIN_MOVEMENT)
+        return false;
+    if (w.archs != g.archs || w.archs != m.archs) return false;
+    if (w.comp[0] != g.comp[0] || w.comp[0] != m.comp[1]) return false;
+    const float k_gravity = (-c->cfg.rain_gravity) * c->cfg.rain_dt;
+    const float cw = c->cfg.rain_wind_accel * c->cfg.rain_dt;
+    *st = RECS_OK;
+    for (uint32_t arch : w.archs) {
+        Column *v, *p;
+        if ((*st = need_column(c, arch, w.comp[0], 12, &v)) != RECS_OK) return true;
+        if ((*st = need_column(c, arch, m.comp[0], 12, &p)) != RECS_OK) return true;
+        if ((*st = same_count(c, v, p)) != RECS_OK) return true;
+        if (v->count == 0) continue;
+        Timed t(c, T_OTHER);
+        cudaError_t e = launch_rain_fused((float*)v->dev, (float*)p->dev, v->count, cw * c->wind[0], cw * c->wind[1],
+                                          cw * c->wind[2], k_gravity, c->cfg.rain_terminal, c->cfg.rain_dt, c->stream);
+        if (e != cudaSuccess) {
+            *st = fail(c, RECS_ERR_CUDA, cudaGetErrorString(e));
+            return true;
+        }
+        c->kernel_launches++;
+        v->version++;
+        p->version++;
+    }
+    return true;
+}
+
+int32_t run_tick_once(recs_gpu_ctx* c) {
+    for (size_t i = 0; i < c->order.size(); ++i) {
+        int32_t st = RECS_OK;
+        if (try_fused_rain(c, i, &st)) {
+            if (st != RECS_OK) return st;
+            i += 2;
+            continue;
+        }
+        st = run_system_locked(c, c->order[i]);
+        if (st != RECS_OK) return st;
+    }
+    return RECS_OK;
+}
+
+bool order_is_capturable(recs_gpu_ctx* c) {
+    for (uint32_t id : c->order)
+        if (c->systems[id].kind == RECS_SYS_RAIN_WIND_DIRECTION || c->systems[id].kind == RECS_SYS_RAIN_WIND)
+            return false;  // wind direction is a host-side per-tick value
+    return true;
+}
+
+void drop_graph(recs_gpu_ctx* c) {
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    c->graph = nullptr;
+    c->graph_epoch = ~0ull;
+}
+
+void fill_system(System& s, recs_gpu_system_kind kind, const uint64_t* ids) {
+    auto acc = [&](uint64_t comp, bool w) {
+        recs_gpu_access a;
+        a.component_id = comp;
+        a.is_write = w ? 1 : 0;
+        s.access.push_back(a);
+    };
+    s.kind = kind;
+    switch (kind) {
+        case RECS_SYS_NBODY_GRAVITY:  // (Read<Position>, Write<Acceleration>, Query<(Read<Position>, Read<Mass>)>)
+            s.name = "gravity";
+            s.n_comp = 3;
+            acc(ids[0], false);
+            acc(ids[1], true);
+            acc(ids[0], false);
+            acc(ids[2], false);
+            break;
+        case RECS_SYS_NBODY_MOVEMENT:  // (Write<Position>, Read<Velocity>)
+        case RECS_SYS_RAIN_MOVEMENT:
+            s.name = "movement";
+            s.n_comp = 2;
+            acc(ids[0], true);
+            acc(ids[1], false);
+            break;
+        case RECS_SYS_NBODY_ACCELERATION:  // (Write<Velocity>, Read<Acceleration>)
+            s.name = "acceleration";
+            s.n_comp = 2;
+            acc(ids[0], true);
+            acc(ids[1], false);
+            break;
+        case RECS_SYS_RAIN_GRAVITY:  // (Write<Velocity>)
+            s.name = "gravity";
+            s.n_comp = 1;
+            acc(ids[0], true);
+            break;
+        case RECS_SYS_RAIN_WIND:
+            s.name = "wind";
+            s.n_comp = 1;
+            acc(ids[0], true);
+            break;
+        case RECS_SYS_RAIN_WIND_DIRECTION:
+            s.name = "wind_direction";
+            s.n_comp = 0;
+            break;
+        case RECS_SYS_QUERY_ADD:
+            s.name = "query_add";
+            s.n_comp = 2;
+            acc(ids[0], true);
+            acc(ids[1], false);
+            break;
+    }
+    for (uint32_t i = 0; i < s.n_comp; ++i) s.comp[i] = ids[i];
+}
+
+uint32_t kind_components(int kind) {
+    switch (kind) {
+        case RECS_SYS_NBODY_GRAVITY:
+            return 3;
+        case RECS_SYS_NBODY_MOVEMENT:
+        case RECS_SYS_NBODY_ACCELERATION:
+        case RECS_SYS_RAIN_MOVEMENT:
+        case RECS_SYS_QUERY_ADD:
+            return 2;
+        case RECS_SYS_RAIN_GRAVITY:
+        case RECS_SYS_RAIN_WIND:
+            return 1;
+        case RECS_SYS_RAIN_WIND_DIRECTION:
+            return 0;
+    }
+    return ~0u;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int32_t recs_gpu_abi_version(void) { return RECS_GPU_ABI_VERSION; }
+
+void recs_gpu_default_config(recs_gpu_config* cfg) {
+    if (!cfg) return;
+    memset(cfg, 0, sizeof *cfg);
+    cfg->device = 0;
+    cfg->rank = 0;
+    cfg->world_size = 1;
+    cfg->use_cuda_graph = 1;
+    cfg->nbody_dt = 1.0f / 20000.0f;     // crates/n-body/src/lib.rs:14
+    cfg->nbody_g = 6.67e-11f;            // :123
+    cfg->nbody_epsilon = 1.1920929e-7f;  // f32::EPSILON, :118
+    cfg->rain_dt = 1.0f / 20.0f;         // crates/rain-simulation/src/lib.rs:15
+    cfg->rain_gravity = 9.82f;           // :59
+    cfg->rain_terminal = 9.0f;           // :60
+    cfg->rain_wind_accel = 10.0f;        // :72
+    cfg->rain_wind_deg_per_s = 10.0f;    // :76
+}
+
+int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
+    if (!cfg || !out_ctx) return RECS_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return RECS_ERR_INVALID_ARGUMENT;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return RECS_ERR_NO_DEVICE;
+    if (cfg->device < 0 || cfg->device >= n_dev) return RECS_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(cfg->device) != cudaSuccess) return RECS_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return RECS_ERR_CUDA;
+    if (prop.major != 10) {
+        fprintf(stderr, "recs_gpu: device %d is sm_%d%d; this library is built for sm_100a only\n", cfg->device,
+                prop.major, prop.minor);
+        return RECS_ERR_NO_DEVICE;
+    }
+    recs_gpu_ctx* c = new recs_gpu_ctx();
+    c->cfg = *cfg;
+    c->sm_count = prop.multiProcessorCount;
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_pack, cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming) == cudaSuccess &&
+              gravity_prepare() == cudaSuccess;
+    if (ok) {
+        c->grav_ctas_per_sm = gravity_max_ctas_per_sm();
+        ok = c->grav_ctas_per_sm > 0;
+    }
+    if (!ok) {
+        fprintf(stderr, "recs_gpu: context creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+        delete c;
+        return RECS_ERR_CUDA;
+    }
+    *out_ctx = c;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
+    if (!c) return RECS_ERR_INVALID_ARGUMENT;
+    {
+        std::lock_guard<std::mutex> lock(c->mu);
+        cudaSetDevice(c->cfg.device);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->comm_stream);
+        if (c->comm) c->nccl.CommDestroy(c->comm);
+        drop_graph(c);
+        for (auto& kv : c->columns)
+            if (kv.second.dev) cudaFree(kv.second.dev);
+        if (c->posm) cudaFree(c->posm);
+        if (c->frags) cudaFree(c->frags);
+        if (c->l2_flush) cudaFree(c->l2_flush);
+        for (auto& s : c->spans) {
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        for (auto e : c->event_pool) cudaEventDestroy(e);
+        cudaEventDestroy(c->ev_pack);
+        cudaEventDestroy(c->ev_gather);
+        cudaStreamDestroy(c->stream);
+        cudaStreamDestroy(c->comm_stream);
+    }
+    delete c;
+    return RECS_OK;
+}
+
+const char* recs_gpu_last_error(recs_gpu_ctx* c) {
+    if (!c) return "null context";
+    std::lock_guard<std::mutex> lock(c->mu);
+    return c->error.c_str();
+}
+
+int32_t recs_gpu_clear_error(recs_gpu_ctx* c) {
+    if (!c) return RECS_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    c->status = RECS_OK;
+    c->error.clear();
+    cudaGetLastError();
+    return RECS_OK;
+}
+
+int32_t recs_gpu_synchronize(recs_gpu_ctx* c) {
+    RECS_ENTER(c);
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    RECS_CUDA(c, cudaStreamSynchronize(c->comm_stream));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_bind_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void* host_ptr, uint32_t elem,
+                             uint64_t count) {
+    RECS_ENTER(c);
+    if (elem == 0 || (count > 0 && !host_ptr)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "bind_column: null host pointer or zero element size");
+    Column& col = c->columns[ColKey(arch, comp)];
+    const size_t bytes = std::max<size_t>((size_t)elem * count, 16);
+    if (col.cap < bytes || !col.dev) {
+        // wait for in-flight work before releasing the old buffer
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (col.dev) RECS_CUDA(c, cudaFree(col.dev));
+        col.dev = nullptr;
+        col.cap = 0;
+        // round capacity up so growing archetypes do not reallocate every tick
+        size_t cap = 256;
+        while (cap < bytes) cap <<= 1;
+        if (cap > bytes + (64u << 20)) cap = (bytes + (64u << 20) - 1) / (64u << 20) * (64u << 20);
+        RECS_CUDA(c, cudaMalloc(&col.dev, cap));
+        col.cap = cap;
+    }
+    col.host = host_ptr;
+    col.elem = elem;
+    col.count = count;
+    col.stale = false;
+    col.version++;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_upload(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "upload: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "upload: column binding is stale");
+    if (col->count)
+        RECS_CUDA(c, cudaMemcpyAsync(col->dev, col->host, (size_t)col->elem * col->count, cudaMemcpyHostToDevice,
+                                     c->stream));
+    col->version++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_download(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "download: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "download: column binding is stale");
+    if (col->count)
+        RECS_CUDA(c, cudaMemcpyAsync(col->host, col->dev, (size_t)col->elem * col->count, cudaMemcpyDeviceToHost,
+                                     c->stream));
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_invalidate(recs_gpu_ctx* c, uint32_t arch) {
+    RECS_ENTER(c);
+    for (auto& kv : c->columns)
+        if (kv.first.first == arch) kv.second.stale = true;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_column_device_ptr(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void** out_ptr, uint64_t* out_count) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev || !out_ptr) return fail(c, RECS_ERR_MISSING_PARAMETER, "column_device_ptr: column is not bound");
+    *out_ptr = col->dev;
+    if (out_count) *out_count = col->count;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_create(recs_gpu_ctx* c, recs_gpu_system_kind kind, const uint64_t* ids, uint32_t n_ids,
+                               uint32_t* out_id) {
+    RECS_ENTER(c);
+    const uint32_t need = kind_components((int)kind);
+    if (need == ~0u) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create: unknown system kind");
+    if (n_ids != need || (need && !ids) || !out_id)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create: wrong number of component ids for this kind");
+    System s;
+    uint64_t none[3] = {0, 0, 0};
+    fill_system(s, kind, need ? ids : none);
+    c->systems.push_back(s);
+    *out_id = (uint32_t)c->systems.size() - 1;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_describe(recs_gpu_ctx* c, uint32_t id, recs_gpu_system_desc* out) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || !out) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_describe: unknown system id");
+    const System& s = c->systems[id];
+    out->name = s.name.c_str();
+    out->n_access = (uint32_t)s.access.size();
+    for (size_t i = 0; i < s.access.size(); ++i) out->access[i] = s.access[i];
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_set_archetypes(recs_gpu_ctx* c, uint32_t id, const uint32_t* archs, uint32_t n) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || (n && !archs)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_archetypes: bad argument");
+    c->systems[id].archs.assign(archs, archs + n);
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* c, uint32_t id, const uint32_t* archs, uint32_t n) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || (n && !archs)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_query_archetypes: bad argument");
+    c->systems[id].qarchs.assign(archs, archs + n);
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_run_system(recs_gpu_ctx* c, uint32_t id, uint32_t flags) {
+    RECS_ENTER(c);
+    int32_t st = run_system_locked(c, id);
+    if (st != RECS_OK) return st;
+    if (flags & RECS_GPU_SYNC) RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_set_tick_order(recs_gpu_ctx* c, const uint32_t* ids, uint32_t n) {
+    RECS_ENTER(c);
+    for (uint32_t i = 0; i < n; ++i)
+        if (!ids || ids[i] >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "set_tick_order: unknown system id");
+    c->order.assign(ids, ids + n);
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
+    RECS_ENTER(c);
+    if (n_ticks == 0 || c->order.empty()) return RECS_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (c->timing) {
+        e0 = get_event(c);
+        e1 = get_event(c);
+        cudaEventRecord(e0, c->stream);
+    }
+    const bool want_graph = c->cfg.use_cuda_graph && c->cfg.world_size == 1 && !c->timing && order_is_capturable(c);
+    uint32_t done = 0;
+    if (want_graph && n_ticks > 1) {
+        if (!c->graph || c->graph_epoch != c->epoch) {
+            drop_graph(c);
+            // one eager tick sizes every workspace, then the same chain is captured
+            int32_t st = run_tick_once(c);
+            if (st != RECS_OK) return st;
+            done = 1;
+            const uint64_t epoch = c->epoch;
+            cudaGraph_t g = nullptr;
+            RECS_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+            c->capturing = true;
+            st = run_tick_once(c);
+            c->capturing = false;
+            cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
+            if (st != RECS_OK) {
+                if (g) cudaGraphDestroy(g);
+                return st;
+            }
+            RECS_CUDA(c, ce);
+            ce = cudaGraphInstantiate(&c->graph, g, 0);
+            cudaGraphDestroy(g);
+            RECS_CUDA(c, ce);
+            c->graph_epoch = epoch;
+        }
+        for (; done < n_ticks; ++done) RECS_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
+    }
+    for (; done < n_ticks; ++done) {
+        int32_t st = run_tick_once(c);
+        if (st != RECS_OK) return st;
+    }
+    if (c->timing) {
+        cudaEventRecord(e1, c->stream);
+        TimedSpan s;
+        s.a = e0;
+        s.b = e1;
+        s.slot = T_CHAIN;
+        c->spans.push_back(s);
+    }
+    return RECS_OK;
+}
+
+int32_t recs_gpu_set_wind_direction(recs_gpu_ctx* c, const float xyz[3]) {
+    RECS_ENTER(c);
+    if (!xyz) return fail(c, RECS_ERR_INVALID_ARGUMENT, "set_wind_direction: null");
+    memcpy(c->wind, xyz, sizeof c->wind);
+    return RECS_OK;
+}
+int32_t recs_gpu_get_wind_direction(recs_gpu_ctx* c, float xyz[3]) {
+    RECS_ENTER(c);
+    if (!xyz) return fail(c, RECS_ERR_INVALID_ARGUMENT, "get_wind_direction: null");
+    memcpy(xyz, c->wind, sizeof c->wind);
+    return RECS_OK;
+}
+
+int32_t recs_gpu_comm_get_unique_id(recs_gpu_ctx* c, uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]) {
+    RECS_ENTER(c);
+    const char* why = "";
+    if (!c->nccl.load(&why)) return fail(c, RECS_ERR_NCCL, why);
+    NcclApi::unique_id id;
+    int r = c->nccl.GetUniqueId(&id);
+    if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclGetUniqueId: ") + c->nccl.GetErrorString(r));
+    memcpy(id_bytes, id.internal, RECS_GPU_NCCL_ID_BYTES);
+    return RECS_OK;
+}
+
+int32_t recs_gpu_comm_init(recs_gpu_ctx* c, const uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]) {
+    RECS_ENTER(c);
+    const char* why = "";
+    if (!c->nccl.load(&why)) return fail(c, RECS_ERR_NCCL, why);
+    if (c->comm) return fail(c, RECS_ERR_NCCL, "communicator already initialised");
+    NcclApi::unique_id id;
+    memcpy(id.internal, id_bytes, RECS_GPU_NCCL_ID_BYTES);
+    int r = c->nccl.CommInitRank(&c->comm, c->cfg.world_size, id, c->cfg.rank);
+    if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_shard_rows(recs_gpu_ctx* c, uint64_t n_rows, uint64_t* row_begin, uint64_t* row_end) {
+    if (!c || !row_begin || !row_end) return RECS_ERR_INVALID_ARGUMENT;
+    uint64_t slice;
+    shard_rows(c->cfg, n_rows, &slice, row_begin, row_end);
+    return RECS_OK;
+}
+
+int32_t recs_gpu_enable_timing(recs_gpu_ctx* c, int32_t enabled) {
+    RECS_ENTER(c);
+    c->timing = enabled != 0;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_get_timing(recs_gpu_ctx* c, recs_gpu_timing* out) {
+    RECS_ENTER(c);
+    if (!out) return fail(c, RECS_ERR_INVALID_ARGUMENT, "get_timing: null");
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    float acc[T_COUNT] = {0};
+    for (auto& s : c->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+            if (s.slot == T_CHAIN)
+                acc[T_CHAIN] = ms;  // last chain
+            else
+                acc[s.slot] += ms;
+        }
+    }
+    memset(out, 0, sizeof *out);
+    out->last_tick_chain_ms = acc[T_CHAIN];
+    out->gravity_ms = acc[T_GRAVITY];
+    out->gravity_reduce_ms = acc[T_REDUCE];
+    out->movement_ms = acc[T_MOVEMENT];
+    out->acceleration_ms = acc[T_ACCEL];
+    out->pack_ms = acc[T_PACK];
+    out->other_ms = acc[T_OTHER];
+    out->kernel_launches = c->kernel_launches;
+    out->gravity_launches = c->gravity_launches;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_reset_timing(recs_gpu_ctx* c) {
+    RECS_ENTER(c);
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (auto& s : c->spans) {
+        c->event_pool.push_back(s.a);
+        c->event_pool.push_back(s.b);
+    }
+    c->spans.clear();
+    c->kernel_launches = 0;
+    c->gravity_launches = 0;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* c, int32_t packed, float* out_tflops, float* out_sm_mhz) {
+    RECS_ENTER(c);
+    if (!out_tflops || !out_sm_mhz) return fail(c, RECS_ERR_INVALID_ARGUMENT, "measure_fp32_peak: null");
+    const uint32_t grid = (uint32_t)c->sm_count * 8;  // 8 CTAs x 256 threads = full occupancy
+    const uint32_t iters = 4096;
+    float* sink = nullptr;
+    unsigned long long* cycles = nullptr;
+    RECS_CUDA(c, cudaMalloc((void**)&sink, 16));
+    RECS_CUDA(c, cudaMalloc((void**)&cycles, grid * sizeof(unsigned long long)));
+    cudaEvent_t a = get_event(c), b = get_event(c);
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, c->stream);
+        cudaError_t e = launch_fp32_peak(packed, iters, grid, sink, cycles, c->stream);
+        cudaEventRecord(b, c->stream);
+        if (e != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+            cudaFree(sink);
+            cudaFree(cycles);
+            return fail(c, RECS_ERR_CUDA, "fp32 peak kernel failed");
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best_ms) best_ms = ms;
+        c->kernel_launches++;
+    }
+    std::vector<unsigned long long> h(grid);
+    cudaMemcpy(h.data(), cycles, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long cyc_max = 0;
+    for (auto v : h) cyc_max = std::max(cyc_max, v);
+    // FMAs: grid * 256 threads * iters * 4 * (12 packed x 2 | 24 scalar)
+    const double fmas = (double)grid * 256.0 * iters * 4.0 * 24.0;
+    *out_tflops = (float)(2.0 * fmas / (best_ms * 1e-3) / 1e12);
+    *out_sm_mhz = (float)((double)cyc_max / (best_ms * 1e-3) / 1e6);
+    c->event_pool.push_back(a);
+    c->event_pool.push_back(b);
+    cudaFree(sink);
+    cudaFree(cycles);
+    return RECS_OK;
+}
+
+int32_t recs_gpu_flush_l2(recs_gpu_ctx* c) {
+    RECS_ENTER(c);
+    const size_t bytes = 256u << 20;  // > 126 MB L2
+    int32_t st = ensure(c, &c->l2_flush, &c->l2_flush_bytes, bytes);
+    if (st != RECS_OK) return st;
+    RECS_CUDA(c, launch_fill(c->l2_flush, bytes / 4, 0.f, c->stream));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_host_alloc(recs_gpu_ctx* c, size_t bytes, void** out_ptr) {
+    RECS_ENTER(c);
+    if (!out_ptr) return fail(c, RECS_ERR_INVALID_ARGUMENT, "host_alloc: null");
+    RECS_CUDA(c, cudaHostAlloc(out_ptr, bytes ? bytes : 16, cudaHostAllocDefault));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_host_free(recs_gpu_ctx* c, void* ptr) {
+    RECS_ENTER(c);
+    if (ptr) RECS_CUDA(c, cudaFreeHost(ptr));
+    return RECS_OK;
+}
+
+}  // extern "C"

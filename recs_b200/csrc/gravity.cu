@@ -1,0 +1,291 @@
+// All-pairs gravity for sm_100a -- the device body of recs' `gravity` system
+// (crates/n-body/src/lib.rs:104-135):
+//
+//   for each body i:  acc_i = sum_j  to_body * ((G*m_j / d2) / sqrt(d2)),   to_body = p_j - p_i,
+//                     d2 = |to_body|^2, pairs with d2 <= f32::EPSILON contribute zero (this is
+//                     what removes j == i).
+//
+// Design (B200-first, not a translation of the scalar Rust loop):
+//   * FP32-FMA-pipe bound, no tensor cores (not a contraction).  Two j bodies are packed into
+//     one f32x2 register pair so the whole pair interaction is FADD2/FMUL2/FFMA2: 12 FMA-pipe
+//     instructions per TWO interactions instead of 24, which leaves issue slots for the two
+//     MUFU.RSQ, the two FSETP/FSEL (epsilon mask) and the LDS.128 tile reads.
+//   * j tiles live in HBM already pair-interleaved ({x0 x1 y0 y1 | z0 z1 gm0 gm1}, 32 B per
+//     pair), so a tile is one contiguous 4 KiB block: a single elected thread of a producer
+//     warp moves it with a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) into a 4-stage
+//     shared-memory ring guarded by full/empty mbarriers.  Consumers read tiles with uniform
+//     (broadcast) LDS.128.
+//   * each consumer thread keeps 4 bodies i in registers (register blocking), so one LDS pair
+//     feeds 8 interactions.
+//   * stream-K work split: the (i-block, j-tile) units of a launch are cut into equal
+//     contiguous spans, one per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies
+//     (64 i-blocks) load all 148 SMs as evenly as 1 M bodies do.  A CTA writes one partial
+//     ("fragment") per i-block it touched; a tiny second kernel adds the fragments of each
+//     i-block in ascending j order -- deterministic, no float atomics.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace recs {
+
+using ptx::f32x2;
+
+namespace {
+
+struct Span {
+    uint32_t begin;
+    uint32_t count;
+};
+
+// Unit span of CTA c when `units` are dealt to `grid` CTAs as evenly as possible.
+__host__ __device__ inline Span span_of(uint32_t c, uint32_t grid, uint32_t units) {
+    const uint32_t q = units / grid, rem = units % grid;
+    Span s;
+    s.begin = c * q + (c < rem ? c : rem);
+    s.count = q + (c < rem ? 1u : 0u);
+    return s;
+}
+// Inverse: which CTA owns unit u.
+__host__ __device__ inline uint32_t cta_of(uint32_t u, uint32_t grid, uint32_t units) {
+    const uint32_t q = units / grid, rem = units % grid;
+    const uint32_t big = rem * (q + 1);
+    if (u < big) return u / (q + 1);
+    return rem + (u - big) / q;
+}
+
+__global__ void __launch_bounds__(kGravThreads, 2) nbody_gravity_kernel(const GravityArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* tiles = reinterpret_cast<float4*>(smem_raw);
+    __shared__ __align__(8) uint64_t full_bar[kGravStages];
+    __shared__ __align__(8) uint64_t empty_bar[kGravStages];
+
+    const uint32_t n_vtiles = a.launch.n_vtiles;
+    const uint32_t units = a.launch.n_iblocks * n_vtiles;
+    const Span span = span_of(blockIdx.x, gridDim.x, units);
+    if (span.count == 0) return;
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kGravStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&empty_bar[s], kGravConsumerWarps);
+        }
+        ptx::mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == kGravConsumerWarps) {
+        // ---- TMA producer: one thread streams this CTA's tiles through the ring --------------
+        if (lane == 0) {
+            uint32_t v = span.begin % n_vtiles;
+            for (uint32_t k = 0; k < span.count; ++k) {
+                const uint32_t stage = k % kGravStages;
+                const uint32_t phase = (k / kGravStages) & 1u;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                uint32_t tile = v + a.launch.tile_offset;
+                if (tile >= a.n_tiles_total) tile -= a.n_tiles_total;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], kGravTileBytes);
+                ptx::bulk_g2s(tiles + stage * kGravTile, a.posm + static_cast<size_t>(tile) * kGravTile,
+                              kGravTileBytes, &full_bar[stage]);
+                if (++v == n_vtiles) v = 0;
+            }
+        }
+        return;
+    }
+
+    // ---- consumers ---------------------------------------------------------------------------
+    const uint32_t tid = threadIdx.x;  // 0..255
+    uint32_t b = span.begin / n_vtiles;
+    uint32_t v = span.begin % n_vtiles;
+
+    float nxi[kGravRowsPerThread], nyi[kGravRowsPerThread], nzi[kGravRowsPerThread];
+    f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
+
+    auto load_rows = [&](uint32_t iblock) {
+#pragma unroll
+        for (int r = 0; r < kGravRowsPerThread; ++r) {
+            const uint32_t local = iblock * kGravRows + r * kGravConsumerThreads + tid;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (local < a.row_count) {
+                const float* p = a.ipos + 3ull * (a.row_begin + local);
+                x = __ldg(p + 0);
+                y = __ldg(p + 1);
+                z = __ldg(p + 2);
+            }
+            nxi[r] = -x;
+            nyi[r] = -y;
+            nzi[r] = -z;
+            ax[r] = 0ull;
+            ay[r] = 0ull;
+            az[r] = 0ull;
+        }
+    };
+    auto flush = [&](uint32_t iblock) {
+        float4* dst = a.frags + static_cast<size_t>(a.launch.frag_base + blockIdx.x + iblock) * kGravRows;
+#pragma unroll
+        for (int r = 0; r < kGravRowsPerThread; ++r) {
+            float x0, x1, y0, y1, z0, z1;
+            ptx::unpack(ax[r], x0, x1);
+            ptx::unpack(ay[r], y0, y1);
+            ptx::unpack(az[r], z0, z1);
+            dst[r * kGravConsumerThreads + tid] = make_float4(x0 + x1, y0 + y1, z0 + z1, 0.f);
+        }
+    };
+
+    load_rows(b);
+    const float eps = a.eps;
+
+    for (uint32_t k = 0; k < span.count; ++k) {
+        const uint32_t stage = k % kGravStages;
+        const uint32_t phase = (k / kGravStages) & 1u;
+        ptx::mbar_wait(&full_bar[stage], phase);
+        const float4* t = tiles + stage * kGravTile;
+
+#pragma unroll 2
+        for (int p = 0; p < kGravTile / 2; ++p) {
+            const float4 lo = t[2 * p];      // x0 x1 y0 y1
+            const float4 hi = t[2 * p + 1];  // z0 z1 gm0 gm1
+            const f32x2 xj = ptx::pack(lo.x, lo.y);
+            const f32x2 yj = ptx::pack(lo.z, lo.w);
+            const f32x2 zj = ptx::pack(hi.x, hi.y);
+            const f32x2 gm = ptx::pack(hi.z, hi.w);
+#pragma unroll
+            for (int r = 0; r < kGravRowsPerThread; ++r) {
+                const f32x2 dx = ptx::add2(xj, ptx::pack(nxi[r], nxi[r]));
+                const f32x2 dy = ptx::add2(yj, ptx::pack(nyi[r], nyi[r]));
+                const f32x2 dz = ptx::add2(zj, ptx::pack(nzi[r], nzi[r]));
+                f32x2 d2 = ptx::mul2(dx, dx);
+                d2 = ptx::fma2(dy, dy, d2);
+                d2 = ptx::fma2(dz, dz, d2);
+                float d2a, d2b;
+                ptx::unpack(d2, d2a, d2b);
+                float ra = ptx::rsqrt_approx(d2a);
+                float rb = ptx::rsqrt_approx(d2b);
+                // `if distance_squared <= f32::EPSILON { return zero }` (lib.rs:118-120); also
+                // turns rsqrt(0) = inf of the self pair into an exact zero contribution.
+                ra = d2a > eps ? ra : 0.f;
+                rb = d2b > eps ? rb : 0.f;
+                const f32x2 rinv = ptx::pack(ra, rb);
+                const f32x2 rinv2 = ptx::mul2(rinv, rinv);
+                f32x2 s = ptx::mul2(gm, rinv);
+                s = ptx::mul2(s, rinv2);  // G*m / d2 / sqrt(d2)
+                ax[r] = ptx::fma2(s, dx, ax[r]);
+                ay[r] = ptx::fma2(s, dy, ay[r]);
+                az[r] = ptx::fma2(s, dz, az[r]);
+            }
+        }
+
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+
+        if (++v == n_vtiles) {
+            v = 0;
+            flush(b);
+            ++b;
+            if (k + 1 < span.count) load_rows(b);
+        }
+    }
+    if (v != 0) flush(b);
+}
+
+__global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.row_count) return;
+    const uint32_t b = i / kGravRows;
+    const uint32_t idx = i % kGravRows;
+    // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
+    float sx = 0.f, sy = 0.f, sz = 0.f;
+    for (uint32_t l = 0; l < a.n_launches; ++l) {
+        const GravityLaunch& L = a.launch[l];
+        if (L.n_vtiles == 0) continue;
+        const uint32_t units = L.n_iblocks * L.n_vtiles;
+        const uint32_t u_lo = b * L.n_vtiles;
+        const uint32_t u_hi = u_lo + L.n_vtiles - 1;
+        const uint32_t c_lo = cta_of(u_lo, L.grid, units);
+        const uint32_t c_hi = cta_of(u_hi, L.grid, units);
+        for (uint32_t c = c_lo; c <= c_hi; ++c) {
+            const float4 f = a.frags[static_cast<size_t>(L.frag_base + c + b) * kGravRows + idx];
+            sx += f.x;
+            sy += f.y;
+            sz += f.z;
+        }
+    }
+    float* out = a.acc + 3ull * (a.row_begin + i);
+    out[0] = sx;
+    out[1] = sy;
+    out[2] = sz;
+}
+
+__global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict__ pos,
+                                                        const float* __restrict__ mass, float g,
+                                                        float* __restrict__ posm, uint64_t row_begin,
+                                                        uint64_t n, uint64_t dst_offset) {
+    const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t row = row_begin + k;
+    const uint64_t J = dst_offset + k;
+    float* d = posm + (J >> 1) * 8 + (J & 1);
+    d[0] = pos[3 * row + 0];
+    d[2] = pos[3 * row + 1];
+    d[4] = pos[3 * row + 2];
+    d[6] = __fmul_rn(g, mass[row]);
+}
+
+__global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm, uint64_t begin,
+                                                       uint64_t end) {
+    const uint64_t J = begin + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (J >= end) return;
+    float* d = posm + (J >> 1) * 8 + (J & 1);
+    d[0] = 0.f;
+    d[2] = 0.f;
+    d[4] = 0.f;
+    d[6] = 0.f;
+}
+
+}  // namespace
+
+cudaError_t gravity_prepare() {
+    return cudaFuncSetAttribute(nbody_gravity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                kGravSmemBytes);
+}
+
+int gravity_max_ctas_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, nbody_gravity_kernel, kGravThreads,
+                                                      kGravSmemBytes) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s) {
+    if (a.launch.n_vtiles == 0 || a.launch.n_iblocks == 0) return cudaSuccess;
+    nbody_gravity_kernel<<<a.launch.grid, kGravThreads, kGravSmemBytes, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s) {
+    if (a.row_count == 0) return cudaSuccess;
+    const uint32_t grid = (a.row_count + 255) / 256;
+    nbody_gravity_reduce_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
+                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t grid = (n + 255) / 256;
+    pack_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(pos, mass, g, posm, row_begin, n,
+                                                                dst_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s) {
+    if (end <= begin) return cudaSuccess;
+    const uint64_t grid = (end - begin + 255) / 256;
+    pad_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(posm, begin, end);
+    return cudaGetLastError();
+}
+
+}  // namespace recs

@@ -1,0 +1,90 @@
+// Internal C++ interface between the context (context.cu) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace recs {
+
+// ---- gravity (crates/n-body/src/lib.rs:104-135) ------------------------------------------------
+constexpr int kGravConsumerWarps = 8;
+constexpr int kGravConsumerThreads = 32 * kGravConsumerWarps;  // 256
+constexpr int kGravThreads = kGravConsumerThreads + 32;        // + 1 TMA producer warp
+constexpr int kGravRowsPerThread = 4;                          // register blocking over i
+constexpr int kGravRows = kGravConsumerThreads * kGravRowsPerThread;  // rows per i-block (1024)
+constexpr int kGravTile = 256;                                 // j bodies per smem tile
+constexpr int kGravStages = 4;
+constexpr int kGravTileBytes = kGravTile * 16;                 // 4 KiB
+constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic smem
+
+// One launch of the interaction kernel: rows [row_begin, row_begin+row_count) of the outer
+// Position column against j tiles [tile_offset, tile_offset + n_vtiles) (mod n_tiles_total).
+struct GravityLaunch {
+    uint32_t grid;        // persistent CTAs (stream-K workers)
+    uint32_t n_iblocks;   // ceil(row_count / kGravRows)
+    uint32_t n_vtiles;    // tiles visited by this launch
+    uint32_t tile_offset; // first tile visited
+    uint32_t frag_base;   // first fragment slot of this launch
+};
+
+struct GravityArgs {
+    const float4* posm;   // pair-interleaved {x0 x1 y0 y1 | z0 z1 gm0 gm1}, n_tiles_total tiles
+    const float* ipos;    // outer Position column, 3 floats per row
+    float4* frags;        // fragment workspace, kGravRows float4 per slot
+    uint32_t row_begin;
+    uint32_t row_count;
+    uint32_t n_tiles_total;
+    float eps;
+    GravityLaunch launch;
+};
+
+struct GravityReduceArgs {
+    const float4* frags;
+    float* acc;           // Acceleration column, 3 floats per row
+    uint32_t row_begin;
+    uint32_t row_count;
+    uint32_t n_launches;  // 1 (single GPU) or 2 (local tiles, then remote tiles)
+    GravityLaunch launch[2];
+};
+
+// Number of fragment slots a launch may touch.
+inline uint32_t gravity_frag_slots(const GravityLaunch& l) { return l.grid + l.n_iblocks; }
+int gravity_max_ctas_per_sm();  // occupancy of the interaction kernel on the current device
+cudaError_t gravity_prepare();  // one-time function attributes
+cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s);
+cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
+
+// Position(12 B) + Mass(4 B) rows [0, n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
+// gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`.
+cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
+                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, cudaStream_t s);
+// Null bodies (gm = 0) for [begin, end) so partially filled tiles contribute nothing.
+cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s);
+
+// ---- streaming systems ---------------------------------------------------------------------------
+// y[k] = y[k] + x[k] * a for k in [0, n): separate IEEE mul and add (no FMA contraction), the
+// arithmetic of `position.point += velocity * FIXED_TIME_STEP` (crates/n-body/src/lib.rs:92),
+// `*velocity += acceleration * FIXED_TIME_STEP` (:101) and, with a == 1, simple_iter's
+// `position.0 += velocity.0` (crates/ecs_bench_suite/src/recs/simple_iter.rs:48).
+cudaError_t launch_axpy_rn(float* y, const float* x, float a, uint64_t n, cudaStream_t s);
+// movement fused with the posm refresh of the moved rows (n-body tick): pos += vel*dt and
+// posm[dst_offset + row] = {pos, G*m}.
+cudaError_t launch_movement_pack(float* pos, const float* vel, const float* mass, float dt, float g,
+                                 float* posm, uint64_t row_begin, uint64_t n, uint64_t dst_offset,
+                                 cudaStream_t s);
+
+// rain (crates/rain-simulation/src/lib.rs:62-96); vel/pos are 3-float rows.
+cudaError_t launch_rain_gravity(float* vel, uint64_t n, float gravity_dt, float terminal,
+                                cudaStream_t s);
+cudaError_t launch_rain_wind(float* vel, uint64_t n, float wx, float wy, float wz, float terminal,
+                             cudaStream_t s);
+// wind -> gravity -> movement in one pass (the bench registration order's DAG).
+cudaError_t launch_rain_fused(float* vel, float* pos, uint64_t n, float wx, float wy, float wz,
+                              float gravity_dt, float terminal, float dt, cudaStream_t s);
+
+// ---- measurement ---------------------------------------------------------------------------------
+cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
+                             unsigned long long* cycles, cudaStream_t s);
+cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
+
+}  // namespace recs

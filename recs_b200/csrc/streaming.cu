@@ -1,0 +1,322 @@
+// HBM-bound streaming systems for sm_100a: the par-iter query path of recs
+// (crates/ecs/src/systems/iteration.rs:151-245) for plain `(Write<A>, Read<B>)` f32-vector
+// systems.  One grid replaces the reference's per-segment tasks; columns are read and written as
+// flat float arrays with 128-bit accesses, and every thread keeps several independent 16-byte
+// loads in flight so that ~35 KB per SM are outstanding (what 6.5 TB/s x HBM latency needs).
+//
+// Arithmetic is kept bit-identical to the Rust code: rustc never contracts `a + b * c` into an
+// FMA, so every mul/add below is an explicit round-to-nearest intrinsic.
+#include "kernels.cuh"
+
+namespace recs {
+namespace {
+
+constexpr int kStreamThreads = 256;
+constexpr int kStreamUnroll = 4;  // float4 per thread per array in flight
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
+
+// y = y + x * a over n4 float4 (both 16-byte aligned).
+__global__ void __launch_bounds__(kStreamThreads) axpy_rn_vec_kernel(float4* __restrict__ y,
+                                                                     const float4* __restrict__ x,
+                                                                     float a, uint64_t n4) {
+    const uint64_t chunk = static_cast<uint64_t>(kStreamThreads) * kStreamUnroll;
+    for (uint64_t base = blockIdx.x * chunk; base < n4; base += gridDim.x * chunk) {
+        float4 yv[kStreamUnroll], xv[kStreamUnroll];
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            const uint64_t i = base + u * kStreamThreads + threadIdx.x;
+            if (i < n4) {
+                xv[u] = ld_stream(x + i);
+                yv[u] = ld_stream(y + i);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kStreamUnroll; ++u) {
+            const uint64_t i = base + u * kStreamThreads + threadIdx.x;
+            if (i < n4) {
+                float4 r;
+                r.x = __fadd_rn(yv[u].x, __fmul_rn(xv[u].x, a));
+                r.y = __fadd_rn(yv[u].y, __fmul_rn(xv[u].y, a));
+                r.z = __fadd_rn(yv[u].z, __fmul_rn(xv[u].z, a));
+                r.w = __fadd_rn(yv[u].w, __fmul_rn(xv[u].w, a));
+                st_stream(y + i, r);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kStreamThreads) axpy_rn_scalar_kernel(float* __restrict__ y,
+                                                                        const float* __restrict__ x,
+                                                                        float a, uint64_t n) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        y[i] = __fadd_rn(y[i], __fmul_rn(x[i], a));
+}
+
+// movement + posm refresh, one thread per body.
+__global__ void __launch_bounds__(kStreamThreads)
+    movement_pack_kernel(float* __restrict__ pos, const float* __restrict__ vel,
+                         const float* __restrict__ mass, float dt, float g, float* __restrict__ posm,
+                         uint64_t row_begin, uint64_t n, uint64_t dst_offset) {
+    const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (k >= n) return;
+    const uint64_t row = row_begin + k;
+    const float x = __fadd_rn(pos[3 * row + 0], __fmul_rn(vel[3 * row + 0], dt));
+    const float y = __fadd_rn(pos[3 * row + 1], __fmul_rn(vel[3 * row + 1], dt));
+    const float z = __fadd_rn(pos[3 * row + 2], __fmul_rn(vel[3 * row + 2], dt));
+    pos[3 * row + 0] = x;
+    pos[3 * row + 1] = y;
+    pos[3 * row + 2] = z;
+    const uint64_t J = dst_offset + k;
+    float* d = posm + (J >> 1) * 8 + (J & 1);
+    d[0] = x;
+    d[2] = y;
+    d[4] = z;
+    d[6] = __fmul_rn(g, mass[row]);
+}
+
+// ---- rain --------------------------------------------------------------------------------------
+// Four entities (12 floats = three float4) per thread per column.
+struct Vec3x4 {
+    float4 a, b, c;  // x0 y0 z0 x1 | y1 z1 x2 y2 | z2 x3 y3 z3
+};
+__device__ __forceinline__ void get3(const Vec3x4& v, int e, float& x, float& y, float& z) {
+    const float f[12] = {v.a.x, v.a.y, v.a.z, v.a.w, v.b.x, v.b.y, v.b.z, v.b.w, v.c.x, v.c.y, v.c.z, v.c.w};
+    x = f[3 * e];
+    y = f[3 * e + 1];
+    z = f[3 * e + 2];
+}
+
+// gravity: `if abs(v.y) >= TERMINAL { return } v += -G * dt * unit_y`
+//   (crates/rain-simulation/src/lib.rs:65-70).  -9.82*0.05 is folded by rustc at compile time in
+//   f32 ((-G) * dt), then multiplied into unit_y = (0,1,0): x += k*0, y += k*1, z += k*0.
+__device__ __forceinline__ void rain_gravity_1(float& x, float& y, float& z, float k, float terminal) {
+    if (fabsf(y) >= terminal) return;
+    x = __fadd_rn(x, __fmul_rn(k, 0.f));
+    y = __fadd_rn(y, __fmul_rn(k, 1.f));
+    z = __fadd_rn(z, __fmul_rn(k, 0.f));
+}
+// wind: `if |v| >= TERMINAL { return } v += (WIND_ACCELERATION * dt) * wind_direction`
+//   (crates/rain-simulation/src/lib.rs:86-92); magnitude = sqrt((x*x + y*y) + z*z).
+//   (wx, wy, wz) arrive pre-multiplied by WIND_ACCELERATION * dt on the host, in f32, which is
+//   the same `f32 * Vector3` product the reference forms before the `+=`.
+__device__ __forceinline__ void rain_wind_1(float& x, float& y, float& z, float wx, float wy, float wz,
+                                            float terminal) {
+    const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+    if (__fsqrt_rn(m2) >= terminal) return;
+    x = __fadd_rn(x, wx);
+    y = __fadd_rn(y, wy);
+    z = __fadd_rn(z, wz);
+}
+
+template <int MODE>  // 0 = gravity only, 1 = wind only, 2 = wind -> gravity -> movement
+__global__ void __launch_bounds__(kStreamThreads)
+    rain_kernel(float* __restrict__ vel, float* __restrict__ pos, uint64_t n, float wx, float wy,
+                float wz, float k_gravity, float terminal, float dt) {
+    const uint64_t groups = n / 4;  // full groups of 4 entities
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t gidx = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; gidx < groups;
+         gidx += stride) {
+        float4* v4 = reinterpret_cast<float4*>(vel) + 3 * gidx;
+        Vec3x4 v;
+        v.a = __ldcs(v4 + 0);
+        v.b = __ldcs(v4 + 1);
+        v.c = __ldcs(v4 + 2);
+        Vec3x4 p;
+        float4* p4 = nullptr;
+        if (MODE == 2) {
+            p4 = reinterpret_cast<float4*>(pos) + 3 * gidx;
+            p.a = __ldcs(p4 + 0);
+            p.b = __ldcs(p4 + 1);
+            p.c = __ldcs(p4 + 2);
+        }
+        float o[12], q[12];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x, y, z;
+            get3(v, e, x, y, z);
+            if (MODE == 1 || MODE == 2) rain_wind_1(x, y, z, wx, wy, wz, terminal);
+            if (MODE == 0 || MODE == 2) rain_gravity_1(x, y, z, k_gravity, terminal);
+            o[3 * e] = x;
+            o[3 * e + 1] = y;
+            o[3 * e + 2] = z;
+            if (MODE == 2) {
+                float px, py, pz;
+                get3(p, e, px, py, pz);
+                q[3 * e] = __fadd_rn(px, __fmul_rn(x, dt));
+                q[3 * e + 1] = __fadd_rn(py, __fmul_rn(y, dt));
+                q[3 * e + 2] = __fadd_rn(pz, __fmul_rn(z, dt));
+            }
+        }
+        __stcs(v4 + 0, make_float4(o[0], o[1], o[2], o[3]));
+        __stcs(v4 + 1, make_float4(o[4], o[5], o[6], o[7]));
+        __stcs(v4 + 2, make_float4(o[8], o[9], o[10], o[11]));
+        if (MODE == 2) {
+            __stcs(p4 + 0, make_float4(q[0], q[1], q[2], q[3]));
+            __stcs(p4 + 1, make_float4(q[4], q[5], q[6], q[7]));
+            __stcs(p4 + 2, make_float4(q[8], q[9], q[10], q[11]));
+        }
+    }
+    // tail entities (n % 4), handled by the first threads of block 0
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const uint64_t e = groups * 4 + threadIdx.x;
+        float x = vel[3 * e], y = vel[3 * e + 1], z = vel[3 * e + 2];
+        if (MODE == 1 || MODE == 2) rain_wind_1(x, y, z, wx, wy, wz, terminal);
+        if (MODE == 0 || MODE == 2) rain_gravity_1(x, y, z, k_gravity, terminal);
+        vel[3 * e] = x;
+        vel[3 * e + 1] = y;
+        vel[3 * e + 2] = z;
+        if (MODE == 2) {
+            pos[3 * e] = __fadd_rn(pos[3 * e], __fmul_rn(x, dt));
+            pos[3 * e + 1] = __fadd_rn(pos[3 * e + 1], __fmul_rn(y, dt));
+            pos[3 * e + 2] = __fadd_rn(pos[3 * e + 2], __fmul_rn(z, dt));
+        }
+    }
+}
+
+inline uint32_t stream_grid(uint64_t work_items, uint32_t per_block) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint64_t need = (work_items + per_block - 1) / per_block;
+    const uint64_t cap = static_cast<uint64_t>(sms) * 8 * 4;  // 8 resident CTAs x 4 waves
+    uint64_t g = need < cap ? need : cap;
+    if (g == 0) g = 1;
+    return static_cast<uint32_t>(g);
+}
+
+}  // namespace
+
+cudaError_t launch_axpy_rn(float* y, const float* x, float a, uint64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uintptr_t ya = reinterpret_cast<uintptr_t>(y), xa = reinterpret_cast<uintptr_t>(x);
+    if ((ya & 15) != (xa & 15) || (ya & 3)) {
+        axpy_rn_scalar_kernel<<<stream_grid(n, kStreamThreads), kStreamThreads, 0, s>>>(y, x, a, n);
+        return cudaGetLastError();
+    }
+    // scalar head up to 16-byte alignment, float4 body, scalar tail
+    uint64_t head = ((16 - (ya & 15)) & 15) / 4;
+    if (head > n) head = n;
+    if (head) axpy_rn_scalar_kernel<<<1, 32, 0, s>>>(y, x, a, head);
+    const uint64_t n4 = (n - head) / 4;
+    if (n4) {
+        const uint32_t grid = stream_grid(n4, kStreamThreads * kStreamUnroll);
+        axpy_rn_vec_kernel<<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(y + head),
+                                                          reinterpret_cast<const float4*>(x + head), a,
+                                                          n4);
+    }
+    const uint64_t tail = n - head - 4 * n4;
+    if (tail) axpy_rn_scalar_kernel<<<1, 32, 0, s>>>(y + head + 4 * n4, x + head + 4 * n4, a, tail);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_movement_pack(float* pos, const float* vel, const float* mass, float dt, float g,
+                                 float* posm, uint64_t row_begin, uint64_t n, uint64_t dst_offset,
+                                 cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const uint64_t grid = (n + kStreamThreads - 1) / kStreamThreads;
+    movement_pack_kernel<<<static_cast<uint32_t>(grid), kStreamThreads, 0, s>>>(
+        pos, vel, mass, dt, g, posm, row_begin, n, dst_offset);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rain_gravity(float* vel, uint64_t n, float gravity_dt, float terminal,
+                                cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    rain_kernel<0><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
+        vel, nullptr, n, 0.f, 0.f, 0.f, gravity_dt, terminal, 0.f);
+    return cudaGetLastError();
+}
+cudaError_t launch_rain_wind(float* vel, uint64_t n, float wx, float wy, float wz, float terminal,
+                             cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    rain_kernel<1><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
+        vel, nullptr, n, wx, wy, wz, 0.f, terminal, 0.f);
+    return cudaGetLastError();
+}
+cudaError_t launch_rain_fused(float* vel, float* pos, uint64_t n, float wx, float wy, float wz,
+                              float gravity_dt, float terminal, float dt, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    rain_kernel<2><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
+        vel, pos, n, wx, wy, wz, gravity_dt, terminal, dt);
+    return cudaGetLastError();
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+namespace {
+template <int PACKED>
+__global__ void __launch_bounds__(256) fp32_peak_kernel(uint32_t iters, float* sink,
+                                                        unsigned long long* cycles) {
+    // 16 independent accumulator chains per thread, all operands in registers.
+    float seed = 1.0f + 1e-7f * threadIdx.x;
+    const long long t0 = clock64();
+    if (PACKED) {
+        unsigned long long acc[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i)
+            asm("mov.b64 %0, {%1, %2};" : "=l"(acc[i]) : "f"(seed + i), "f"(seed - i));
+        unsigned long long m, c;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(m) : "f"(0.999999f), "f"(1.000001f));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(1e-6f), "f"(-1e-6f));
+        for (uint32_t k = 0; k < iters; ++k) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 12; ++i)
+                    asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(acc[i]) : "l"(m), "l"(c));
+        }
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+            float lo, hi;
+            asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(acc[i]));
+            r += lo + hi;
+        }
+        seed = r;
+    } else {
+        float acc[24];
+#pragma unroll
+        for (int i = 0; i < 24; ++i) acc[i] = seed + i;
+        const float m = 0.999999f, c = 1e-6f;
+        for (uint32_t k = 0; k < iters; ++k) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int i = 0; i < 24; ++i)
+                    asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(acc[i]) : "f"(m), "f"(c));
+        }
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < 24; ++i) r += acc[i];
+        seed = r;
+    }
+    const long long t1 = clock64();
+    if (seed == 123.456f) sink[0] = seed;  // keep the chains alive
+    if (threadIdx.x == 0) cycles[blockIdx.x] = static_cast<unsigned long long>(t1 - t0);
+}
+
+__global__ void fill_kernel(float* p, uint64_t n, float v) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+        p[i] = v;
+}
+}  // namespace
+
+cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
+                             unsigned long long* cycles, cudaStream_t s) {
+    if (packed)
+        fp32_peak_kernel<1><<<grid, 256, 0, s>>>(iters, sink, cycles);
+    else
+        fp32_peak_kernel<0><<<grid, 256, 0, s>>>(iters, sink, cycles);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    fill_kernel<<<stream_grid(n, 256 * 4), 256, 0, s>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+}  // namespace recs

@@ -1,0 +1,209 @@
+"""Thin object wrapper over the C ABI (include/recs_gpu.h): one `GpuContext` per device.
+
+Only plumbing lives here (ctypes marshalling, keeping bound numpy buffers alive); all compute is
+in librecs_gpu.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import lib
+
+
+class RecsGpuError(RuntimeError):
+    def __init__(self, code: int, where: str, detail: str = ""):
+        self.code = code
+        name = _lib.ERR_NAMES.get(code, str(code))
+        super().__init__(f"{where}: {name}{': ' + detail if detail else ''}")
+
+
+def _u32s(values: Iterable[int]):
+    values = list(values)
+    arr = (C.c_uint32 * max(len(values), 1))(*values)
+    return arr, len(values)
+
+
+class GpuContext:
+    """Owns a `recs_gpu_ctx`.  Mirrors the lifecycle of the reference's executor
+    (`E::default()` ... `Drop`, crates/ecs/src/lib.rs:386-400)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, use_cuda_graph: bool = True, **overrides):
+        cfg = _lib.Config()
+        lib.recs_gpu_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.rank = rank
+        cfg.world_size = world_size
+        cfg.use_cuda_graph = 1 if use_cuda_graph else 0
+        for key, value in overrides.items():
+            if not hasattr(cfg, key):
+                raise TypeError(f"unknown recs_gpu_config field {key!r}")
+            setattr(cfg, key, value)
+        self.config = cfg
+        self._ctx = C.c_void_p()
+        self._bound = {}  # (arch, comp) -> ndarray kept alive while bound
+        code = lib.recs_gpu_create(C.byref(cfg), C.byref(self._ctx))
+        if code != _lib.RECS_OK:
+            self._ctx = C.c_void_p()
+            raise RecsGpuError(code, "recs_gpu_create", "no usable sm_100a device; recs_b200 has no CPU fallback")
+
+    # -- lifecycle ---------------------------------------------------------------------------
+    def close(self) -> None:
+        if self._ctx:
+            lib.recs_gpu_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+            self._bound.clear()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code: int, where: str) -> None:
+        if code != _lib.RECS_OK:
+            detail = lib.recs_gpu_last_error(self._ctx)
+            raise RecsGpuError(code, where, detail.decode() if detail else "")
+
+    def clear_error(self) -> None:
+        lib.recs_gpu_clear_error(self._ctx)
+
+    def last_error(self) -> str:
+        return lib.recs_gpu_last_error(self._ctx).decode()
+
+    def synchronize(self) -> None:
+        self._check(lib.recs_gpu_synchronize(self._ctx), "recs_gpu_synchronize")
+
+    # -- columns -----------------------------------------------------------------------------
+    def bind_column(self, archetype: int, component: int, array: np.ndarray, elem_size: int | None = None) -> None:
+        if not array.flags["C_CONTIGUOUS"]:
+            raise ValueError("component columns must be C-contiguous")
+        if elem_size is None:
+            elem_size = array.dtype.itemsize * (int(np.prod(array.shape[1:])) if array.ndim > 1 else 1)
+        count = array.shape[0] if array.ndim else 0
+        self._check(
+            lib.recs_gpu_bind_column(self._ctx, archetype, component, array.ctypes.data_as(C.c_void_p), elem_size, count),
+            "recs_gpu_bind_column",
+        )
+        self._bound[(archetype, component)] = array
+
+    def upload(self, archetype: int, component: int) -> None:
+        self._check(lib.recs_gpu_upload(self._ctx, archetype, component), "recs_gpu_upload")
+
+    def download(self, archetype: int, component: int) -> np.ndarray:
+        self._check(lib.recs_gpu_download(self._ctx, archetype, component), "recs_gpu_download")
+        return self._bound[(archetype, component)]
+
+    def invalidate(self, archetype: int) -> None:
+        self._check(lib.recs_gpu_invalidate(self._ctx, archetype), "recs_gpu_invalidate")
+
+    def column_device_ptr(self, archetype: int, component: int) -> tuple[int, int]:
+        ptr = C.c_void_p()
+        count = C.c_uint64()
+        self._check(
+            lib.recs_gpu_column_device_ptr(self._ctx, archetype, component, C.byref(ptr), C.byref(count)),
+            "recs_gpu_column_device_ptr",
+        )
+        return int(ptr.value or 0), int(count.value)
+
+    # -- systems -----------------------------------------------------------------------------
+    def create_system(self, kind: int, components: Sequence[int]) -> int:
+        ids = (C.c_uint64 * max(len(components), 1))(*components)
+        out = C.c_uint32()
+        self._check(lib.recs_gpu_system_create(self._ctx, kind, ids, len(components), C.byref(out)), "recs_gpu_system_create")
+        return int(out.value)
+
+    def describe_system(self, system: int) -> tuple[str, list[tuple[int, bool]]]:
+        desc = _lib.SystemDesc()
+        self._check(lib.recs_gpu_system_describe(self._ctx, system, C.byref(desc)), "recs_gpu_system_describe")
+        accesses = [(int(desc.access[i].component_id), bool(desc.access[i].is_write)) for i in range(desc.n_access)]
+        return desc.name.decode(), accesses
+
+    def set_archetypes(self, system: int, archetypes: Iterable[int]) -> None:
+        arr, n = _u32s(archetypes)
+        self._check(lib.recs_gpu_system_set_archetypes(self._ctx, system, arr, n), "recs_gpu_system_set_archetypes")
+
+    def set_query_archetypes(self, system: int, archetypes: Iterable[int]) -> None:
+        arr, n = _u32s(archetypes)
+        self._check(
+            lib.recs_gpu_system_set_query_archetypes(self._ctx, system, arr, n), "recs_gpu_system_set_query_archetypes"
+        )
+
+    def run_system(self, system: int, sync: bool = True) -> None:
+        self._check(
+            lib.recs_gpu_run_system(self._ctx, system, _lib.GPU_SYNC if sync else _lib.GPU_ASYNC), "recs_gpu_run_system"
+        )
+
+    def set_tick_order(self, systems: Iterable[int]) -> None:
+        arr, n = _u32s(systems)
+        self._check(lib.recs_gpu_set_tick_order(self._ctx, arr, n), "recs_gpu_set_tick_order")
+
+    def tick(self, n_ticks: int = 1) -> None:
+        self._check(lib.recs_gpu_tick(self._ctx, n_ticks), "recs_gpu_tick")
+
+    # -- rain --------------------------------------------------------------------------------
+    def set_wind_direction(self, xyz: Sequence[float]) -> None:
+        arr = (C.c_float * 3)(*xyz)
+        self._check(lib.recs_gpu_set_wind_direction(self._ctx, arr), "recs_gpu_set_wind_direction")
+
+    def get_wind_direction(self) -> np.ndarray:
+        arr = (C.c_float * 3)()
+        self._check(lib.recs_gpu_get_wind_direction(self._ctx, arr), "recs_gpu_get_wind_direction")
+        return np.array(list(arr), dtype=np.float32)
+
+    # -- sharding ----------------------------------------------------------------------------
+    def comm_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * _lib.NCCL_ID_BYTES)()
+        self._check(lib.recs_gpu_comm_get_unique_id(self._ctx, buf), "recs_gpu_comm_get_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes) -> None:
+        buf = (C.c_uint8 * _lib.NCCL_ID_BYTES)(*unique_id)
+        self._check(lib.recs_gpu_comm_init(self._ctx, buf), "recs_gpu_comm_init")
+
+    def shard_rows(self, n_rows: int) -> tuple[int, int]:
+        b, e = C.c_uint64(), C.c_uint64()
+        self._check(lib.recs_gpu_shard_rows(self._ctx, n_rows, C.byref(b), C.byref(e)), "recs_gpu_shard_rows")
+        return int(b.value), int(e.value)
+
+    # -- measurement -------------------------------------------------------------------------
+    def enable_timing(self, enabled: bool = True) -> None:
+        self._check(lib.recs_gpu_enable_timing(self._ctx, 1 if enabled else 0), "recs_gpu_enable_timing")
+
+    def timing(self) -> dict:
+        t = _lib.Timing()
+        self._check(lib.recs_gpu_get_timing(self._ctx, C.byref(t)), "recs_gpu_get_timing")
+        return {name: getattr(t, name) for name, _ in _lib.Timing._fields_}
+
+    def reset_timing(self) -> None:
+        self._check(lib.recs_gpu_reset_timing(self._ctx), "recs_gpu_reset_timing")
+
+    def measure_fp32_peak(self, packed: bool = True) -> tuple[float, float]:
+        tf, mhz = C.c_float(), C.c_float()
+        self._check(
+            lib.recs_gpu_measure_fp32_peak(self._ctx, 1 if packed else 0, C.byref(tf), C.byref(mhz)),
+            "recs_gpu_measure_fp32_peak",
+        )
+        return float(tf.value), float(mhz.value)
+
+    def flush_l2(self) -> None:
+        self._check(lib.recs_gpu_flush_l2(self._ctx), "recs_gpu_flush_l2")
+
+    def pinned_empty(self, shape, dtype=np.float32) -> np.ndarray:
+        """A numpy array over page-locked host memory (end-to-end path: H2D/D2H at full PCIe rate)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        ptr = C.c_void_p()
+        self._check(lib.recs_gpu_host_alloc(self._ctx, nbytes, C.byref(ptr)), "recs_gpu_host_alloc")
+        buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        return arr
