@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -66,6 +67,7 @@ struct recs_gpu_ctx {
     cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
     int sm_count = 148;
     int grav_ctas_per_sm = 2;
+    int grav_variant = 0;
 
     std::map<ColKey, Column> columns;
     std::vector<System> systems;
@@ -291,6 +293,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
 
     // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
     const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm);
+    const uint32_t kGravRows = (uint32_t)gravity_variant(c->grav_variant).rows();
     for (uint32_t a : sys.archs) {
         Column *p, *acc;
         if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
@@ -312,6 +315,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
         ra.acc = (float*)acc->dev;
         ra.row_begin = (uint32_t)row_begin;
         ra.row_count = (uint32_t)row_count;
+        ra.iblock_rows = kGravRows;
         // launch A: local tiles (all tiles when not sharded); launch B: the other ranks' tiles
         const uint32_t own_tiles = sharded ? (uint32_t)(slice / kGravTile) : n_tiles;
         const uint32_t own_off = sharded ? own_tiles * (uint32_t)c->cfg.rank : 0;
@@ -343,6 +347,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
             ga.n_tiles_total = n_tiles;
             ga.eps = c->cfg.nbody_epsilon;
             ga.launch = ra.launch[l];
+            ga.variant = c->grav_variant;
             if (ga.launch.n_vtiles == 0) continue;
             Timed t(c, T_GRAVITY);
             RECS_CUDA(c, launch_gravity(ga, c->stream));
@@ -628,7 +633,9 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
               cudaEventCreateWithFlags(&c->ev_gather, cudaEventDisableTiming) == cudaSuccess &&
               gravity_prepare() == cudaSuccess;
     if (ok) {
-        c->grav_ctas_per_sm = gravity_max_ctas_per_sm();
+        const char* v = getenv("RECS_GPU_GRAVITY_VARIANT");  // tuning knob; default chosen by measurement
+        if (v && v[0] >= '0' && v[0] < '0' + kGravVariantCount) c->grav_variant = v[0] - '0';
+        c->grav_ctas_per_sm = gravity_max_ctas_per_sm(c->grav_variant);
         ok = c->grav_ctas_per_sm > 0;
     }
     if (!ok) {

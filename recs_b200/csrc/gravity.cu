@@ -52,7 +52,10 @@ __host__ __device__ inline uint32_t cta_of(uint32_t u, uint32_t grid, uint32_t u
     return rem + (u - big) / q;
 }
 
-__global__ void __launch_bounds__(kGravThreads, 2) nbody_gravity_kernel(const GravityArgs a) {
+template <int RI, int MIN_CTAS>
+__global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(const GravityArgs a) {
+    constexpr int kGravRowsPerThread = RI;
+    constexpr int kGravRows = kGravConsumerThreads * RI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
     __shared__ __align__(8) uint64_t full_bar[kGravStages];
@@ -193,6 +196,7 @@ __global__ void __launch_bounds__(kGravThreads, 2) nbody_gravity_kernel(const Gr
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.row_count) return;
+    const uint32_t kGravRows = a.iblock_rows;
     const uint32_t b = i / kGravRows;
     const uint32_t idx = i % kGravRows;
     // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
@@ -246,14 +250,38 @@ __global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm,
 
 }  // namespace
 
+namespace {
+typedef void (*GravityKernel)(const GravityArgs);
+const GravityVariant kVariants[kGravVariantCount] = {{4, 2}, {4, 3}, {2, 4}, {3, 3}};
+GravityKernel variant_kernel(int v) {
+    switch (v) {
+        case 0:
+            return nbody_gravity_kernel<4, 2>;
+        case 1:
+            return nbody_gravity_kernel<4, 3>;
+        case 2:
+            return nbody_gravity_kernel<2, 4>;
+        case 3:
+            return nbody_gravity_kernel<3, 3>;
+    }
+    return nullptr;
+}
+}  // namespace
+
+GravityVariant gravity_variant(int index) { return kVariants[index]; }
+
 cudaError_t gravity_prepare() {
-    return cudaFuncSetAttribute(nbody_gravity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                kGravSmemBytes);
+    for (int v = 0; v < kGravVariantCount; ++v) {
+        cudaError_t e = cudaFuncSetAttribute(variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kGravSmemBytes);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
-int gravity_max_ctas_per_sm() {
+int gravity_max_ctas_per_sm(int variant) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, nbody_gravity_kernel, kGravThreads,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, variant_kernel(variant), kGravThreads,
                                                       kGravSmemBytes) != cudaSuccess)
         return 0;
     return n;
@@ -261,7 +289,7 @@ int gravity_max_ctas_per_sm() {
 
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s) {
     if (a.launch.n_vtiles == 0 || a.launch.n_iblocks == 0) return cudaSuccess;
-    nbody_gravity_kernel<<<a.launch.grid, kGravThreads, kGravSmemBytes, s>>>(a);
+    variant_kernel(a.variant)<<<a.launch.grid, kGravThreads, kGravSmemBytes, s>>>(a);
     return cudaGetLastError();
 }
 

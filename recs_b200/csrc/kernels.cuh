@@ -10,8 +10,7 @@ namespace recs {
 constexpr int kGravConsumerWarps = 8;
 constexpr int kGravConsumerThreads = 32 * kGravConsumerWarps;  // 256
 constexpr int kGravThreads = kGravConsumerThreads + 32;        // + 1 TMA producer warp
-constexpr int kGravRowsPerThread = 4;                          // register blocking over i
-constexpr int kGravRows = kGravConsumerThreads * kGravRowsPerThread;  // rows per i-block (1024)
+constexpr int kGravMaxRowsPerThread = 4;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
 constexpr int kGravTileBytes = kGravTile * 16;                 // 4 KiB
@@ -19,9 +18,18 @@ constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic
 
 // One launch of the interaction kernel: rows [row_begin, row_begin+row_count) of the outer
 // Position column against j tiles [tile_offset, tile_offset + n_vtiles) (mod n_tiles_total).
+// Kernel variants (register blocking x resident CTAs per SM), selected per context.
+struct GravityVariant {
+    int rows_per_thread;  // bodies i per consumer thread
+    int min_ctas;         // __launch_bounds__ residency target
+    int rows() const { return kGravConsumerThreads * rows_per_thread; }  // rows per i-block
+};
+constexpr int kGravVariantCount = 4;
+GravityVariant gravity_variant(int index);
+
 struct GravityLaunch {
     uint32_t grid;        // persistent CTAs (stream-K workers)
-    uint32_t n_iblocks;   // ceil(row_count / kGravRows)
+    uint32_t n_iblocks;   // ceil(row_count / rows per i-block)
     uint32_t n_vtiles;    // tiles visited by this launch
     uint32_t tile_offset; // first tile visited
     uint32_t frag_base;   // first fragment slot of this launch
@@ -30,12 +38,13 @@ struct GravityLaunch {
 struct GravityArgs {
     const float4* posm;   // pair-interleaved {x0 x1 y0 y1 | z0 z1 gm0 gm1}, n_tiles_total tiles
     const float* ipos;    // outer Position column, 3 floats per row
-    float4* frags;        // fragment workspace, kGravRows float4 per slot
+    float4* frags;        // fragment workspace, rows-per-i-block float4 per slot
     uint32_t row_begin;
     uint32_t row_count;
     uint32_t n_tiles_total;
     float eps;
     GravityLaunch launch;
+    int variant;
 };
 
 struct GravityReduceArgs {
@@ -44,12 +53,13 @@ struct GravityReduceArgs {
     uint32_t row_begin;
     uint32_t row_count;
     uint32_t n_launches;  // 1 (single GPU) or 2 (local tiles, then remote tiles)
+    uint32_t iblock_rows; // rows per i-block of the variant that produced the fragments
     GravityLaunch launch[2];
 };
 
 // Number of fragment slots a launch may touch.
 inline uint32_t gravity_frag_slots(const GravityLaunch& l) { return l.grid + l.n_iblocks; }
-int gravity_max_ctas_per_sm();  // occupancy of the interaction kernel on the current device
+int gravity_max_ctas_per_sm(int variant);  // occupancy of the interaction kernel on the current device
 cudaError_t gravity_prepare();  // one-time function attributes
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s);
 cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
