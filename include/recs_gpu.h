@@ -205,7 +205,7 @@ int32_t recs_gpu_shard_rows(recs_gpu_ctx* ctx, uint64_t n_rows, uint64_t* row_be
  * Measurement hooks (used by bench.py; all times are CUDA-event times on the context stream).
  * ---------------------------------------------------------------------------------------- */
 typedef struct recs_gpu_timing {
-    float last_tick_chain_ms;    /* whole recs_gpu_tick call                                  */
+    float last_tick_chain_ms;    /* sum over recs_gpu_tick calls since reset (whole chains)   */
     float gravity_ms;            /* sum over launches of the interaction kernel               */
     float gravity_reduce_ms;
     float movement_ms;
@@ -218,6 +218,10 @@ typedef struct recs_gpu_timing {
 int32_t recs_gpu_enable_timing(recs_gpu_ctx* ctx, int32_t enabled);
 int32_t recs_gpu_get_timing(recs_gpu_ctx* ctx, recs_gpu_timing* out);
 int32_t recs_gpu_reset_timing(recs_gpu_ctx* ctx);
+/* Generic CUDA-event bracket on the context stream: start records an event, stop records a second
+ * one, waits for it and returns the elapsed device time. */
+int32_t recs_gpu_timer_start(recs_gpu_ctx* ctx);
+int32_t recs_gpu_timer_stop(recs_gpu_ctx* ctx, float* out_ms);
 /* Issue rate of the FP32 FMA pipe measured on this GPU with a register-resident FFMA2 loop:
  * out_tflops = 2 * FMAs / s; out_sm_mhz = the SM clock derived from clock64 over the run. */
 int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* ctx, int32_t packed, float* out_tflops,

@@ -204,7 +204,8 @@ enum { SYS_GRAVITY = 0, SYS_MOVEMENT = 1, SYS_ACCELERATION = 2 };
 typedef struct {
     float *pos, *vel, *acc;
     const float* mass;
-    size_t n;
+    size_t n;       /* bodies the nested query iterates */
+    size_t n_outer; /* outer rows iterated (== n except for the bounded row sample of bench.py) */
     int n_threads;
     int n_ticks;
     int order[3];
@@ -241,7 +242,7 @@ static void* pool_worker(void* arg) {
                 if (t >= p->n_tasks) break;
                 const size_t b = t * p->seg_size;
                 size_t e = b + p->seg_size;
-                if (e > p->n) e = p->n;
+                if (e > p->n_outer) e = p->n_outer;
                 run_segment(p, sys, b, e);
             }
             pthread_barrier_wait(&p->barrier); /* all segments of the layer finished */
@@ -251,9 +252,20 @@ static void* pool_worker(void* arg) {
 }
 
 /* Runs n_ticks of the n-body systems in `order` on n_threads workers; returns seconds. */
+ORACLE_API double oracle_nbody_run_pool_rows(float* pos, const float* mass, float* vel, float* acc, size_t n,
+                                             size_t n_outer, int n_ticks, int n_threads, const int order[3]);
+
 ORACLE_API double oracle_nbody_run_pool(float* pos, const float* mass, float* vel, float* acc, size_t n, int n_ticks,
                                         int n_threads, const int order[3]) {
+    return oracle_nbody_run_pool_rows(pos, mass, vel, acc, n, n, n_ticks, n_threads, order);
+}
+
+/* Same, with the outer iteration restricted to rows [0, n_outer) (the query still sees all n
+ * bodies): the bounded sample bench.py times when a full tick would take too long on the CPU. */
+ORACLE_API double oracle_nbody_run_pool_rows(float* pos, const float* mass, float* vel, float* acc, size_t n,
+                                             size_t n_outer, int n_ticks, int n_threads, const int order[3]) {
     if (n_threads < 1) n_threads = 1;
+    if (n_outer > n) n_outer = n;
     pool_t p;
     memset(&p, 0, sizeof p);
     p.pos = pos;
@@ -261,14 +273,15 @@ ORACLE_API double oracle_nbody_run_pool(float* pos, const float* mass, float* ve
     p.acc = acc;
     p.mass = mass;
     p.n = n;
+    p.n_outer = n_outer;
     p.n_threads = n_threads;
     p.n_ticks = n_ticks;
     memcpy(p.order, order, sizeof p.order);
     /* calculate_auto_segment_size / calculate_segment_count, systems/mod.rs:397-411 */
-    size_t seg = n / ((size_t)n_threads * 4);
+    size_t seg = n_outer / ((size_t)n_threads * 4);
     if (seg < 16) seg = 16;
     p.seg_size = seg;
-    p.n_tasks = n ? 1 + (n - 1) / seg : 1;
+    p.n_tasks = n_outer ? 1 + (n_outer - 1) / seg : 1;
 
     /* n_threads workers + this thread as the scheduling thread */
     pthread_barrier_init(&p.barrier, NULL, (unsigned)n_threads + 1);

@@ -113,6 +113,8 @@ GPU_SYMBOLS = {
     "recs_gpu_enable_timing": (C.c_int32, [_ctx, C.c_int32]),
     "recs_gpu_get_timing": (C.c_int32, [_ctx, C.POINTER(Timing)]),
     "recs_gpu_reset_timing": (C.c_int32, [_ctx]),
+    "recs_gpu_timer_start": (C.c_int32, [_ctx]),
+    "recs_gpu_timer_stop": (C.c_int32, [_ctx, C.POINTER(C.c_float)]),
     "recs_gpu_measure_fp32_peak": (C.c_int32, [_ctx, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "recs_gpu_flush_l2": (C.c_int32, [_ctx]),
     "recs_gpu_host_alloc": (C.c_int32, [_ctx, C.c_size_t, C.POINTER(C.c_void_p)]),

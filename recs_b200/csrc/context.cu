@@ -103,6 +103,7 @@ struct recs_gpu_ctx {
     NcclApi::comm_t comm = nullptr;
 
     // misc
+    cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     float* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
 };
@@ -666,6 +667,8 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
             cudaEventDestroy(s.b);
         }
         for (auto e : c->event_pool) cudaEventDestroy(e);
+        if (c->timer_a) cudaEventDestroy(c->timer_a);
+        if (c->timer_b) cudaEventDestroy(c->timer_b);
         cudaEventDestroy(c->ev_pack);
         cudaEventDestroy(c->ev_gather);
         cudaStreamDestroy(c->stream);
@@ -934,10 +937,7 @@ int32_t recs_gpu_get_timing(recs_gpu_ctx* c, recs_gpu_timing* out) {
     for (auto& s : c->spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
-            if (s.slot == T_CHAIN)
-                acc[T_CHAIN] = ms;  // last chain
-            else
-                acc[s.slot] += ms;
+            acc[s.slot] += ms;
         }
     }
     memset(out, 0, sizeof *out);
@@ -966,10 +966,30 @@ int32_t recs_gpu_reset_timing(recs_gpu_ctx* c) {
     return RECS_OK;
 }
 
+int32_t recs_gpu_timer_start(recs_gpu_ctx* c) {
+    RECS_ENTER(c);
+    if (!c->timer_a) {
+        RECS_CUDA(c, cudaEventCreate(&c->timer_a));
+        RECS_CUDA(c, cudaEventCreate(&c->timer_b));
+    }
+    RECS_CUDA(c, cudaEventRecord(c->timer_a, c->stream));
+    return RECS_OK;
+}
+
+int32_t recs_gpu_timer_stop(recs_gpu_ctx* c, float* out_ms) {
+    RECS_ENTER(c);
+    if (!c->timer_a || !out_ms) return fail(c, RECS_ERR_INVALID_ARGUMENT, "timer_stop without timer_start");
+    RECS_CUDA(c, cudaEventRecord(c->timer_b, c->stream));
+    RECS_CUDA(c, cudaEventSynchronize(c->timer_b));
+    RECS_CUDA(c, cudaStreamSynchronize(c->comm_stream));
+    RECS_CUDA(c, cudaEventElapsedTime(out_ms, c->timer_a, c->timer_b));
+    return RECS_OK;
+}
+
 int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* c, int32_t packed, float* out_tflops, float* out_sm_mhz) {
     RECS_ENTER(c);
     if (!out_tflops || !out_sm_mhz) return fail(c, RECS_ERR_INVALID_ARGUMENT, "measure_fp32_peak: null");
-    const uint32_t grid = (uint32_t)c->sm_count * 8;  // 8 CTAs x 256 threads = full occupancy
+    const uint32_t grid = (uint32_t)c->sm_count * 4;  // one resident wave: 4 CTAs x 256 threads per SM
     const uint32_t iters = 4096;
     float* sink = nullptr;
     unsigned long long* cycles = nullptr;

@@ -187,6 +187,14 @@ class GpuContext:
     def reset_timing(self) -> None:
         self._check(lib.recs_gpu_reset_timing(self._ctx), "recs_gpu_reset_timing")
 
+    def timer_start(self) -> None:
+        self._check(lib.recs_gpu_timer_start(self._ctx), "recs_gpu_timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        self._check(lib.recs_gpu_timer_stop(self._ctx, C.byref(ms)), "recs_gpu_timer_stop")
+        return float(ms.value)
+
     def measure_fp32_peak(self, packed: bool = True) -> tuple[float, float]:
         tf, mhz = C.c_float(), C.c_float()
         self._check(
