@@ -174,6 +174,14 @@ int32_t recs_schedule_edges(recs_schedule* schedule, uint32_t* from, uint32_t* t
 int32_t recs_schedule_next_batch(recs_schedule* schedule, int32_t reaction, uint32_t* out_systems, uint32_t cap,
                                  uint32_t* out_count);
 int32_t recs_schedule_complete(recs_schedule* schedule, uint32_t system);
+/* Which completed pending system the schedule acknowledges first when several have completed
+ * (the reference blocks in crossbeam's Select, schedule/mod.rs:271-297):
+ *   RECS_SELECT_CROSSBEAM  crossbeam-channel's thread-local xorshift shuffle, state as in a fresh
+ *                          thread -- reproduces the batch sequences the reference's tests expect
+ *   RECS_SELECT_FIRST      oldest pending completion first (deterministic; what recs_app uses) */
+#define RECS_SELECT_CROSSBEAM 0
+#define RECS_SELECT_FIRST 1
+int32_t recs_schedule_set_select_policy(recs_schedule* schedule, int32_t policy);
 /* Convenience: the batches of one whole tick when every dispatched system completes before the
  * next request (what a single-stream GPU chain does).  batch_of[i] = batch number of order[i]. */
 int32_t recs_schedule_tick_order(recs_schedule* schedule, uint32_t* out_order, uint32_t* out_batch_of, uint32_t cap,

@@ -200,6 +200,10 @@ int32_t recs_gpu_comm_init(recs_gpu_ctx* ctx, const uint8_t id_bytes[RECS_GPU_NC
 /* Rows [row_begin, row_end) of gravity / movement / acceleration that this rank computes. */
 int32_t recs_gpu_shard_rows(recs_gpu_ctx* ctx, uint64_t n_rows, uint64_t* row_begin,
                             uint64_t* row_end);
+/* The same partition as a pure function (no device needed): every rank owns one slice of
+ * `*slice_rows` rows of the tile-padded body range; the all-gather moves 16 bytes per slice row. */
+int32_t recs_gpu_shard_plan(uint64_t n_rows, int32_t rank, int32_t world_size, uint64_t* row_begin,
+                            uint64_t* row_end, uint64_t* slice_rows);
 
 /* ------------------------------------------------------------------------------------------
  * Measurement hooks (used by bench.py; all times are CUDA-event times on the context stream).

@@ -110,6 +110,7 @@ GPU_SYMBOLS = {
     "recs_gpu_comm_get_unique_id": (C.c_int32, [_ctx, C.POINTER(C.c_uint8)]),
     "recs_gpu_comm_init": (C.c_int32, [_ctx, C.POINTER(C.c_uint8)]),
     "recs_gpu_shard_rows": (C.c_int32, [_ctx, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "recs_gpu_shard_plan": (C.c_int32, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_enable_timing": (C.c_int32, [_ctx, C.c_int32]),
     "recs_gpu_get_timing": (C.c_int32, [_ctx, C.POINTER(Timing)]),
     "recs_gpu_reset_timing": (C.c_int32, [_ctx]),

@@ -923,6 +923,19 @@ int32_t recs_gpu_shard_rows(recs_gpu_ctx* c, uint64_t n_rows, uint64_t* row_begi
     return RECS_OK;
 }
 
+int32_t recs_gpu_shard_plan(uint64_t n_rows, int32_t rank, int32_t world_size, uint64_t* row_begin, uint64_t* row_end,
+                            uint64_t* slice_rows) {
+    if (world_size < 1 || rank < 0 || rank >= world_size || !row_begin || !row_end) return RECS_ERR_INVALID_ARGUMENT;
+    recs_gpu_config cfg;
+    recs_gpu_default_config(&cfg);
+    cfg.rank = rank;
+    cfg.world_size = world_size;
+    uint64_t slice;
+    shard_rows(cfg, n_rows, &slice, row_begin, row_end);
+    if (slice_rows) *slice_rows = slice;
+    return RECS_OK;
+}
+
 int32_t recs_gpu_enable_timing(recs_gpu_ctx* c, int32_t enabled) {
     RECS_ENTER(c);
     c->timing = enabled != 0;

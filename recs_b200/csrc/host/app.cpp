@@ -1,0 +1,339 @@
+// BasicApplication + run loop (crates/ecs/src/lib.rs:69-341) with an executor that dispatches GPU
+// systems on the context stream and CPU systems on the calling thread -- the "GPU system kind" of
+// the north star behind the reference's System / Schedule / Executor contract.
+//
+//   * systems are registered in order (ApplicationBuilder::add_system, lib.rs:76-81);
+//   * the schedule is generated from their names + component accesses exactly like
+//     `S::generate(systems)` in into_tickable (lib.rs:386-400);
+//   * per tick the executor asks the schedule for batches (Executor::execute_once,
+//     crates/scheduler/src/executor/mod.rs:191-236) and completes each dispatched system, which for
+//     a GPU system means "enqueued on the stream" (every dependent GPU system is stream-ordered
+//     behind it) and for a CPU system means "returned";
+//   * component columns live in the host World and are mirrored to HBM on demand: a column is
+//     (re)bound when its archetype changed structurally, uploaded when the host copy is newer,
+//     downloaded before a CPU system touches a column the device wrote.
+#include <string.h>
+
+#include <map>
+
+#include "host.h"
+
+using namespace recs::host;
+
+namespace {
+
+struct AppSystem {
+    bool gpu = false;
+    uint32_t gpu_id = 0;
+    recs_gpu_system_kind kind = RECS_SYS_QUERY_ADD;
+    std::string name;
+    std::vector<Param> params;
+    std::vector<recs_gpu_access> access;
+    recs_cpu_system_fn fn = nullptr;
+    void* user = nullptr;
+};
+
+struct Mirror {
+    uint64_t bound_version = ~0ull;  // archetype version the device buffer was bound at
+    bool host_dirty = true;          // host copy newer than device
+    bool device_dirty = false;       // device copy newer than host
+};
+
+typedef std::pair<uint32_t, uint64_t> ColKey;
+
+recs_param_token tok(uint32_t op, uint64_t comp = 0) {
+    recs_param_token t;
+    t.op = op;
+    t.component_id = comp;
+    return t;
+}
+
+// Parameter list of each GPU system kind == the signature of the reference function it replaces.
+std::vector<recs_param_token> gpu_kind_tokens(recs_gpu_system_kind kind, const uint64_t* c) {
+    switch (kind) {
+        case RECS_SYS_NBODY_GRAVITY:  // crates/n-body/src/lib.rs:106-110
+            return {tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_WRITE, c[1]), tok(RECS_PARAM_QUERY_BEGIN),
+                    tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_READ, c[2]), tok(RECS_PARAM_QUERY_END)};
+        case RECS_SYS_NBODY_MOVEMENT:      // :89
+        case RECS_SYS_RAIN_MOVEMENT:       // crates/rain-simulation/src/lib.rs:94
+        case RECS_SYS_NBODY_ACCELERATION:  // :97
+        case RECS_SYS_QUERY_ADD:           // crates/ecs_bench_suite/src/recs/simple_iter.rs:47
+            return {tok(RECS_PARAM_WRITE, c[0]), tok(RECS_PARAM_READ, c[1])};
+        case RECS_SYS_RAIN_GRAVITY:  // crates/rain-simulation/src/lib.rs:65
+        case RECS_SYS_RAIN_WIND:     // :86
+            return {tok(RECS_PARAM_WRITE, c[0])};
+        case RECS_SYS_RAIN_WIND_DIRECTION:  // :78
+            return {};
+    }
+    return {};
+}
+
+}  // namespace
+
+struct recs_app {
+    recs_gpu_ctx* gpu = nullptr;
+    recs_world* world = nullptr;
+    std::vector<AppSystem> systems;
+    recs_schedule* schedule = nullptr;
+    int32_t schedule_ordered = -1;
+    size_t scheduled_systems = 0;
+    std::vector<uint32_t> last_order, last_batch;
+    std::map<ColKey, Mirror> mirror;
+    std::string error;
+
+    int32_t fail(int32_t code, const std::string& msg) {
+        error = msg;
+        return code;
+    }
+};
+
+namespace {
+
+int32_t gpu_fail(recs_app* app, int32_t st) { return app->fail(st, recs_gpu_last_error(app->gpu)); }
+
+// Makes the device copy of (archetype, component) current before a GPU system uses it.
+int32_t ensure_on_device(recs_app* app, uint32_t arch, uint64_t comp) {
+    recs_world* w = app->world;
+    if (arch >= w->archetypes.size()) return app->fail(RECS_ERR_WORLD, "could not find archetype with the given index");
+    Archetype& a = w->archetypes[arch];
+    auto it = a.columns.find(comp);
+    if (it == a.columns.end()) return app->fail(RECS_ERR_MISSING_PARAMETER, "could not execute system due to missing parameter");
+    Mirror& m = app->mirror[ColKey(arch, comp)];
+    if (m.bound_version != a.version) {
+        if (m.device_dirty) return app->fail(RECS_ERR_STALE_BINDING, "archetype changed structurally while its device copy was newer; call recs_app_sync_to_host before mutating the world");
+        int32_t st = recs_gpu_bind_column(app->gpu, arch, comp, it->second.data.data(), it->second.elem ? it->second.elem : 1,
+                                          it->second.elem ? it->second.len : 0);
+        if (st != RECS_OK) return gpu_fail(app, st);
+        m.bound_version = a.version;
+        m.host_dirty = true;
+    }
+    if (m.host_dirty) {
+        int32_t st = recs_gpu_upload(app->gpu, arch, comp);
+        if (st != RECS_OK) return gpu_fail(app, st);
+        m.host_dirty = false;
+    }
+    return RECS_OK;
+}
+
+int32_t ensure_on_host(recs_app* app, uint32_t arch, uint64_t comp) {
+    auto it = app->mirror.find(ColKey(arch, comp));
+    if (it == app->mirror.end() || !it->second.device_dirty) return RECS_OK;
+    int32_t st = recs_gpu_download(app->gpu, arch, comp);
+    if (st != RECS_OK) return gpu_fail(app, st);
+    it->second.device_dirty = false;
+    return RECS_OK;
+}
+
+// Query membership of the system + residency of every column it touches, then the launch.
+int32_t run_gpu_system(recs_app* app, AppSystem& s) {
+    if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "GPU system registered on an application without a GPU context");
+    std::vector<uint32_t> archs = params_archetypes(*app->world, s.params);
+    std::vector<uint32_t> qarchs;
+    for (const Param& p : s.params)
+        if (p.op == RECS_PARAM_QUERY_BEGIN) qarchs = params_archetypes(*app->world, p.children);
+    int32_t st;
+    for (const Param& p : s.params) {
+        if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE)
+            for (uint32_t a : archs)
+                if ((st = ensure_on_device(app, a, p.comp)) != RECS_OK) return st;
+        if (p.op == RECS_PARAM_QUERY_BEGIN)
+            for (const Param& q : p.children)
+                if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
+                    for (uint32_t a : qarchs)
+                        if ((st = ensure_on_device(app, a, q.comp)) != RECS_OK) return st;
+    }
+    if ((st = recs_gpu_system_set_archetypes(app->gpu, s.gpu_id, archs.data(), (uint32_t)archs.size())) != RECS_OK)
+        return gpu_fail(app, st);
+    if (!qarchs.empty() || s.kind == RECS_SYS_NBODY_GRAVITY)
+        if ((st = recs_gpu_system_set_query_archetypes(app->gpu, s.gpu_id, qarchs.data(), (uint32_t)qarchs.size())) != RECS_OK)
+            return gpu_fail(app, st);
+    if ((st = recs_gpu_run_system(app->gpu, s.gpu_id, RECS_GPU_ASYNC)) != RECS_OK) return gpu_fail(app, st);
+    for (const Param& p : s.params)
+        if (p.op == RECS_PARAM_WRITE)
+            for (uint32_t a : archs) app->mirror[ColKey(a, p.comp)].device_dirty = true;
+    return RECS_OK;
+}
+
+// `SequentiallyIterable::run` for a CPU system (crates/ecs/src/systems/iteration.rs:26-57).
+int32_t run_cpu_system(recs_app* app, AppSystem& s) {
+    if (!params_controls_iteration(s.params)) {
+        // no iterating parameter: the function runs exactly once (iterate_once, iteration.rs:43)
+        s.fn(s.user, 0, 0, nullptr, 0);
+        return RECS_OK;
+    }
+    const std::vector<uint32_t> archs = params_archetypes(*app->world, s.params);
+    std::vector<void*> cols;
+    for (uint32_t a : archs) {
+        cols.clear();
+        uint64_t count = app->world->archetypes[a].entities.size();
+        for (const Param& p : s.params) {
+            if (p.op != RECS_PARAM_READ && p.op != RECS_PARAM_WRITE) continue;
+            int32_t st = ensure_on_host(app, a, p.comp);
+            if (st != RECS_OK) return st;
+            auto it = app->world->archetypes[a].columns.find(p.comp);
+            if (it == app->world->archetypes[a].columns.end())
+                return app->fail(RECS_ERR_MISSING_PARAMETER, "could not execute system due to missing parameter");
+            // RwLock try_read / try_write for the duration of the call (archetypes.rs:106-138)
+            st = recs_world_borrow_column(app->world, a, p.comp, p.op == RECS_PARAM_WRITE);
+            if (st != RECS_OK) {
+                for (const Param& q : s.params) {  // release what was taken so far
+                    if (&q == &p) break;
+                    if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
+                        recs_world_release_column(app->world, a, q.comp, q.op == RECS_PARAM_WRITE);
+                }
+                return app->fail(st, recs_world_last_error(app->world));
+            }
+            cols.push_back(it->second.data.data());
+        }
+        s.fn(s.user, a, count, cols.data(), (uint32_t)cols.size());
+        for (const Param& p : s.params) {
+            if (p.op != RECS_PARAM_READ && p.op != RECS_PARAM_WRITE) continue;
+            recs_world_release_column(app->world, a, p.comp, p.op == RECS_PARAM_WRITE);
+            if (p.op == RECS_PARAM_WRITE) app->mirror[ColKey(a, p.comp)].host_dirty = true;
+        }
+    }
+    return RECS_OK;
+}
+
+int32_t ensure_schedule(recs_app* app, int32_t ordered) {
+    if (app->schedule && app->schedule_ordered == ordered && app->scheduled_systems == app->systems.size()) return RECS_OK;
+    if (app->schedule) recs_schedule_destroy(app->schedule);
+    app->schedule = nullptr;
+    std::vector<recs_system_info> infos(app->systems.size());
+    for (size_t i = 0; i < app->systems.size(); ++i) {
+        infos[i].name = app->systems[i].name.c_str();
+        infos[i].n_access = (uint32_t)app->systems[i].access.size();
+        infos[i].access = app->systems[i].access.data();
+    }
+    int32_t st = recs_schedule_generate(infos.data(), (uint32_t)infos.size(), ordered, &app->schedule);
+    if (st != RECS_OK) return app->fail(st, "schedule generation failed");
+    recs_schedule_set_select_policy(app->schedule, 1);  // deterministic: oldest pending completion first
+    app->schedule_ordered = ordered;
+    app->scheduled_systems = app->systems.size();
+    return RECS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t recs_app_create(recs_gpu_ctx* gpu, recs_app** out) {
+    if (!out) return RECS_ERR_INVALID_ARGUMENT;
+    recs_app* app = new recs_app();
+    app->gpu = gpu;
+    recs_world_create(&app->world);
+    *out = app;
+    return RECS_OK;
+}
+
+int32_t recs_app_destroy(recs_app* app) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (app->schedule) recs_schedule_destroy(app->schedule);
+    recs_world_destroy(app->world);
+    delete app;
+    return RECS_OK;
+}
+
+const char* recs_app_last_error(recs_app* app) { return app ? app->error.c_str() : "null app"; }
+
+recs_world* recs_app_world(recs_app* app) { return app ? app->world : nullptr; }
+
+int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const uint64_t* ids, uint32_t n_ids,
+                                uint32_t* out_index) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "no GPU context: GPU systems cannot be registered (there is no CPU fallback)");
+    AppSystem s;
+    s.gpu = true;
+    s.kind = kind;
+    int32_t st = recs_gpu_system_create(app->gpu, kind, ids, n_ids, &s.gpu_id);
+    if (st != RECS_OK) return gpu_fail(app, st);
+    recs_gpu_system_desc desc;
+    if ((st = recs_gpu_system_describe(app->gpu, s.gpu_id, &desc)) != RECS_OK) return gpu_fail(app, st);
+    s.name = desc.name;
+    s.access.assign(desc.access, desc.access + desc.n_access);
+    const std::vector<recs_param_token> tokens = gpu_kind_tokens(kind, ids);
+    std::string err;
+    if (!parse_params(tokens.data(), (uint32_t)tokens.size(), &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
+    app->systems.push_back(s);
+    if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
+    return RECS_OK;
+}
+
+int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
+                                recs_cpu_system_fn fn, void* user, uint32_t* out_index) {
+    if (!app || !fn) return RECS_ERR_INVALID_ARGUMENT;
+    AppSystem s;
+    s.gpu = false;
+    s.name = name ? name : "system";
+    s.fn = fn;
+    s.user = user;
+    std::string err;
+    if (!parse_params(tokens, n_tokens, &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
+    params_accesses(s.params, &s.access);
+    app->systems.push_back(s);
+    if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
+    return RECS_OK;
+}
+
+int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    int32_t st = ensure_schedule(app, ordered ? 1 : 0);
+    if (st != RECS_OK) return st;
+    std::vector<uint32_t> batch(app->systems.size() + 1);
+    for (uint32_t tick = 0; tick < n_ticks; ++tick) {
+        app->last_order.clear();
+        app->last_batch.clear();
+        uint32_t batch_no = 0;
+        for (;;) {  // Executor::execute_once
+            uint32_t got = 0;
+            st = recs_schedule_next_batch(app->schedule, RECS_REACTION_RETURN_ERROR, batch.data(), (uint32_t)batch.size(), &got);
+            if (st == RECS_SCHEDULE_NEW_TICK) break;
+            if (st != RECS_OK) return app->fail(st, "schedule error");
+            for (uint32_t i = 0; i < got; ++i) {
+                AppSystem& s = app->systems[batch[i]];
+                st = s.gpu ? run_gpu_system(app, s) : run_cpu_system(app, s);
+                if (st != RECS_OK) return st;
+                app->last_order.push_back(batch[i]);
+                app->last_batch.push_back(batch_no);
+            }
+            // completion == dropping the SystemExecutionGuard (lib.rs:525-557)
+            for (uint32_t i = 0; i < got; ++i) recs_schedule_complete(app->schedule, batch[i]);
+            ++batch_no;
+        }
+    }
+    return RECS_OK;
+}
+
+int32_t recs_app_last_tick_order(recs_app* app, uint32_t* out_order, uint32_t* out_batch_of, uint32_t cap, uint32_t* out_n) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (out_n) *out_n = (uint32_t)app->last_order.size();
+    for (uint32_t i = 0; i < app->last_order.size() && i < cap; ++i) {
+        if (out_order) out_order[i] = app->last_order[i];
+        if (out_batch_of) out_batch_of[i] = app->last_batch[i];
+    }
+    return RECS_OK;
+}
+
+int32_t recs_app_sync_to_host(recs_app* app) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    for (auto& kv : app->mirror) {
+        if (!kv.second.device_dirty) continue;
+        int32_t st = recs_gpu_download(app->gpu, kv.first.first, kv.first.second);
+        if (st != RECS_OK) return gpu_fail(app, st);
+        kv.second.device_dirty = false;
+    }
+    if (app->gpu) {
+        int32_t st = recs_gpu_synchronize(app->gpu);
+        if (st != RECS_OK) return gpu_fail(app, st);
+    }
+    return RECS_OK;
+}
+
+int32_t recs_app_mark_host_dirty(recs_app* app, uint32_t archetype) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    for (auto& kv : app->mirror)
+        if (kv.first.first == archetype) kv.second.host_dirty = true;
+    return RECS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,137 @@
+"""Application run loop (crates/ecs/src/lib.rs:314-341) with CPU systems (no GPU needed) and, on
+the GPU box, the n-body benchmark assembled exactly like
+crates/ecs_bench_suite/src/recs/n_body.rs:54-63 behind the World / System / Schedule contract."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from recs_b200 import _lib, ecs, scenes
+from tests.util import rel_err_rows
+
+POS, MASS, VEL, ACC = 1, 2, 3, 4
+F3 = np.dtype((np.float32, 3))
+
+
+def _f32(ptr, count, width=1):
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(count * width,))
+
+
+def test_cpu_application_runs_systems_in_schedule_order():
+    app = ecs.Application(gpu=None)
+    w = app.world
+    w.register_component(POS, F3, "Position")
+    w.register_component(VEL, F3, "Velocity")
+    n = 10
+    w.create_entities(n, {POS: np.zeros((n, 3), np.float32), VEL: np.ones((n, 3), np.float32)})
+    log = []
+
+    def movement(arch, count, cols):  # (Write<Position>, Read<Velocity>)
+        log.append("movement")
+        p, v = _f32(cols[0], count, 3), _f32(cols[1], count, 3)
+        p += v * np.float32(0.5)
+
+    def double_velocity(arch, count, cols):  # (Write<Velocity>,)
+        log.append("double_velocity")
+        _f32(cols[0], count, 3)[:] *= np.float32(2.0)
+
+    def tick_counter(arch, count, cols):  # no parameters: runs once per tick
+        log.append("tick_counter")
+
+    app.add_cpu_system("movement", [("write", POS), ("read", VEL)], movement)
+    app.add_cpu_system("double_velocity", [("write", VEL)], double_velocity)
+    app.add_cpu_system("tick_counter", [], tick_counter)
+    app.run(2)
+    # readers of Velocity run before its writer within a tick (schedule/mod.rs:1208-1224)
+    assert [x for x in log if x != "tick_counter"] == ["movement", "double_velocity"] * 2
+    assert log.count("tick_counter") == 2
+    assert np.array_equal(w.column(1, POS), np.full((n, 3), 0.5 + 1.0, np.float32))
+    assert np.array_equal(w.column(1, VEL), np.full((n, 3), 4.0, np.float32))
+    order, batches = app.last_tick_order()
+    assert [app.system_names[i] for i in order if app.system_names[i] != "tick_counter"] == ["movement", "double_velocity"]
+
+
+def test_gpu_system_without_gpu_context_is_refused():
+    app = ecs.Application(gpu=None)
+    with pytest.raises(ecs.EcsError) as e:
+        app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL])
+    assert e.value.code == 2  # RECS_ERR_NO_DEVICE: no CPU fallback for GPU systems
+
+
+def _nbody_app(gpu, n, seed, ticks_counter):
+    app = ecs.Application(gpu=gpu)
+    w = app.world
+    w.register_component(POS, F3, "Position")
+    w.register_component(MASS, np.float32, "Mass")
+    w.register_component(VEL, F3, "Velocity")
+    w.register_component(ACC, F3, "Acceleration")
+    # registration order of the benchmark (n_body.rs:54-59)
+    app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+    app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+    app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+    app.add_cpu_system("benchmark_system", [], lambda a, c, cols: ticks_counter.append(1))
+    pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), seed)
+    # create_planet_entity: app.create_entity((position, mass, velocity, acceleration)) (scenes.rs:108-117)
+    w.create_entities(n, {POS: pos, MASS: mass, VEL: vel, ACC: acc})
+    return app, (pos, mass, vel, acc)
+
+
+@pytest.mark.gpu
+def test_nbody_benchmark_through_application(gpu_ctx, nbody_oracle):
+    ticks = []
+    n = 1000
+    app, (pos, mass, vel, acc) = _nbody_app(gpu_ctx, n, 1, ticks)
+    w = app.world
+    assert w.archetype_count() == 2 and w.archetype_entities(1) == [(k, 0) for k in range(n)]
+    app.run(1)
+    order, batches = app.last_tick_order()
+    names = [app.system_names[i] for i in order]
+    assert [x for x in names if x != "benchmark_system"] == ["gravity", "movement", "acceleration"]
+    app.sync_to_host()
+    nbody_oracle.run_sequential(pos, mass, vel, acc, 1)
+    assert np.array_equal(w.column(1, POS).view(np.uint32), pos.view(np.uint32))
+    assert rel_err_rows(w.column(1, ACC), acc).max() <= 1e-4
+    assert rel_err_rows(w.column(1, VEL), vel).max() <= 1e-4
+    app.run(9)
+    assert len(ticks) == 10
+    app.sync_to_host()
+    nbody_oracle.run_sequential(pos, mass, vel, acc, 9)
+    assert rel_err_rows(w.column(1, POS), pos, floor=1.0).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_structural_change_rebinds_device_columns(gpu_ctx, nbody_oracle):
+    """Entities created between ticks (command playback, lib.rs:321-323) move the host columns; the
+    device mirror must re-bind and see the new rows."""
+    ticks = []
+    app, (pos, mass, vel, acc) = _nbody_app(gpu_ctx, 300, 2, ticks)
+    w = app.world
+    app.run(1)
+    app.sync_to_host()
+    extra = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(50), 9)
+    w.create_entities(50, {POS: extra[0], MASS: extra[1], VEL: extra[2], ACC: extra[3]})
+    assert w.archetype_entities(1)[-1] == (349, 0)
+    ref = [np.ascontiguousarray(w.column(1, c).copy()) for c in (POS, MASS, VEL, ACC)]
+    app.run(1)
+    app.sync_to_host()
+    nbody_oracle.run_sequential(ref[0], ref[1], ref[2], ref[3], 1)
+    assert np.array_equal(w.column(1, POS).view(np.uint32), ref[0].view(np.uint32))
+    assert rel_err_rows(w.column(1, ACC), ref[3]).max() <= 1e-4
+
+
+@pytest.mark.gpu
+def test_cpu_system_sees_device_results(gpu_ctx):
+    """A CPU system reading a column a GPU system wrote gets the downloaded values (the executor
+    orders the copy like the reference orders the channel drop)."""
+    seen = []
+    app = ecs.Application(gpu=gpu_ctx)
+    w = app.world
+    w.register_component(POS, F3, "Position")
+    w.register_component(VEL, F3, "Velocity")
+    n = 64
+    w.create_entities(n, {POS: np.zeros((n, 3), np.float32), VEL: np.full((n, 3), 2.0, np.float32)})
+    app.add_gpu_system(_lib.SYS_QUERY_ADD, [POS, VEL], "add")  # pos += vel
+    app.add_cpu_system("observer", [("read", POS)], lambda a, c, cols: seen.append(_f32(cols[0], c, 3).copy()))
+    app.run(3)
+    # observer reads Position, add writes it: readers first within a tick -> sees 0, 2, 4
+    assert [float(s[0]) for s in seen] == [0.0, 2.0, 4.0]

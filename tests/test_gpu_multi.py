@@ -1,0 +1,33 @@
+"""Index-sharded n-body over NCCL on >= 2 GPUs (skipped on a single-GPU box)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_count():
+    try:
+        out = subprocess.run(["nvidia-smi", "-L"], capture_output=True, text=True).stdout
+        return sum(1 for line in out.splitlines() if line.startswith("GPU "))
+    except OSError:
+        return 0
+
+
+@pytest.mark.parametrize("bodies,ticks", [(10000, 1), (5000, 4), (300, 2)])
+def test_sharded_ticks_match_oracle(bodies, ticks):
+    n_gpu = _gpu_count()
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n_gpu < 4 else 4
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), "tools/multi_gpu_check.py", str(bodies), str(ticks)]
+    proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]

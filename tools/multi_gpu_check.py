@@ -1,0 +1,60 @@
+"""Multi-rank parity check of the index-sharded n-body path (run under torchrun, one rank per GPU).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port P \
+        tools/multi_gpu_check.py [bodies] [ticks]
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import torch.distributed as dist  # noqa: E402
+
+import oracle  # noqa: E402  (checker)
+from recs_b200 import GpuContext, scenes  # noqa: E402
+from recs_b200.nbody import NBodyGpuApp  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+dist.init_process_group("gloo")
+ctx = GpuContext(device=local, rank=rank, world_size=world, use_cuda_graph=False)
+uid = [ctx.comm_unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+ctx.comm_init(uid[0])
+rb, re = ctx.shard_rows(n)
+pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 5)
+ref = [a.copy() for a in (pos, mass, vel, acc)]
+app = NBodyGpuApp(ctx, pos, mass, vel, acc)
+app.upload()
+app.tick(ticks)
+app.download()
+ctx.synchronize()
+orc = oracle.load_nbody()
+orc.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks)
+
+
+def rel(got, want, floor=0.0):
+    num = np.linalg.norm(got.astype(np.float64) - want, axis=1)
+    den = np.maximum(np.linalg.norm(want.astype(np.float64), axis=1), floor)
+    return float((num / np.where(den == 0, 1, den)).max()) if len(got) else 0.0
+
+
+errs = {
+    "pos": rel(pos[rb:re], ref[0][rb:re], 1.0),
+    "vel": rel(vel[rb:re], ref[2][rb:re], 1.0),
+    "acc": rel(acc[rb:re], ref[3][rb:re]),
+}
+ok = errs["pos"] <= 1e-4 and errs["vel"] <= 1e-4 and errs["acc"] <= (1e-4 if ticks == 1 else 1e-3)
+if ticks == 1:
+    ok = ok and np.array_equal(pos[rb:re].view(np.uint32), ref[0][rb:re].view(np.uint32))
+results = [None] * world
+dist.all_gather_object(results, (rank, rb, re, errs, bool(ok)))
+if rank == 0:
+    for r in results:
+        print(r)
+    print("MULTI_GPU_CHECK", "OK" if all(r[4] for r in results) else "FAILED", f"bodies={n} ticks={ticks} world={world}")
+ctx.close()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
