@@ -222,9 +222,10 @@ def run_reference_arm(args) -> None:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def sampled_parity(app, host_state, rb, re, n_rows=8):
-    """Parity gate of the run: accelerations of a few rows of this rank's shard after
-    the first tick against the oracle, all j."""
+def sampled_parity(app, host_state, rb, re, n_rows=32):
+    """Parity gate of the run: accelerations of sampled rows of this rank's shard after
+    the first tick against the oracle, all j.  Returns max norm-wise relative errors
+    (gpu vs reference-order f32, gpu vs f64, reference-order f32 vs f64)."""
     import oracle
 
     orc = oracle.load_nbody()
@@ -232,8 +233,11 @@ def sampled_parity(app, host_state, rb, re, n_rows=8):
     rows = np.random.default_rng(11).choice(np.arange(rb, re), size=min(n_rows, re - rb), replace=False)
     ref32, ref64 = orc.gravity_sample(pos0, mass0, rows)
     got = app.acc[rows].astype(np.float64)
-    err = np.linalg.norm(got - ref32, axis=1) / np.maximum(np.linalg.norm(ref32, axis=1), 1e-30)
-    return float(err.max())
+
+    def rel(a, b):
+        return float((np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)).max())
+
+    return rel(got, ref32.astype(np.float64)), rel(got, ref64), rel(ref32.astype(np.float64), ref64)
 
 
 def run_gpu_arm(args) -> None:
@@ -291,7 +295,8 @@ def run_gpu_arm(args) -> None:
     app.upload()
     app.tick(1)
     app.download()
-    parity_err = max_over_ranks(sampled_parity(app, (pos0, mass0), rb, re))
+    perr = sampled_parity(app, (pos0, mass0), rb, re)
+    parity_err, parity_f64, oracle_f64 = (max_over_ranks(x) for x in perr)
     # positions after tick 1 must be bit-exact (movement precedes acceleration)
     import oracle
 
@@ -419,7 +424,9 @@ def run_gpu_arm(args) -> None:
             "gpu_launches": int(round(launches_per_step * steps)),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "parity": {"acc_max_rel_err_vs_oracle": parity_err, "tolerance": 1e-4, "pos_bit_exact_after_tick1": pos_exact},
+            "parity": {"acc_max_rel_err_vs_oracle": parity_err, "tolerance": 1e-4, "pos_bit_exact_after_tick1": pos_exact,
+                       "acc_max_rel_err_vs_f64": parity_f64, "oracle_f32_order_vs_f64": oracle_f64, "rows_per_rank": 32},
+            "step_ms": [round(x, 3) for x in step_ms],
             "wall_ms_per_step_incl_flush": wall / steps * 1e3,
             "extras": extras,
         }

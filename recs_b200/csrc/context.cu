@@ -67,7 +67,7 @@ struct recs_gpu_ctx {
     cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
     int sm_count = 148;
     int grav_ctas_per_sm = 2;
-    int grav_variant = 0;
+    int grav_variant = 2;  // 2 rows per thread, 4 CTAs per SM: fastest in profiles/r01_gravity_variant_sweep*.txt
 
     std::map<ColKey, Column> columns;
     std::vector<System> systems;

@@ -125,6 +125,12 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
             az[r] = 0ull;
         }
     };
+    // Partial sums leave the registers every kGravFlushTiles tiles: the first flush of an
+    // (i-block, CTA) fragment stores, later ones add in place (the slot is owned by this CTA, so
+    // the order is fixed).  Keeps every f32 accumulation chain <= 32 tiles x 128 pairs long, which
+    // holds the summation error ~1e-6 instead of the ~2e-5 a 500 000-term chain reaches.
+    bool frag_started = false;
+    uint32_t tiles_in_regs = 0;
     auto flush = [&](uint32_t iblock) {
         float4* dst = a.frags + static_cast<size_t>(a.launch.frag_base + blockIdx.x + iblock) * kGravRows;
 #pragma unroll
@@ -133,8 +139,21 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
             ptx::unpack(ax[r], x0, x1);
             ptx::unpack(ay[r], y0, y1);
             ptx::unpack(az[r], z0, z1);
-            dst[r * kGravConsumerThreads + tid] = make_float4(x0 + x1, y0 + y1, z0 + z1, 0.f);
+            float4 v = make_float4(x0 + x1, y0 + y1, z0 + z1, 0.f);
+            float4* slot = dst + r * kGravConsumerThreads + tid;
+            if (frag_started) {
+                const float4 prev = *slot;
+                v.x += prev.x;
+                v.y += prev.y;
+                v.z += prev.z;
+            }
+            *slot = v;
+            ax[r] = 0ull;
+            ay[r] = 0ull;
+            az[r] = 0ull;
         }
+        frag_started = true;
+        tiles_in_regs = 0;
     };
 
     load_rows(b);
@@ -183,14 +202,18 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
 
+        ++tiles_in_regs;
         if (++v == n_vtiles) {
             v = 0;
             flush(b);
             ++b;
+            frag_started = false;
             if (k + 1 < span.count) load_rows(b);
+        } else if (tiles_in_regs == kGravFlushTiles) {
+            flush(b);
         }
     }
-    if (v != 0) flush(b);
+    if (tiles_in_regs != 0) flush(b);
 }
 
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {

@@ -16,7 +16,7 @@ def _declared(header):
 
 
 def test_library_exports_every_declared_symbol():
-    from recs_b200 import _lib
+    from recs_b200 import _lib, ecs
 
     names = _declared("recs_gpu.h")
     assert len(names) >= 30
@@ -24,6 +24,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(_lib.lib, name), f"librecs_gpu.so does not export {name}"
     # and the ctypes table binds exactly the declared set
     assert sorted(_lib.GPU_SYMBOLS) == names
+
+    ecs_names = [n for n in _declared("recs_ecs.h") if n not in names and n != "recs_cpu_system_fn"]
+    assert len(ecs_names) >= 40
+    for name in ecs_names:
+        assert hasattr(_lib.lib, name), f"librecs_gpu.so does not export {name}"
+    assert sorted(ecs.ECS_SYMBOLS) == sorted(ecs_names)
 
 
 def test_abi_version_and_default_config():
