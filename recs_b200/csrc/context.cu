@@ -67,7 +67,7 @@ struct recs_gpu_ctx {
     cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
     int sm_count = 148;
     int grav_ctas_per_sm = 2;
-    int grav_variant = 2;  // 2 rows per thread, 4 CTAs per SM: fastest in profiles/r01_gravity_variant_sweep*.txt
+    int grav_variant = 13;  // 2 rows/thread, 2 CTAs/SM, unroll 8, detector fast path (profiles/r01_gravity_variant_sweep*.txt)  // see profiles/r01_gravity_variant_sweep*.txt
 
     std::map<ColKey, Column> columns;
     std::vector<System> systems;
@@ -635,7 +635,7 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
               gravity_prepare() == cudaSuccess;
     if (ok) {
         const char* v = getenv("RECS_GPU_GRAVITY_VARIANT");  // tuning knob; default chosen by measurement
-        if (v && v[0] >= '0' && v[0] < '0' + kGravVariantCount) c->grav_variant = v[0] - '0';
+        if (v && atoi(v) >= 0 && atoi(v) < kGravVariantCount) c->grav_variant = atoi(v);
         c->grav_ctas_per_sm = gravity_max_ctas_per_sm(c->grav_variant);
         ok = c->grav_ctas_per_sm > 0;
     }

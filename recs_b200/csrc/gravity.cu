@@ -52,12 +52,68 @@ __host__ __device__ inline uint32_t cta_of(uint32_t u, uint32_t grid, uint32_t u
     return rem + (u - big) / q;
 }
 
-template <int RI, int MIN_CTAS>
+// One pair-interaction: two bodies j (the f32x2 lanes) against one body i.
+//   MASKED  = true : the reference's `if distance_squared <= f32::EPSILON { zero }` applied exactly
+//                    (compare + select per lane; also turns rsqrt(0) = inf of the self pair into 0).
+//   MASKED  = false: no mask; instead the smallest d2 seen is tracked (two FMNMX) so the caller can
+//                    detect that this tile needed the mask and redo it exactly.
+template <bool MASKED>
+__device__ __forceinline__ void pair_interaction(const f32x2 xj, const f32x2 yj, const f32x2 zj, const f32x2 gm,
+                                                 const float nx, const float ny, const float nz, const float eps,
+                                                 f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {
+    const f32x2 dx = ptx::add2(xj, ptx::pack(nx, nx));
+    const f32x2 dy = ptx::add2(yj, ptx::pack(ny, ny));
+    const f32x2 dz = ptx::add2(zj, ptx::pack(nz, nz));
+    f32x2 d2 = ptx::mul2(dx, dx);
+    d2 = ptx::fma2(dy, dy, d2);
+    d2 = ptx::fma2(dz, dz, d2);
+    float d2a, d2b;
+    ptx::unpack(d2, d2a, d2b);
+    float ra = ptx::rsqrt_approx(d2a);
+    float rb = ptx::rsqrt_approx(d2b);
+    if (MASKED) {
+        ra = d2a > eps ? ra : 0.f;
+        rb = d2b > eps ? rb : 0.f;
+    } else {
+        dmin_a = fminf(dmin_a, d2a);
+        dmin_b = fminf(dmin_b, d2b);
+    }
+    const f32x2 rinv = ptx::pack(ra, rb);
+    const f32x2 rinv2 = ptx::mul2(rinv, rinv);
+    f32x2 s = ptx::mul2(gm, rinv);
+    s = ptx::mul2(s, rinv2);  // G*m / d2 / sqrt(d2)
+    ax = ptx::fma2(s, dx, ax);
+    ay = ptx::fma2(s, dy, ay);
+    az = ptx::fma2(s, dz, az);
+}
+
+template <int RI, int UNROLL, bool MASKED>
+__device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const float (&nxi)[RI], const float (&nyi)[RI],
+                                          const float (&nzi)[RI], const float eps, f32x2 (&ax)[RI], f32x2 (&ay)[RI],
+                                          f32x2 (&az)[RI], float& dmin_a, float& dmin_b) {
+#pragma unroll UNROLL
+    for (int p = 0; p < kGravTile / 2; ++p) {
+        const float4 lo = t[2 * p];      // x0 x1 y0 y1
+        const float4 hi = t[2 * p + 1];  // z0 z1 gm0 gm1
+        const f32x2 xj = ptx::pack(lo.x, lo.y);
+        const f32x2 yj = ptx::pack(lo.z, lo.w);
+        const f32x2 zj = ptx::pack(hi.x, hi.y);
+        const f32x2 gm = ptx::pack(hi.z, hi.w);
+#pragma unroll
+        for (int r = 0; r < RI; ++r)
+            pair_interaction<MASKED>(xj, yj, zj, gm, nxi[r], nyi[r], nzi[r], eps, ax[r], ay[r], az[r], dmin_a, dmin_b);
+    }
+}
+
+template <int RI, int MIN_CTAS, int UNROLL, bool DETECT>
 __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(const GravityArgs a) {
     constexpr int kGravRowsPerThread = RI;
     constexpr int kGravRows = kGravConsumerThreads * RI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
+    // running sums of the current i-block, one private float4 slot per (row, thread): the second
+    // level of the summation (level 1 = one tile of 128 pairs in registers)
+    float4* run = reinterpret_cast<float4*>(smem_raw + kGravSmemBytes);
     __shared__ __align__(8) uint64_t full_bar[kGravStages];
     __shared__ __align__(8) uint64_t empty_bar[kGravStages];
 
@@ -104,7 +160,6 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
     uint32_t v = span.begin % n_vtiles;
 
     float nxi[kGravRowsPerThread], nyi[kGravRowsPerThread], nzi[kGravRowsPerThread];
-    f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
 
     auto load_rows = [&](uint32_t iblock) {
 #pragma unroll
@@ -120,40 +175,15 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
             nxi[r] = -x;
             nyi[r] = -y;
             nzi[r] = -z;
-            ax[r] = 0ull;
-            ay[r] = 0ull;
-            az[r] = 0ull;
+            run[r * kGravConsumerThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    // Partial sums leave the registers every kGravFlushTiles tiles: the first flush of an
-    // (i-block, CTA) fragment stores, later ones add in place (the slot is owned by this CTA, so
-    // the order is fixed).  Keeps every f32 accumulation chain <= 32 tiles x 128 pairs long, which
-    // holds the summation error ~1e-6 instead of the ~2e-5 a 500 000-term chain reaches.
-    bool frag_started = false;
-    uint32_t tiles_in_regs = 0;
+    // the (CTA, i-block) fragment is written exactly once, when the CTA leaves the i-block
     auto flush = [&](uint32_t iblock) {
         float4* dst = a.frags + static_cast<size_t>(a.launch.frag_base + blockIdx.x + iblock) * kGravRows;
 #pragma unroll
-        for (int r = 0; r < kGravRowsPerThread; ++r) {
-            float x0, x1, y0, y1, z0, z1;
-            ptx::unpack(ax[r], x0, x1);
-            ptx::unpack(ay[r], y0, y1);
-            ptx::unpack(az[r], z0, z1);
-            float4 v = make_float4(x0 + x1, y0 + y1, z0 + z1, 0.f);
-            float4* slot = dst + r * kGravConsumerThreads + tid;
-            if (frag_started) {
-                const float4 prev = *slot;
-                v.x += prev.x;
-                v.y += prev.y;
-                v.z += prev.z;
-            }
-            *slot = v;
-            ax[r] = 0ull;
-            ay[r] = 0ull;
-            az[r] = 0ull;
-        }
-        frag_started = true;
-        tiles_in_regs = 0;
+        for (int r = 0; r < kGravRowsPerThread; ++r)
+            dst[r * kGravConsumerThreads + tid] = run[r * kGravConsumerThreads + tid];
     };
 
     load_rows(b);
@@ -165,55 +195,47 @@ __global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(c
         ptx::mbar_wait(&full_bar[stage], phase);
         const float4* t = tiles + stage * kGravTile;
 
-#pragma unroll 2
-        for (int p = 0; p < kGravTile / 2; ++p) {
-            const float4 lo = t[2 * p];      // x0 x1 y0 y1
-            const float4 hi = t[2 * p + 1];  // z0 z1 gm0 gm1
-            const f32x2 xj = ptx::pack(lo.x, lo.y);
-            const f32x2 yj = ptx::pack(lo.z, lo.w);
-            const f32x2 zj = ptx::pack(hi.x, hi.y);
-            const f32x2 gm = ptx::pack(hi.z, hi.w);
+        f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
 #pragma unroll
-            for (int r = 0; r < kGravRowsPerThread; ++r) {
-                const f32x2 dx = ptx::add2(xj, ptx::pack(nxi[r], nxi[r]));
-                const f32x2 dy = ptx::add2(yj, ptx::pack(nyi[r], nyi[r]));
-                const f32x2 dz = ptx::add2(zj, ptx::pack(nzi[r], nzi[r]));
-                f32x2 d2 = ptx::mul2(dx, dx);
-                d2 = ptx::fma2(dy, dy, d2);
-                d2 = ptx::fma2(dz, dz, d2);
-                float d2a, d2b;
-                ptx::unpack(d2, d2a, d2b);
-                float ra = ptx::rsqrt_approx(d2a);
-                float rb = ptx::rsqrt_approx(d2b);
-                // `if distance_squared <= f32::EPSILON { return zero }` (lib.rs:118-120); also
-                // turns rsqrt(0) = inf of the self pair into an exact zero contribution.
-                ra = d2a > eps ? ra : 0.f;
-                rb = d2b > eps ? rb : 0.f;
-                const f32x2 rinv = ptx::pack(ra, rb);
-                const f32x2 rinv2 = ptx::mul2(rinv, rinv);
-                f32x2 s = ptx::mul2(gm, rinv);
-                s = ptx::mul2(s, rinv2);  // G*m / d2 / sqrt(d2)
-                ax[r] = ptx::fma2(s, dx, ax[r]);
-                ay[r] = ptx::fma2(s, dy, ay[r]);
-                az[r] = ptx::fma2(s, dz, az[r]);
+        for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
+        float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
+        if (DETECT) {
+            tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+            if (fminf(dmin_a, dmin_b) <= eps) {
+                // some pair of this thread in this tile is at or below epsilon (its own body, or a
+                // coincident one): the unmasked sums are garbage (inf/NaN) -- redo the tile exactly.
+#pragma unroll
+                for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
+                tile_loop<RI, 1, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
             }
+        } else {
+            tile_loop<RI, UNROLL, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+        }
+        // level-2 accumulation in shared memory (private slots, no synchronisation needed)
+#pragma unroll
+        for (int r = 0; r < kGravRowsPerThread; ++r) {
+            float x0, x1, y0, y1, z0, z1;
+            ptx::unpack(ax[r], x0, x1);
+            ptx::unpack(ay[r], y0, y1);
+            ptx::unpack(az[r], z0, z1);
+            float4 acc = run[r * kGravConsumerThreads + tid];
+            acc.x += x0 + x1;
+            acc.y += y0 + y1;
+            acc.z += z0 + z1;
+            run[r * kGravConsumerThreads + tid] = acc;
         }
 
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
 
-        ++tiles_in_regs;
         if (++v == n_vtiles) {
             v = 0;
             flush(b);
             ++b;
-            frag_started = false;
             if (k + 1 < span.count) load_rows(b);
-        } else if (tiles_in_regs == kGravFlushTiles) {
-            flush(b);
         }
     }
-    if (tiles_in_regs != 0) flush(b);
+    if (v != 0) flush(b);
 }
 
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
@@ -275,28 +297,56 @@ __global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm,
 
 namespace {
 typedef void (*GravityKernel)(const GravityArgs);
-const GravityVariant kVariants[kGravVariantCount] = {{4, 2}, {4, 3}, {2, 4}, {3, 3}};
+//                                                 rows/thread, CTAs/SM
+const GravityVariant kVariants[kGravVariantCount] = {{4, 2}, {2, 4}, {3, 3}, {2, 4}, {4, 2}, {3, 3}, {2, 4}, {2, 3},
+                                                      {2, 2}, {2, 3}, {3, 3}, {4, 2}, {3, 2}, {2, 2}, {4, 2}, {3, 2}};
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
-            return nbody_gravity_kernel<4, 2>;
+            return nbody_gravity_kernel<4, 2, 2, false>;  // exact mask everywhere
         case 1:
-            return nbody_gravity_kernel<4, 3>;
+            return nbody_gravity_kernel<2, 4, 2, false>;
         case 2:
-            return nbody_gravity_kernel<2, 4>;
+            return nbody_gravity_kernel<3, 3, 2, false>;
         case 3:
-            return nbody_gravity_kernel<3, 3>;
+            return nbody_gravity_kernel<2, 4, 2, true>;   // detector fast path + exact redo
+        case 4:
+            return nbody_gravity_kernel<4, 2, 2, true>;
+        case 5:
+            return nbody_gravity_kernel<3, 3, 2, true>;
+        case 6:
+            return nbody_gravity_kernel<2, 4, 4, true>;
+        case 7:
+            return nbody_gravity_kernel<2, 3, 4, true>;
+        case 8:
+            return nbody_gravity_kernel<2, 2, 16, true>;
+        case 9:
+            return nbody_gravity_kernel<2, 3, 8, true>;
+        case 10:
+            return nbody_gravity_kernel<3, 3, 4, true>;
+        case 11:
+            return nbody_gravity_kernel<4, 2, 4, true>;
+        case 12:
+            return nbody_gravity_kernel<3, 2, 4, true>;
+        case 13:
+            return nbody_gravity_kernel<2, 2, 8, true>;
+        case 14:
+            return nbody_gravity_kernel<4, 2, 8, true>;
+        case 15:
+            return nbody_gravity_kernel<3, 2, 8, true>;
     }
     return nullptr;
 }
 }  // namespace
 
 GravityVariant gravity_variant(int index) { return kVariants[index]; }
+// tile ring + the running-sum slots of one i-block
+static int gravity_smem_bytes(int variant) { return kGravSmemBytes + kVariants[variant].rows() * (int)sizeof(float4); }
 
 cudaError_t gravity_prepare() {
     for (int v = 0; v < kGravVariantCount; ++v) {
         cudaError_t e = cudaFuncSetAttribute(variant_kernel(v), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             kGravSmemBytes);
+                                             gravity_smem_bytes(v));
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -305,14 +355,14 @@ cudaError_t gravity_prepare() {
 int gravity_max_ctas_per_sm(int variant) {
     int n = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, variant_kernel(variant), kGravThreads,
-                                                      kGravSmemBytes) != cudaSuccess)
+                                                      gravity_smem_bytes(variant)) != cudaSuccess)
         return 0;
     return n;
 }
 
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s) {
     if (a.launch.n_vtiles == 0 || a.launch.n_iblocks == 0) return cudaSuccess;
-    variant_kernel(a.variant)<<<a.launch.grid, kGravThreads, kGravSmemBytes, s>>>(a);
+    variant_kernel(a.variant)<<<a.launch.grid, kGravThreads, gravity_smem_bytes(a.variant), s>>>(a);
     return cudaGetLastError();
 }
 

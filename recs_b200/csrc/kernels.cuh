@@ -13,7 +13,6 @@ constexpr int kGravThreads = kGravConsumerThreads + 32;        // + 1 TMA produc
 constexpr int kGravMaxRowsPerThread = 4;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
-constexpr int kGravFlushTiles = 32;                            // tiles summed in registers between fragment updates
 constexpr int kGravTileBytes = kGravTile * 16;                 // 4 KiB
 constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic smem
 
@@ -25,7 +24,7 @@ struct GravityVariant {
     int min_ctas;         // __launch_bounds__ residency target
     int rows() const { return kGravConsumerThreads * rows_per_thread; }  // rows per i-block
 };
-constexpr int kGravVariantCount = 4;
+constexpr int kGravVariantCount = 16;
 GravityVariant gravity_variant(int index);
 
 struct GravityLaunch {

@@ -11,10 +11,16 @@ typedef unsigned long long u64;
 #define ALU(x, y) asm volatile("lop3.b32 %0, %0, %1, %1, 0x96;" : "+r"(x) : "r"(y))
 #define FSELOP(x, y, p) asm volatile("{.reg .pred q; setp.ne.u32 q, %2, 0; selp.f32 %0, %0, %1, q;}" : "+f"(x) : "f"(y), "r"(p))
 #define MUFU(x) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(x))
+#define FMNMX3(x, y, z) asm volatile("min.f32 %0, %0, %1, %2;" : "+f"(x) : "f"(y), "f"(z))
+#define MASKSEL(r, d, eps) asm volatile("{.reg .pred q; setp.gt.f32 q, %1, %2; selp.f32 %0, %0, 0f00000000, q;}" : "+f"(r) : "f"(d), "f"(eps))
 #define FMNMX(x, y) asm volatile("max.f32 %0, %0, %1;" : "+f"(x) : "f"(y))
 
 template <int MODE>
 __global__ void __launch_bounds__(256, 4) k(int iters, float* sink, u64* cyc) {
+    __shared__ float4 sm[512];
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sm[i] = make_float4(1.f + i, 2.f, 3.f, 4.f);
+    __syncthreads();
+    float4 l0 = make_float4(0, 0, 0, 0), l1 = l0;
     u64 a[8];
     float f[8];
     unsigned x[8];
@@ -29,6 +35,7 @@ __global__ void __launch_bounds__(256, 4) k(int iters, float* sink, u64* cyc) {
     asm("mov.b64 %0, {%1,%2};" : "=l"(c) : "f"(1e-6f), "f"(-1e-6f));
     float fm = 0.99999f, fc = 1e-6f;
     unsigned y = blockIdx.x + 12345;
+    const unsigned smbase = (unsigned)__cvta_generic_to_shared(sm);
     long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -90,6 +97,60 @@ __global__ void __launch_bounds__(256, 4) k(int iters, float* sink, u64* cyc) {
                     MUFU(f[i]); MUFU(f[i + 2]);
                     FMNMX(f[i + 4], fm); FMNMX(f[i + 6], fc); FMNMX(f[i + 4], fc); FMNMX(f[i + 6], fm);
                 }
+            } else if (MODE == 14) {  // exact mask: 12 FFMA2 + 2 MUFU + 2 (FSETP+FSEL)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    MASKSEL(f[i], f[i + 4], fc); MASKSEL(f[i + 2], f[i + 6], fc);
+                }
+            } else if (MODE == 15) {  // detector: 12 FFMA2 + 2 MUFU + 1 FMNMX3
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    FMNMX3(f[7], f[i + 4], f[i + 5]);
+                }
+            } else if (MODE == 16) {  // detector with two 2-input mins
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    FMNMX(f[7], f[i + 4]); FMNMX(f[6], f[i + 5]);
+                }
+            } else if (MODE == 17) {  // no mask at all: 12 FFMA2 + 2 MUFU
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                }
+            } else if (MODE == 18) {  // 12 FFMA2 + 2 MUFU + 1 FMNMX + 1 LDS.128 (uniform address)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    FMNMX(f[7], f[i + 4]);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l0.x), "=f"(l0.y), "=f"(l0.z), "=f"(l0.w) : "r"(smbase + ((it * 8 + u * 2 + i) & 255) * 16));
+                    f[4] += l0.x;
+                }
+            } else if (MODE == 19) {  // same with 2 LDS.128 per body
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    FMNMX(f[7], f[i + 4]);
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l0.x), "=f"(l0.y), "=f"(l0.z), "=f"(l0.w) : "r"(smbase + ((it * 8 + u * 2 + i) & 255) * 16));
+                    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(l1.x), "=f"(l1.y), "=f"(l1.z), "=f"(l1.w) : "r"(smbase + 4096 + ((it * 8 + u * 2 + i) & 255) * 16));
+                    f[4] += l0.x; f[5] += l1.y;
+                }
+            } else if (MODE == 20) {  // 12 FFMA2 + 2 MUFU + 1 FMNMX, no LDS (reference for 18/19, same extra FADDs)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    for (int j = 0; j < 12; ++j) FMA2(a[(i * 4 + j) & 7], m, c);
+                    MUFU(f[i]); MUFU(f[i + 2]);
+                    FMNMX(f[7], f[i + 4]);
+                    f[4] += l0.x;
+                }
             } else if (MODE == 12) {  // 24 scalar FFMA + 2 MUFU + 4 ALU (scalar formulation of 2 interactions)
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
@@ -105,7 +166,7 @@ __global__ void __launch_bounds__(256, 4) k(int iters, float* sink, u64* cyc) {
     for (int i = 0; i < 8; ++i) {
         float lo, hi;
         asm("mov.b64 {%0,%1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a[i]));
-        r += lo + hi + f[i] + x[i];
+        r += lo + hi + f[i] + x[i] + l0.y + l1.z;
     }
     if (r == 12345.678f) sink[0] = r;
     if (threadIdx.x == 0) cyc[blockIdx.x] = (u64)(t1 - t0);
@@ -182,6 +243,13 @@ int main() {
         run<11>("2 x (12 FFMA2 + 2 MUFU)", 28, w);
         run<12>("2 x (24 FFMA + 2 MUFU + 4 ALU)", 60, w);
         run<13>("2 x (12 FFMA2 + 2 MUFU + 4 FSEL-like)", 36, w);
+        run<14>("2 x (12 FFMA2 + 2 MUFU + 2 FSETP + 2 FSEL)", 36, w);
+        run<15>("2 x (12 FFMA2 + 2 MUFU + 1 FMNMX3)", 30, w);
+        run<16>("2 x (12 FFMA2 + 2 MUFU + 2 FMNMX)", 32, w);
+        run<17>("2 x (12 FFMA2 + 2 MUFU)", 28, w);
+        run<20>("2 x (12 FFMA2 + 2 MUFU + FMNMX + FADD)", 32, w);
+        run<18>("2 x (.. + 1 LDS.128)", 34, w);
+        run<19>("2 x (.. + 2 LDS.128)", 36, w);
     }
     {   // latency: one warp per SM, dependent chain
         const int iters = 20000;
