@@ -176,6 +176,88 @@ __global__ void __launch_bounds__(kStreamThreads)
     }
 }
 
+
+// Same systems, full 1024-entity chunks: the 12-byte rows are moved with perfectly coalesced
+// 128-bit accesses (thread t touches float4 t, t+256, t+512 of the chunk) and regrouped into whole
+// entities through shared memory (each thread then owns entities 4t..4t+3 = float4 3t..3t+2; a
+// 48-byte stride is conflict-free for LDS.128 quarter-warps).
+constexpr int kRainChunk = 1024;                      // entities per block iteration
+constexpr int kRainChunkVec = kRainChunk * 3 / 4;     // 768 float4 per column per chunk
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads)
+    rain_staged_kernel(float4* __restrict__ vel, float4* __restrict__ pos, uint64_t n_chunks, float wx, float wy,
+                       float wz, float k_gravity, float terminal, float dt) {
+    __shared__ float4 sv[kRainChunkVec];
+    __shared__ float4 sp[MODE == 2 ? kRainChunkVec : 1];
+    const int t = threadIdx.x;
+    for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+        float4* gv = vel + chunk * kRainChunkVec;
+        float4* gp = MODE == 2 ? pos + chunk * kRainChunkVec : nullptr;
+        float4 v0 = __ldcs(gv + t), v1 = __ldcs(gv + t + 256), v2 = __ldcs(gv + t + 512);
+        float4 p0, p1, p2;
+        if (MODE == 2) {
+            p0 = __ldcs(gp + t);
+            p1 = __ldcs(gp + t + 256);
+            p2 = __ldcs(gp + t + 512);
+        }
+        sv[t] = v0;
+        sv[t + 256] = v1;
+        sv[t + 512] = v2;
+        if (MODE == 2) {
+            sp[t] = p0;
+            sp[t + 256] = p1;
+            sp[t + 512] = p2;
+        }
+        __syncthreads();
+        Vec3x4 v, p;
+        v.a = sv[3 * t];
+        v.b = sv[3 * t + 1];
+        v.c = sv[3 * t + 2];
+        if (MODE == 2) {
+            p.a = sp[3 * t];
+            p.b = sp[3 * t + 1];
+            p.c = sp[3 * t + 2];
+        }
+        float o[12], q[12];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x, y, z;
+            get3(v, e, x, y, z);
+            if (MODE == 1 || MODE == 2) rain_wind_1(x, y, z, wx, wy, wz, terminal);
+            if (MODE == 0 || MODE == 2) rain_gravity_1(x, y, z, k_gravity, terminal);
+            o[3 * e] = x;
+            o[3 * e + 1] = y;
+            o[3 * e + 2] = z;
+            if (MODE == 2) {
+                float px, py, pz;
+                get3(p, e, px, py, pz);
+                q[3 * e] = __fadd_rn(px, __fmul_rn(x, dt));
+                q[3 * e + 1] = __fadd_rn(py, __fmul_rn(y, dt));
+                q[3 * e + 2] = __fadd_rn(pz, __fmul_rn(z, dt));
+            }
+        }
+        sv[3 * t] = make_float4(o[0], o[1], o[2], o[3]);
+        sv[3 * t + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        sv[3 * t + 2] = make_float4(o[8], o[9], o[10], o[11]);
+        if (MODE == 2) {
+            sp[3 * t] = make_float4(q[0], q[1], q[2], q[3]);
+            sp[3 * t + 1] = make_float4(q[4], q[5], q[6], q[7]);
+            sp[3 * t + 2] = make_float4(q[8], q[9], q[10], q[11]);
+        }
+        __syncthreads();
+        __stcs(gv + t, sv[t]);
+        __stcs(gv + t + 256, sv[t + 256]);
+        __stcs(gv + t + 512, sv[t + 512]);
+        if (MODE == 2) {
+            __stcs(gp + t, sp[t]);
+            __stcs(gp + t + 256, sp[t + 256]);
+            __stcs(gp + t + 512, sp[t + 512]);
+        }
+        __syncthreads();
+    }
+}
+
+
 inline uint32_t stream_grid(uint64_t work_items, uint32_t per_block) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -222,26 +304,41 @@ cudaError_t launch_movement_pack(float* pos, const float* vel, const float* mass
     return cudaGetLastError();
 }
 
-cudaError_t launch_rain_gravity(float* vel, uint64_t n, float gravity_dt, float terminal,
-                                cudaStream_t s) {
+namespace {
+template <int MODE>
+cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float wy, float wz, float k_gravity,
+                             float terminal, float dt, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    rain_kernel<0><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
-        vel, nullptr, n, 0.f, 0.f, 0.f, gravity_dt, terminal, 0.f);
+    const bool aligned = (reinterpret_cast<uintptr_t>(vel) & 15) == 0 && (MODE != 2 || (reinterpret_cast<uintptr_t>(pos) & 15) == 0);
+    const uint64_t n_chunks = aligned ? n / kRainChunk : 0;
+    if (n_chunks) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
+        const uint32_t grid = static_cast<uint32_t>(n_chunks < cap ? n_chunks : cap);
+        rain_staged_kernel<MODE><<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(vel), reinterpret_cast<float4*>(pos),
+                                                                 n_chunks, wx, wy, wz, k_gravity, terminal, dt);
+    }
+    const uint64_t done = n_chunks * kRainChunk;
+    if (done < n) {  // tail (< 1024 entities, or everything when unaligned)
+        const uint64_t rest = n - done;
+        rain_kernel<MODE><<<stream_grid(rest / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
+            vel + 3 * done, pos ? pos + 3 * done : nullptr, rest, wx, wy, wz, k_gravity, terminal, dt);
+    }
     return cudaGetLastError();
 }
-cudaError_t launch_rain_wind(float* vel, uint64_t n, float wx, float wy, float wz, float terminal,
-                             cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    rain_kernel<1><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
-        vel, nullptr, n, wx, wy, wz, 0.f, terminal, 0.f);
-    return cudaGetLastError();
+}  // namespace
+
+cudaError_t launch_rain_gravity(float* vel, uint64_t n, float gravity_dt, float terminal, cudaStream_t s) {
+    return launch_rain_impl<0>(vel, nullptr, n, 0.f, 0.f, 0.f, gravity_dt, terminal, 0.f, s);
 }
-cudaError_t launch_rain_fused(float* vel, float* pos, uint64_t n, float wx, float wy, float wz,
-                              float gravity_dt, float terminal, float dt, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    rain_kernel<2><<<stream_grid(n / 4 + 1, kStreamThreads), kStreamThreads, 0, s>>>(
-        vel, pos, n, wx, wy, wz, gravity_dt, terminal, dt);
-    return cudaGetLastError();
+cudaError_t launch_rain_wind(float* vel, uint64_t n, float wx, float wy, float wz, float terminal, cudaStream_t s) {
+    return launch_rain_impl<1>(vel, nullptr, n, wx, wy, wz, 0.f, terminal, 0.f, s);
+}
+cudaError_t launch_rain_fused(float* vel, float* pos, uint64_t n, float wx, float wy, float wz, float gravity_dt,
+                              float terminal, float dt, cudaStream_t s) {
+    return launch_rain_impl<2>(vel, pos, n, wx, wy, wz, gravity_dt, terminal, dt, s);
 }
 
 // ---- measurement ---------------------------------------------------------------------------------
