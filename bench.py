@@ -323,6 +323,11 @@ def run_gpu_arm(args) -> None:
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
     total_ms = max_over_ranks(float(np.sum(step_ms)))
+    per_rank_ms = [float(np.mean(step_ms))]
+    if dist is not None:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, float(np.mean(step_ms)))
+        per_rank_ms = gathered
     launches_per_step = ctx.timing()["kernel_launches"] / steps
     value = n * n * steps / (total_ms * 1e-3) / 1e9
 
@@ -427,6 +432,7 @@ def run_gpu_arm(args) -> None:
             "parity": {"acc_max_rel_err_vs_oracle": parity_err, "tolerance": 1e-4, "pos_bit_exact_after_tick1": pos_exact,
                        "acc_max_rel_err_vs_f64": parity_f64, "oracle_f32_order_vs_f64": oracle_f64, "rows_per_rank": 32},
             "step_ms": [round(x, 3) for x in step_ms],
+            "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms],
             "wall_ms_per_step_incl_flush": wall / steps * 1e3,
             "extras": extras,
         }

@@ -282,15 +282,18 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
         c->posm_sources = sources;
         c->posm_bodies = n_jpad;
     }
-    if (sharded) {
-        if (!c->comm) return fail(c, RECS_ERR_NCCL, "world_size > 1 but recs_gpu_comm_init was not called");
-        RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));
+    if (sharded && !c->comm) return fail(c, RECS_ERR_NCCL, "world_size > 1 but recs_gpu_comm_init was not called");
+    // The all-gather is enqueued further down, AFTER launch A: an NCCL kernel that is resident
+    // while it waits for a late peer would keep persistent gravity CTAs off its SMs.
+    auto enqueue_gather = [&]() -> int32_t {
+        RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));  // after launch A (and the pack before it)
         RECS_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
         float* send = c->posm + (size_t)slice * (uint64_t)c->cfg.rank * 4;
         int r = c->nccl.AllGather(send, c->posm, (size_t)slice * 4, /*ncclFloat32*/ 7, c->comm, c->comm_stream);
         if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclAllGather: ") + c->nccl.GetErrorString(r));
         RECS_CUDA(c, cudaEventRecord(c->ev_gather, c->comm_stream));
-    }
+        return RECS_OK;
+    };
 
     // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
     const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm);
@@ -338,7 +341,10 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
         ra.frags = c->frags;
 
         for (uint32_t l = 0; l < ra.n_launches; ++l) {
-            if (l == 1) RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+            if (l == 1) {
+                if ((st = enqueue_gather()) != RECS_OK) return st;
+                RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+            }
             GravityArgs ga;
             ga.posm = reinterpret_cast<const float4*>(c->posm);
             ga.ipos = (const float*)p->dev;
@@ -362,7 +368,10 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
         }
         acc->version++;
     }
-    if (sharded && sys.archs.empty()) RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+    if (sharded && (sys.archs.empty() || re == rb)) {  // nothing launched here: still take part in the collective
+        if ((st = enqueue_gather()) != RECS_OK) return st;
+        RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+    }
     return RECS_OK;
 }
 

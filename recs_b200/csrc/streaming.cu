@@ -258,15 +258,17 @@ __global__ void __launch_bounds__(kStreamThreads)
 }
 
 
+// Grid for a grid-stride streaming kernel: at most `cap` resident-ish CTAs, and every CTA gets the
+// same number of chunks (a ragged last pass would leave most SMs idle for a whole chunk time).
 inline uint32_t stream_grid(uint64_t work_items, uint32_t per_block) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint64_t need = (work_items + per_block - 1) / per_block;
-    const uint64_t cap = static_cast<uint64_t>(sms) * 8 * 4;  // 8 resident CTAs x 4 waves
-    uint64_t g = need < cap ? need : cap;
-    if (g == 0) g = 1;
-    return static_cast<uint32_t>(g);
+    const uint64_t chunks = (work_items + per_block - 1) / per_block;
+    const uint64_t cap = static_cast<uint64_t>(sms) * 8 * 2;  // 8 resident CTAs of 256 threads x 2 waves
+    if (chunks <= cap) return static_cast<uint32_t>(chunks ? chunks : 1);
+    const uint64_t passes = (chunks + cap - 1) / cap;
+    return static_cast<uint32_t>((chunks + passes - 1) / passes);
 }
 
 }  // namespace
@@ -316,7 +318,8 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
-        const uint32_t grid = static_cast<uint32_t>(n_chunks < cap ? n_chunks : cap);
+        const uint64_t passes = (n_chunks + cap - 1) / cap;   // same number of chunks for every CTA
+        const uint32_t grid = static_cast<uint32_t>((n_chunks + passes - 1) / passes);
         rain_staged_kernel<MODE><<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(vel), reinterpret_cast<float4*>(pos),
                                                                  n_chunks, wx, wy, wz, k_gravity, terminal, dt);
     }
