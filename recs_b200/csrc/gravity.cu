@@ -105,9 +105,11 @@ __device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const fl
     }
 }
 
-template <int RI, int MIN_CTAS, int UNROLL, bool DETECT>
-__global__ void __launch_bounds__(kGravThreads, MIN_CTAS) nbody_gravity_kernel(const GravityArgs a) {
+template <int RI, int MIN_CTAS, int UNROLL, bool DETECT, int CW = 8>
+__global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(const GravityArgs a) {
     constexpr int kGravRowsPerThread = RI;
+    constexpr int kGravConsumerWarps = CW;
+    constexpr int kGravConsumerThreads = 32 * CW;
     constexpr int kGravRows = kGravConsumerThreads * RI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
@@ -298,8 +300,10 @@ __global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm,
 namespace {
 typedef void (*GravityKernel)(const GravityArgs);
 //                                                 rows/thread, CTAs/SM
-const GravityVariant kVariants[kGravVariantCount] = {{4, 2}, {2, 4}, {3, 3}, {2, 4}, {4, 2}, {3, 3}, {2, 4}, {2, 3},
-                                                      {2, 2}, {2, 3}, {3, 3}, {4, 2}, {3, 2}, {2, 2}, {4, 2}, {3, 2}};
+//                                                 rows/thread, CTAs/SM, consumer warps
+const GravityVariant kVariants[kGravVariantCount] = {
+    {4, 2, 8}, {2, 4, 8}, {3, 3, 8}, {2, 4, 8}, {4, 2, 8}, {3, 3, 8}, {2, 4, 8}, {2, 3, 8}, {2, 2, 8}, {2, 3, 8},
+    {3, 3, 8}, {4, 2, 8}, {3, 2, 8}, {2, 2, 8}, {4, 2, 8}, {3, 2, 8}, {4, 1, 16}, {4, 1, 16}, {3, 1, 16}, {2, 1, 16}};
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
@@ -334,6 +338,14 @@ GravityKernel variant_kernel(int v) {
             return nbody_gravity_kernel<4, 2, 8, true>;
         case 15:
             return nbody_gravity_kernel<3, 2, 8, true>;
+        case 16:
+            return nbody_gravity_kernel<4, 1, 4, true, 16>;
+        case 17:
+            return nbody_gravity_kernel<4, 1, 8, true, 16>;
+        case 18:
+            return nbody_gravity_kernel<3, 1, 8, true, 16>;
+        case 19:
+            return nbody_gravity_kernel<2, 1, 8, true, 16>;
     }
     return nullptr;
 }
@@ -354,7 +366,7 @@ cudaError_t gravity_prepare() {
 
 int gravity_max_ctas_per_sm(int variant) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, variant_kernel(variant), kGravThreads,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, variant_kernel(variant), kVariants[variant].threads(),
                                                       gravity_smem_bytes(variant)) != cudaSuccess)
         return 0;
     return n;
@@ -362,7 +374,7 @@ int gravity_max_ctas_per_sm(int variant) {
 
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s) {
     if (a.launch.n_vtiles == 0 || a.launch.n_iblocks == 0) return cudaSuccess;
-    variant_kernel(a.variant)<<<a.launch.grid, kGravThreads, gravity_smem_bytes(a.variant), s>>>(a);
+    variant_kernel(a.variant)<<<a.launch.grid, kVariants[a.variant].threads(), gravity_smem_bytes(a.variant), s>>>(a);
     return cudaGetLastError();
 }
 

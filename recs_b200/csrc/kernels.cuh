@@ -7,9 +7,7 @@
 namespace recs {
 
 // ---- gravity (crates/n-body/src/lib.rs:104-135) ------------------------------------------------
-constexpr int kGravConsumerWarps = 8;
-constexpr int kGravConsumerThreads = 32 * kGravConsumerWarps;  // 256
-constexpr int kGravThreads = kGravConsumerThreads + 32;        // + 1 TMA producer warp
+constexpr int kGravMaxConsumerWarps = 16;                      // consumer warps per CTA are variant dependent (8 or 16)
 constexpr int kGravMaxRowsPerThread = 4;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
@@ -22,9 +20,12 @@ constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic
 struct GravityVariant {
     int rows_per_thread;  // bodies i per consumer thread
     int min_ctas;         // __launch_bounds__ residency target
-    int rows() const { return kGravConsumerThreads * rows_per_thread; }  // rows per i-block
+    int consumer_warps;   // 8 or 16 (+ 1 TMA producer warp)
+    int consumer_threads() const { return 32 * consumer_warps; }
+    int threads() const { return consumer_threads() + 32; }
+    int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
-constexpr int kGravVariantCount = 16;
+constexpr int kGravVariantCount = 20;
 GravityVariant gravity_variant(int index);
 
 struct GravityLaunch {
