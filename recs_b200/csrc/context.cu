@@ -67,7 +67,7 @@ struct recs_gpu_ctx {
     cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
     int sm_count = 148;
     int grav_ctas_per_sm = 2;
-    int grav_variant = 13;  // 2 rows/thread, 2 CTAs/SM, unroll 8, detector fast path (profiles/r01_gravity_variant_sweep*.txt)  // see profiles/r01_gravity_variant_sweep*.txt
+    int grav_variant = 23;  // 2 rows/thread, 12 consumer warps, 1 CTA/SM, unroll 8, detector fast path (profiles/r01_gravity_variant_sweep*.txt)
 
     std::map<ColKey, Column> columns;
     std::vector<System> systems;

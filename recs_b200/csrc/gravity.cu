@@ -61,9 +61,11 @@ template <bool MASKED>
 __device__ __forceinline__ void pair_interaction(const f32x2 xj, const f32x2 yj, const f32x2 zj, const f32x2 gm,
                                                  const float nx, const float ny, const float nz, const float eps,
                                                  f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {
-    const f32x2 dx = ptx::add2(xj, ptx::pack(nx, nx));
-    const f32x2 dy = ptx::add2(yj, ptx::pack(ny, ny));
-    const f32x2 dz = ptx::add2(zj, ptx::pack(nz, nz));
+    // (x_j0, x_j1) - x_i: written as an add of the negated scalar so ptxas can use FADD2's
+    // broadcast-scalar operand form (`-R.F32`): one register read instead of a materialised pair
+    const f32x2 dx = ptx::add2(xj, ptx::pack(-nx, -nx));
+    const f32x2 dy = ptx::add2(yj, ptx::pack(-ny, -ny));
+    const f32x2 dz = ptx::add2(zj, ptx::pack(-nz, -nz));
     f32x2 d2 = ptx::mul2(dx, dx);
     d2 = ptx::fma2(dy, dy, d2);
     d2 = ptx::fma2(dz, dz, d2);
@@ -174,9 +176,9 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                 y = __ldg(p + 1);
                 z = __ldg(p + 2);
             }
-            nxi[r] = -x;
-            nyi[r] = -y;
-            nzi[r] = -z;
+            nxi[r] = x;  // kept positive; negated at the use (see pair_interaction)
+            nyi[r] = y;
+            nzi[r] = z;
             run[r * kGravConsumerThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
@@ -303,7 +305,9 @@ typedef void (*GravityKernel)(const GravityArgs);
 //                                                 rows/thread, CTAs/SM, consumer warps
 const GravityVariant kVariants[kGravVariantCount] = {
     {4, 2, 8}, {2, 4, 8}, {3, 3, 8}, {2, 4, 8}, {4, 2, 8}, {3, 3, 8}, {2, 4, 8}, {2, 3, 8}, {2, 2, 8}, {2, 3, 8},
-    {3, 3, 8}, {4, 2, 8}, {3, 2, 8}, {2, 2, 8}, {4, 2, 8}, {3, 2, 8}, {4, 1, 16}, {4, 1, 16}, {3, 1, 16}, {2, 1, 16}};
+    {3, 3, 8}, {4, 2, 8}, {3, 2, 8}, {2, 2, 8}, {4, 2, 8}, {3, 2, 8}, {4, 1, 16}, {4, 1, 16}, {3, 1, 16}, {2, 1, 16},
+    {2, 1, 24}, {2, 1, 20}, {2, 1, 16}, {2, 1, 12}, {3, 1, 20}, {2, 1, 28},
+    {2, 1, 8}, {2, 1, 10}, {2, 1, 14}, {2, 1, 12}, {2, 1, 12}, {3, 1, 12}};
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
@@ -346,6 +350,30 @@ GravityKernel variant_kernel(int v) {
             return nbody_gravity_kernel<3, 1, 8, true, 16>;
         case 19:
             return nbody_gravity_kernel<2, 1, 8, true, 16>;
+        case 20:
+            return nbody_gravity_kernel<2, 1, 8, true, 24>;
+        case 21:
+            return nbody_gravity_kernel<2, 1, 8, true, 20>;
+        case 22:
+            return nbody_gravity_kernel<2, 1, 16, true, 16>;
+        case 23:
+            return nbody_gravity_kernel<2, 1, 8, true, 12>;
+        case 24:
+            return nbody_gravity_kernel<3, 1, 8, true, 20>;
+        case 25:
+            return nbody_gravity_kernel<2, 1, 4, true, 28>;
+        case 26:
+            return nbody_gravity_kernel<2, 1, 8, true, 8>;
+        case 27:
+            return nbody_gravity_kernel<2, 1, 8, true, 10>;
+        case 28:
+            return nbody_gravity_kernel<2, 1, 8, true, 14>;
+        case 29:
+            return nbody_gravity_kernel<2, 1, 16, true, 12>;
+        case 30:
+            return nbody_gravity_kernel<2, 1, 4, true, 12>;
+        case 31:
+            return nbody_gravity_kernel<3, 1, 8, true, 12>;
     }
     return nullptr;
 }

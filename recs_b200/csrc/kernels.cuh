@@ -7,7 +7,7 @@
 namespace recs {
 
 // ---- gravity (crates/n-body/src/lib.rs:104-135) ------------------------------------------------
-constexpr int kGravMaxConsumerWarps = 16;                      // consumer warps per CTA are variant dependent (8 or 16)
+constexpr int kGravMaxConsumerWarps = 31;                      // consumer warps per CTA are variant dependent (8 or 16)
 constexpr int kGravMaxRowsPerThread = 4;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
@@ -25,7 +25,7 @@ struct GravityVariant {
     int threads() const { return consumer_threads() + 32; }
     int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
-constexpr int kGravVariantCount = 20;
+constexpr int kGravVariantCount = 32;
 GravityVariant gravity_variant(int index);
 
 struct GravityLaunch {
