@@ -40,6 +40,10 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_INTERACTION = 20.0  # all-pairs convention; the kernel issues 12 FMA-pipe lane-ops
 FMA_LANE_OPS_PER_INTERACTION = 12.0
+# dram__bytes_read.sum + dram__bytes_write.sum of one interaction-kernel launch on one GPU, from ncu
+# (profiles/r01_gravity_traffic_1M.csv, profiles/r01_gravity_default_ncu_summary.txt); the kernel is
+# FP32-bound, the figure only shows there are no wasted re-reads (posm + outer positions = 28 MB at 1 M)
+KERNEL_DRAM_TRAFFIC_BYTES = {1_048_576: 29_822_464 + 18_688, 65_536: 1_848_320}
 DEFAULT_BODIES = 1_048_576
 SEED = 1
 
@@ -375,7 +379,8 @@ def run_gpu_arm(args) -> None:
         "fma_pipe_frac": fma_lane_rate / (tf_peak * 1e12 / 2.0),
         "kernel_ms_per_step": grav_ms,
         "kernel_share_of_step": grav_ms / (t["last_tick_chain_ms"] / k_steps) if t["last_tick_chain_ms"] else None,
-        "traffic": None,
+        "traffic": KERNEL_DRAM_TRAFFIC_BYTES.get(n) if world == 1 else None,
+        "traffic_unit": "bytes of DRAM traffic per launch (ncu, single GPU)",
         "sm_mhz_during_peak_probe": mhz,
     }
 
