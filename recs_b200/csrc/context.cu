@@ -66,8 +66,9 @@ struct recs_gpu_ctx {
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_pack = nullptr, ev_gather = nullptr;
     int sm_count = 148;
-    int grav_ctas_per_sm = 2;
-    int grav_variant = 23;  // 2 rows/thread, 12 consumer warps, 1 CTA/SM, unroll 8, detector fast path (profiles/r01_gravity_variant_sweep*.txt)
+    int grav_ctas_per_sm[kGravVariantCount] = {0};
+    bool grav_variant_forced = false;
+    int grav_variant = kGravVariantDefault;
 
     std::map<ColKey, Column> columns;
     std::vector<System> systems;
@@ -296,8 +297,20 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
     };
 
     // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
-    const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm);
-    const uint32_t kGravRows = (uint32_t)gravity_variant(c->grav_variant).rows();
+    // kernel shape: up to 24 576 outer rows the small-i-block / exact-mask shape wins (more stream-K
+    // units, and the detector's redo of self tiles is a large share of a small problem); measured in
+    // profiles/r01_gravity_small_n_sweep.txt
+    int variant = c->grav_variant;
+    if (!c->grav_variant_forced) {
+        uint64_t max_rows = 0;
+        for (uint32_t a : sys.archs) {
+            Column* p = find_column(c, a, POS);
+            if (p) max_rows = std::max<uint64_t>(max_rows, sharded ? re - rb : p->count);
+        }
+        if (max_rows <= 24576) variant = kGravVariantSmall;
+    }
+    const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm[variant]);
+    const uint32_t kGravRows = (uint32_t)gravity_variant(variant).rows();
     for (uint32_t a : sys.archs) {
         Column *p, *acc;
         if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
@@ -354,7 +367,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
             ga.n_tiles_total = n_tiles;
             ga.eps = c->cfg.nbody_epsilon;
             ga.launch = ra.launch[l];
-            ga.variant = c->grav_variant;
+            ga.variant = variant;
             if (ga.launch.n_vtiles == 0) continue;
             Timed t(c, T_GRAVITY);
             RECS_CUDA(c, launch_gravity(ga, c->stream));
@@ -644,9 +657,14 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
               gravity_prepare() == cudaSuccess;
     if (ok) {
         const char* v = getenv("RECS_GPU_GRAVITY_VARIANT");  // tuning knob; default chosen by measurement
-        if (v && atoi(v) >= 0 && atoi(v) < kGravVariantCount) c->grav_variant = atoi(v);
-        c->grav_ctas_per_sm = gravity_max_ctas_per_sm(c->grav_variant);
-        ok = c->grav_ctas_per_sm > 0;
+        if (v && v[0] && atoi(v) >= 0 && atoi(v) < kGravVariantCount) {
+            c->grav_variant = atoi(v);
+            c->grav_variant_forced = true;
+        }
+        for (int k = 0; k < kGravVariantCount && ok; ++k) {
+            c->grav_ctas_per_sm[k] = gravity_max_ctas_per_sm(k);
+            ok = c->grav_ctas_per_sm[k] > 0;
+        }
     }
     if (!ok) {
         fprintf(stderr, "recs_gpu: context creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));

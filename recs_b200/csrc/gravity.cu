@@ -301,79 +301,37 @@ __global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm,
 
 namespace {
 typedef void (*GravityKernel)(const GravityArgs);
-//                                                 rows/thread, CTAs/SM
+// Compiled shapes (profiles/r01_gravity_variant_sweep*.txt has the full sweep they were picked from).
 //                                                 rows/thread, CTAs/SM, consumer warps
 const GravityVariant kVariants[kGravVariantCount] = {
-    {4, 2, 8}, {2, 4, 8}, {3, 3, 8}, {2, 4, 8}, {4, 2, 8}, {3, 3, 8}, {2, 4, 8}, {2, 3, 8}, {2, 2, 8}, {2, 3, 8},
-    {3, 3, 8}, {4, 2, 8}, {3, 2, 8}, {2, 2, 8}, {4, 2, 8}, {3, 2, 8}, {4, 1, 16}, {4, 1, 16}, {3, 1, 16}, {2, 1, 16},
-    {2, 1, 24}, {2, 1, 20}, {2, 1, 16}, {2, 1, 12}, {3, 1, 20}, {2, 1, 28},
-    {2, 1, 8}, {2, 1, 10}, {2, 1, 14}, {2, 1, 12}, {2, 1, 12}, {3, 1, 12}};
+    {2, 1, 12},  // 0  default: detector fast path, unroll 8, <= 120 registers
+    {2, 1, 12},  // 1  same shape, exact mask on every pair (A/B of the detector)
+    {2, 3, 4},   // 2  small problems: 256-row i-blocks, 3 CTAs/SM (more work units for the stream-K split), exact
+                 //    mask everywhere (the detector's redo of self tiles is a large share of a small problem)
+    {2, 3, 4},   // 3  small i-blocks with the detector
+    {4, 1, 8},   // 4  4 rows/thread, 8 warps, up to 224 registers
+    {2, 1, 16},  // 5
+    {4, 1, 16},  // 6  4 rows/thread: half the LDS cost, worse ptxas schedule
+    {4, 2, 8},   // 7  the first version's shape with the exact mask
+};
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
-            return nbody_gravity_kernel<4, 2, 2, false>;  // exact mask everywhere
-        case 1:
-            return nbody_gravity_kernel<2, 4, 2, false>;
-        case 2:
-            return nbody_gravity_kernel<3, 3, 2, false>;
-        case 3:
-            return nbody_gravity_kernel<2, 4, 2, true>;   // detector fast path + exact redo
-        case 4:
-            return nbody_gravity_kernel<4, 2, 2, true>;
-        case 5:
-            return nbody_gravity_kernel<3, 3, 2, true>;
-        case 6:
-            return nbody_gravity_kernel<2, 4, 4, true>;
-        case 7:
-            return nbody_gravity_kernel<2, 3, 4, true>;
-        case 8:
-            return nbody_gravity_kernel<2, 2, 16, true>;
-        case 9:
-            return nbody_gravity_kernel<2, 3, 8, true>;
-        case 10:
-            return nbody_gravity_kernel<3, 3, 4, true>;
-        case 11:
-            return nbody_gravity_kernel<4, 2, 4, true>;
-        case 12:
-            return nbody_gravity_kernel<3, 2, 4, true>;
-        case 13:
-            return nbody_gravity_kernel<2, 2, 8, true>;
-        case 14:
-            return nbody_gravity_kernel<4, 2, 8, true>;
-        case 15:
-            return nbody_gravity_kernel<3, 2, 8, true>;
-        case 16:
-            return nbody_gravity_kernel<4, 1, 4, true, 16>;
-        case 17:
-            return nbody_gravity_kernel<4, 1, 8, true, 16>;
-        case 18:
-            return nbody_gravity_kernel<3, 1, 8, true, 16>;
-        case 19:
-            return nbody_gravity_kernel<2, 1, 8, true, 16>;
-        case 20:
-            return nbody_gravity_kernel<2, 1, 8, true, 24>;
-        case 21:
-            return nbody_gravity_kernel<2, 1, 8, true, 20>;
-        case 22:
-            return nbody_gravity_kernel<2, 1, 16, true, 16>;
-        case 23:
             return nbody_gravity_kernel<2, 1, 8, true, 12>;
-        case 24:
-            return nbody_gravity_kernel<3, 1, 8, true, 20>;
-        case 25:
-            return nbody_gravity_kernel<2, 1, 4, true, 28>;
-        case 26:
-            return nbody_gravity_kernel<2, 1, 8, true, 8>;
-        case 27:
-            return nbody_gravity_kernel<2, 1, 8, true, 10>;
-        case 28:
-            return nbody_gravity_kernel<2, 1, 8, true, 14>;
-        case 29:
-            return nbody_gravity_kernel<2, 1, 16, true, 12>;
-        case 30:
-            return nbody_gravity_kernel<2, 1, 4, true, 12>;
-        case 31:
-            return nbody_gravity_kernel<3, 1, 8, true, 12>;
+        case 1:
+            return nbody_gravity_kernel<2, 1, 8, false, 12>;
+        case 2:
+            return nbody_gravity_kernel<2, 3, 8, false, 4>;
+        case 3:
+            return nbody_gravity_kernel<2, 3, 8, true, 4>;
+        case 4:
+            return nbody_gravity_kernel<4, 1, 8, true, 8>;
+        case 5:
+            return nbody_gravity_kernel<2, 1, 8, true, 16>;
+        case 6:
+            return nbody_gravity_kernel<4, 1, 8, true, 16>;
+        case 7:
+            return nbody_gravity_kernel<4, 2, 2, false, 8>;
     }
     return nullptr;
 }

@@ -25,7 +25,9 @@ struct GravityVariant {
     int threads() const { return consumer_threads() + 32; }
     int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
-constexpr int kGravVariantCount = 32;
+constexpr int kGravVariantCount = 8;
+constexpr int kGravVariantDefault = 0;
+constexpr int kGravVariantSmall = 2;
 GravityVariant gravity_variant(int index);
 
 struct GravityLaunch {
