@@ -227,7 +227,8 @@ void shard_rows(const recs_gpu_config& cfg, uint64_t n, uint64_t* slice, uint64_
 }
 
 // ---- systems -----------------------------------------------------------------------------------
-int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
+// `movement` / `acceleration`: the systems fused into the tail of the reduce kernel, or null.
+int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, System* acceleration = nullptr) {
     const uint64_t POS = sys.comp[0], ACC = sys.comp[1], MASS = sys.comp[2];
     const bool sharded = c->cfg.world_size > 1;
     // 1. the nested Query<(Read<Position>, Read<Mass>)>: concatenation of its archetypes
@@ -259,8 +260,8 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
     if (st != RECS_OK) return st;
 
     // 2. refresh the posm mirror if any source column changed since it was packed
-    const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad || c->capturing;
-    if (dirty || sharded) {
+    const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad;
+    if (dirty) {
         Timed t(c, T_PACK);
         if (!sharded) {
             uint64_t off = 0;
@@ -374,12 +375,43 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys) {
             c->kernel_launches++;
             c->gravity_launches++;
         }
+        Column *tail_pos = nullptr, *tail_vel = nullptr;
+        if (movement) {
+            Column* mass_col = nullptr;
+            if ((st = need_column(c, a, movement->comp[0], 12, &tail_pos)) != RECS_OK) return st;
+            if ((st = need_column(c, a, movement->comp[1], 12, &tail_vel)) != RECS_OK) return st;
+            if ((st = same_count(c, tail_pos, tail_vel)) != RECS_OK) return st;
+            ra.tail.pos = (float*)tail_pos->dev;
+            ra.tail.vel = (float*)tail_vel->dev;
+            ra.tail.dt = c->cfg.nbody_dt;
+            ra.tail.g = c->cfg.nbody_g;
+            // refresh the mirror in place when this archetype is part of the nested query
+            uint64_t off = 0;
+            for (size_t qi = 0; qi < sys.qarchs.size(); ++qi) {
+                if (sys.qarchs[qi] == a && movement->comp[0] == POS) {
+                    if ((st = need_column(c, a, MASS, 4, &mass_col)) != RECS_OK) return st;
+                    ra.tail.mass = (const float*)mass_col->dev;
+                    ra.tail.posm = c->posm;
+                    ra.tail.posm_offset = (uint32_t)off;
+                    break;
+                }
+                off += q[qi].first->count;
+            }
+        }
         {
             Timed t(c, T_REDUCE);
             RECS_CUDA(c, launch_gravity_reduce(ra, c->stream));
             c->kernel_launches++;
         }
         acc->version++;
+        if (movement) {
+            tail_pos->version++;
+            tail_vel->version++;
+        }
+    }
+    if (movement && movement->comp[0] == POS && sys.archs == sys.qarchs) {
+        // every source of the mirror was just refreshed by the tail: record it as current
+        for (auto& src : c->posm_sources) src.second = find_column(c, src.first.first, src.first.second)->version;
     }
     if (sharded && (sys.archs.empty() || re == rb)) {  // nothing launched here: still take part in the collective
         if ((st = enqueue_gather()) != RECS_OK) return st;
@@ -507,9 +539,30 @@ bool try_fused_rain(recs_gpu_ctx* c, size_t i, int32_t* st) {
     return true;
 }
 
+// gravity -> movement -> acceleration adjacent in the tick order over the same archetypes and
+// components: the two integrations run in the tail of the fragment-reduce kernel.
+bool try_fused_nbody(recs_gpu_ctx* c, size_t i, int32_t* st) {
+    if (i + 2 >= c->order.size()) return false;
+    System& g = c->systems[c->order[i]];
+    System& m = c->systems[c->order[i + 1]];
+    System& a = c->systems[c->order[i + 2]];
+    if (g.kind != RECS_SYS_NBODY_GRAVITY || m.kind != RECS_SYS_NBODY_MOVEMENT || a.kind != RECS_SYS_NBODY_ACCELERATION)
+        return false;
+    if (g.archs != m.archs || g.archs != a.archs) return false;
+    // movement(Write<Position>, Read<Velocity>), acceleration(Write<Velocity>, Read<Acceleration>)
+    if (m.comp[0] != g.comp[0] || a.comp[0] != m.comp[1] || a.comp[1] != g.comp[1]) return false;
+    *st = run_gravity(c, g, &m, &a);
+    return true;
+}
+
 int32_t run_tick_once(recs_gpu_ctx* c) {
     for (size_t i = 0; i < c->order.size(); ++i) {
         int32_t st = RECS_OK;
+        if (try_fused_nbody(c, i, &st)) {
+            if (st != RECS_OK) return st;
+            i += 2;
+            continue;
+        }
         if (try_fused_rain(c, i, &st)) {
             if (st != RECS_OK) return st;
             i += 2;
@@ -764,6 +817,7 @@ int32_t recs_gpu_upload(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
         RECS_CUDA(c, cudaMemcpyAsync(col->dev, col->host, (size_t)col->elem * col->count, cudaMemcpyHostToDevice,
                                      c->stream));
     col->version++;
+    c->epoch++;  // a captured tick may have elided the posm re-pack: capture again after new host data
     return RECS_OK;
 }
 
@@ -825,16 +879,22 @@ int32_t recs_gpu_system_describe(recs_gpu_ctx* c, uint32_t id, recs_gpu_system_d
 int32_t recs_gpu_system_set_archetypes(recs_gpu_ctx* c, uint32_t id, const uint32_t* archs, uint32_t n) {
     RECS_ENTER(c);
     if (id >= c->systems.size() || (n && !archs)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_archetypes: bad argument");
-    c->systems[id].archs.assign(archs, archs + n);
-    c->epoch++;
+    std::vector<uint32_t> next(archs, archs + n);
+    if (next != c->systems[id].archs) {  // unchanged membership keeps the captured tick graph valid
+        c->systems[id].archs.swap(next);
+        c->epoch++;
+    }
     return RECS_OK;
 }
 
 int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* c, uint32_t id, const uint32_t* archs, uint32_t n) {
     RECS_ENTER(c);
     if (id >= c->systems.size() || (n && !archs)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_query_archetypes: bad argument");
-    c->systems[id].qarchs.assign(archs, archs + n);
-    c->epoch++;
+    std::vector<uint32_t> next(archs, archs + n);
+    if (next != c->systems[id].qarchs) {
+        c->systems[id].qarchs.swap(next);
+        c->epoch++;
+    }
     return RECS_OK;
 }
 
@@ -850,8 +910,11 @@ int32_t recs_gpu_set_tick_order(recs_gpu_ctx* c, const uint32_t* ids, uint32_t n
     RECS_ENTER(c);
     for (uint32_t i = 0; i < n; ++i)
         if (!ids || ids[i] >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "set_tick_order: unknown system id");
-    c->order.assign(ids, ids + n);
-    c->epoch++;
+    std::vector<uint32_t> next(ids, ids + n);
+    if (next != c->order) {
+        c->order.swap(next);
+        c->epoch++;
+    }
     return RECS_OK;
 }
 

@@ -265,10 +265,36 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
             sz += f.z;
         }
     }
-    float* out = a.acc + 3ull * (a.row_begin + i);
+    const uint64_t row = a.row_begin + i;
+    float* out = a.acc + 3ull * row;
     out[0] = sx;
     out[1] = sy;
     out[2] = sz;
+    if (a.tail.pos) {
+        // movement: position.point += velocity * dt (crates/n-body/src/lib.rs:92), then
+        // acceleration: velocity += acceleration * dt (:101) -- the order the schedule produced;
+        // separate roundings like the Rust code
+        float* p = a.tail.pos + 3ull * row;
+        float* v = a.tail.vel + 3ull * row;
+        const float vx = v[0], vy = v[1], vz = v[2];
+        const float px = __fadd_rn(p[0], __fmul_rn(vx, a.tail.dt));
+        const float py = __fadd_rn(p[1], __fmul_rn(vy, a.tail.dt));
+        const float pz = __fadd_rn(p[2], __fmul_rn(vz, a.tail.dt));
+        p[0] = px;
+        p[1] = py;
+        p[2] = pz;
+        v[0] = __fadd_rn(vx, __fmul_rn(sx, a.tail.dt));
+        v[1] = __fadd_rn(vy, __fmul_rn(sy, a.tail.dt));
+        v[2] = __fadd_rn(vz, __fmul_rn(sz, a.tail.dt));
+        if (a.tail.posm) {
+            const uint64_t J = a.tail.posm_offset + row;
+            float* d = a.tail.posm + (J >> 1) * 8 + (J & 1);
+            d[0] = px;
+            d[2] = py;
+            d[4] = pz;
+            d[6] = __fmul_rn(a.tail.g, a.tail.mass[row]);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict__ pos,

@@ -50,6 +50,18 @@ struct GravityArgs {
     int variant;
 };
 
+// Optional fused tail of the n-body tick (schedule order gravity -> movement -> acceleration over the
+// same rows): after the fragment sum the same thread integrates its row and refreshes posm.
+struct GravityTail {
+    float* pos;           // Position column (null: plain reduce)
+    float* vel;           // Velocity column
+    const float* mass;    // Mass column (for the posm refresh; may be null together with posm)
+    float* posm;          // pair-interleaved mirror to refresh, or null
+    uint32_t posm_offset; // posm body index of row 0 of this column
+    float dt;
+    float g;
+};
+
 struct GravityReduceArgs {
     const float4* frags;
     float* acc;           // Acceleration column, 3 floats per row
@@ -58,6 +70,7 @@ struct GravityReduceArgs {
     uint32_t n_launches;  // 1 (single GPU) or 2 (local tiles, then remote tiles)
     uint32_t iblock_rows; // rows per i-block of the variant that produced the fragments
     GravityLaunch launch[2];
+    GravityTail tail;
 };
 
 // Number of fragment slots a launch may touch.
