@@ -5,7 +5,7 @@ ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
 CSRC      := recs_b200/csrc
 LIB       := recs_b200/librecs_gpu.so
-CU        := $(CSRC)/gravity.cu $(CSRC)/streaming.cu $(CSRC)/context.cu
+CU        := $(CSRC)/gravity.cu $(CSRC)/streaming.cu $(CSRC)/select.cu $(CSRC)/context.cu
 HOSTCPP   := $(wildcard $(CSRC)/host/*.cpp)
 OBJ       := $(CU:.cu=.o) $(HOSTCPP:.cpp=.o)
 HDR       := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/host/*.h) include/recs_gpu.h include/recs_ecs.h

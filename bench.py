@@ -384,6 +384,16 @@ def run_gpu_arm(args) -> None:
         "sm_mhz_during_peak_probe": mhz,
     }
 
+    comm = None
+    if world > 1:
+        comm = {
+            "collective": "ncclAllGather of the pair-interleaved position/mass mirror, in place, once per tick",
+            "bytes_per_rank_per_step": int((re - rb) * 16),
+            "bytes_total_per_step": int(n * 16),
+            "gather_ms_per_step_incl_peer_wait": t["gather_ms"] / k_steps,
+            "overlap": "enqueued after the local-tile launch; never on the critical path before it",
+        }
+
     # ---- secondary configs (streaming systems), reported as extras ---------------------------------
     extras = {}
     if not args.no_extras and rank == 0:
@@ -439,6 +449,7 @@ def run_gpu_arm(args) -> None:
             "step_ms": [round(x, 3) for x in step_ms],
             "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms],
             "wall_ms_per_step_incl_flush": wall / steps * 1e3,
+            "comm": comm,
             "extras": extras,
         }
         print(json.dumps(line), flush=True)

@@ -212,6 +212,17 @@ int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_para
  * (into_tickable, :386-400), then per tick execute_once + playback (structural commands are
  * applied by the caller between calls).  ordered != 0 selects OrderedPrecedenceGraph. */
 int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered);
+/* `Commands` for CPU systems (crates/ecs/src/systems/command_buffers.rs:53-112): may be called from
+ * inside a recs_cpu_system_fn; recorded and played back after the tick like
+ * `CommandPlayer::playback_commands` (:377-435): all creates first (record order), then removes.
+ * GPU systems that decide removals (RECS_SYS_NBODY_COLLISION, RECS_SYS_RAIN_GROUND_COLLISION) feed
+ * the same playback with the rows they flagged.  Before entities are removed or created the host
+ * columns are made current (recs_app_sync_to_host); the device mirror re-binds on the next tick. */
+int32_t recs_app_command_create(recs_app* app, const uint64_t* component_ids, const void* const* values,
+                                uint32_t n_components);
+int32_t recs_app_command_remove(recs_app* app, recs_entity entity);
+/* Number of entities created / removed by the playback of the last tick. */
+int32_t recs_app_last_playback(recs_app* app, uint64_t* out_created, uint64_t* out_removed);
 /* Order in which systems were dispatched during the last tick, and their batch numbers. */
 int32_t recs_app_last_tick_order(recs_app* app, uint32_t* out_order, uint32_t* out_batch_of, uint32_t cap,
                                  uint32_t* out_count);

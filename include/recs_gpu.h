@@ -72,6 +72,8 @@ typedef struct recs_gpu_config {
     float rain_terminal;       /* 9.0                                                          */
     float rain_wind_accel;     /* 10.0                                                         */
     float rain_wind_deg_per_s; /* 10.0 (WIND_ROTATION_SPEED)                                   */
+    float rain_ground_height;  /* 0.0  (GROUND_HEIGHT, crates/rain-simulation/src/lib.rs:150)  */
+    float nbody_collision_radius; /* 0.1 (COLLISION_RADIUS, crates/n-body/examples/n_body_demo.rs:16) */
 } recs_gpu_config;
 
 void recs_gpu_default_config(recs_gpu_config* cfg);
@@ -136,7 +138,15 @@ typedef enum recs_gpu_system_kind {
     /* crates/ecs_bench_suite/src/recs/simple_iter.rs:47-49 -- |Write<Position>, Read<Velocity>|
      * position.0 += velocity.0; also the generic (Write<A>, Read<B>) f32-vector par-iter query.
      * components = {A (written), B (read)}                                                   */
-    RECS_SYS_QUERY_ADD = 8
+    RECS_SYS_QUERY_ADD = 8,
+    /* crates/n-body/examples/n_body_demo.rs:54-71 -- collision(Entity, Read<Position>,
+     * Query<(Entity, Read<Position>)>, Commands): an entity is removed when another entity of the
+     * query is closer than COLLISION_RADIUS.  components = {Position}.  The system only DECIDES;
+     * the removals are fetched with recs_gpu_system_removals and played back on the host World. */
+    RECS_SYS_NBODY_COLLISION = 9,
+    /* crates/rain-simulation/src/lib.rs:152-156 -- ground_collision(Entity, Read<Position>, Commands):
+     * removed when position.y <= GROUND_HEIGHT.  components = {Position}                          */
+    RECS_SYS_RAIN_GROUND_COLLISION = 10
 } recs_gpu_system_kind;
 
 /* One entry of `System::component_accesses()` (crates/ecs/src/systems/mod.rs:88-94). */
@@ -168,6 +178,11 @@ int32_t recs_gpu_system_set_archetypes(recs_gpu_ctx* ctx, uint32_t system_id,
  * crates/ecs/src/systems/mod.rs:1042). */
 int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* ctx, uint32_t system_id,
                                              const uint32_t* archetype_indices, uint32_t n);
+
+/* The `Commands::remove(entity)` calls a removal-deciding system issued during its last run, as
+ * ascending component indices (rows) of one of its outer archetypes.  Synchronises the stream. */
+int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t archetype_index,
+                                 uint32_t* out_rows, uint32_t cap, uint32_t* out_count);
 
 #define RECS_GPU_ASYNC 0u /* enqueue only: every dependent is a GPU system of this context    */
 #define RECS_GPU_SYNC 1u  /* return after the system's writes are visible to the host thread  */
@@ -216,6 +231,7 @@ typedef struct recs_gpu_timing {
     float acceleration_ms;
     float pack_ms;
     float other_ms;
+    float gather_ms;             /* NCCL position all-gather (comm stream; includes waiting for peers) */
     uint64_t kernel_launches;    /* kernels launched by this library since create / reset     */
     uint64_t gravity_launches;
 } recs_gpu_timing;

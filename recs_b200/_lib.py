@@ -37,6 +37,8 @@ SYS_RAIN_WIND = 5
 SYS_RAIN_MOVEMENT = 6
 SYS_RAIN_WIND_DIRECTION = 7
 SYS_QUERY_ADD = 8
+SYS_NBODY_COLLISION = 9
+SYS_RAIN_GROUND_COLLISION = 10
 
 GPU_ASYNC = 0
 GPU_SYNC = 1
@@ -58,6 +60,8 @@ class Config(C.Structure):
         ("rain_terminal", C.c_float),
         ("rain_wind_accel", C.c_float),
         ("rain_wind_deg_per_s", C.c_float),
+        ("rain_ground_height", C.c_float),
+        ("nbody_collision_radius", C.c_float),
     ]
 
 
@@ -78,6 +82,7 @@ class Timing(C.Structure):
         ("acceleration_ms", C.c_float),
         ("pack_ms", C.c_float),
         ("other_ms", C.c_float),
+        ("gather_ms", C.c_float),
         ("kernel_launches", C.c_uint64),
         ("gravity_launches", C.c_uint64),
     ]
@@ -102,6 +107,7 @@ GPU_SYMBOLS = {
     "recs_gpu_system_describe": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(SystemDesc)]),
     "recs_gpu_system_set_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_system_set_query_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
+    "recs_gpu_system_removals": (C.c_int32, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
     "recs_gpu_run_system": (C.c_int32, [_ctx, C.c_uint32, C.c_uint32]),
     "recs_gpu_set_tick_order": (C.c_int32, [_ctx, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_tick": (C.c_int32, [_ctx, C.c_uint32]),

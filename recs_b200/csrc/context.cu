@@ -40,10 +40,20 @@ struct System {
     std::string name;
     std::vector<recs_gpu_access> access;
     std::vector<uint32_t> archs;   // outer parameters' archetypes, iteration order
-    std::vector<uint32_t> qarchs;  // nested Query archetypes (gravity)
+    std::vector<uint32_t> qarchs;  // nested Query archetypes (gravity, collision)
+    // removal-deciding systems: per outer archetype, flags + compacted row list of the last run
+    struct Removals {
+        uint32_t* flags = nullptr;
+        uint32_t* rows = nullptr;
+        uint32_t* counter = nullptr;
+        size_t cap_rows = 0;
+        uint32_t n_rows = 0;
+        bool valid = false;
+    };
+    std::map<uint32_t, Removals> removals;
 };
 
-enum TimeSlot { T_GRAVITY = 0, T_REDUCE, T_MOVEMENT, T_ACCEL, T_PACK, T_OTHER, T_CHAIN, T_COUNT };
+enum TimeSlot { T_GRAVITY = 0, T_REDUCE, T_MOVEMENT, T_ACCEL, T_PACK, T_OTHER, T_CHAIN, T_GATHER, T_COUNT };
 
 struct TimedSpan {
     cudaEvent_t a, b;
@@ -291,8 +301,20 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));  // after launch A (and the pack before it)
         RECS_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
         float* send = c->posm + (size_t)slice * (uint64_t)c->cfg.rank * 4;
+        TimedSpan span;
+        const bool timed = c->timing && !c->capturing;
+        if (timed) {
+            span.a = get_event(c);
+            span.b = get_event(c);
+            span.slot = T_GATHER;
+            cudaEventRecord(span.a, c->comm_stream);
+        }
         int r = c->nccl.AllGather(send, c->posm, (size_t)slice * 4, /*ncclFloat32*/ 7, c->comm, c->comm_stream);
         if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclAllGather: ") + c->nccl.GetErrorString(r));
+        if (timed) {
+            cudaEventRecord(span.b, c->comm_stream);
+            c->spans.push_back(span);
+        }
         RECS_CUDA(c, cudaEventRecord(c->ev_gather, c->comm_stream));
         return RECS_OK;
     };
@@ -480,6 +502,57 @@ int32_t run_rain_vel(recs_gpu_ctx* c, System& sys, bool wind) {
     return RECS_OK;
 }
 
+// collision / ground_collision: one flag per outer row, then a compacted list of flagged rows.
+int32_t run_removal_system(recs_gpu_ctx* c, System& sys) {
+    if (c->cfg.world_size > 1) return fail(c, RECS_ERR_UNSUPPORTED, "removal-deciding systems are single-GPU");
+    const uint64_t POS = sys.comp[0];
+    const float r2 = c->cfg.nbody_collision_radius * c->cfg.nbody_collision_radius;  // COLLISION_RADIUS * COLLISION_RADIUS
+    for (auto& kv : sys.removals) kv.second.valid = false;
+    for (uint32_t a : sys.archs) {
+        Column* p;
+        int32_t st;
+        if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
+        if (p->count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
+        const uint32_t n = (uint32_t)p->count;
+        System::Removals& r = sys.removals[a];
+        if (r.cap_rows < std::max<uint32_t>(n, 1)) {
+            if (c->capturing) return fail(c, RECS_ERR_CUDA, "workspace growth during graph capture");
+            if (r.flags) RECS_CUDA(c, cudaFree(r.flags));
+            if (r.rows) RECS_CUDA(c, cudaFree(r.rows));
+            if (!r.counter) RECS_CUDA(c, cudaMalloc((void**)&r.counter, sizeof(uint32_t)));
+            size_t cap = 256;
+            while (cap < n) cap <<= 1;
+            RECS_CUDA(c, cudaMalloc((void**)&r.flags, cap * sizeof(uint32_t)));
+            RECS_CUDA(c, cudaMalloc((void**)&r.rows, cap * sizeof(uint32_t)));
+            r.cap_rows = cap;
+        }
+        r.n_rows = n;
+        RECS_CUDA(c, cudaMemsetAsync(r.counter, 0, sizeof(uint32_t), c->stream));
+        if (n == 0) {
+            r.valid = true;
+            continue;
+        }
+        Timed t(c, T_OTHER);
+        if (sys.kind == RECS_SYS_NBODY_COLLISION) {
+            RECS_CUDA(c, cudaMemsetAsync(r.flags, 0, (size_t)n * sizeof(uint32_t), c->stream));
+            for (uint32_t qa : sys.qarchs) {
+                Column* q;
+                if ((st = need_column(c, qa, POS, 12, &q)) != RECS_OK) return st;
+                RECS_CUDA(c, launch_collision_flags((const float*)q->dev, (uint32_t)q->count, (const float*)p->dev, n,
+                                                    qa == a ? 1 : 0, r2, r.flags, c->stream));
+                c->kernel_launches += q->count ? 1 : 0;
+            }
+        } else {
+            RECS_CUDA(c, launch_below_flags((const float*)p->dev, n, /*y*/ 1, c->cfg.rain_ground_height, r.flags, c->stream));
+            c->kernel_launches++;
+        }
+        RECS_CUDA(c, launch_compact_flags(r.flags, n, r.rows, r.counter, (uint32_t)r.cap_rows, c->stream));
+        c->kernel_launches++;
+        r.valid = true;
+    }
+    return RECS_OK;
+}
+
 int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
     if (id >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system id");
     System& s = c->systems[id];
@@ -502,6 +575,9 @@ int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
             return RECS_OK;
         case RECS_SYS_QUERY_ADD:
             return run_axpy(c, s, s.comp[0], s.comp[1], 1.0f, T_OTHER, false);
+        case RECS_SYS_NBODY_COLLISION:
+        case RECS_SYS_RAIN_GROUND_COLLISION:
+            return run_removal_system(c, s);
     }
     return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system kind");
 }
@@ -637,6 +713,17 @@ void fill_system(System& s, recs_gpu_system_kind kind, const uint64_t* ids) {
             acc(ids[0], true);
             acc(ids[1], false);
             break;
+        case RECS_SYS_NBODY_COLLISION:  // (Entity, Read<Position>, Query<(Entity, Read<Position>)>, Commands)
+            s.name = "collision";
+            s.n_comp = 1;
+            acc(ids[0], false);
+            acc(ids[0], false);
+            break;
+        case RECS_SYS_RAIN_GROUND_COLLISION:  // (Entity, Read<Position>, Commands)
+            s.name = "ground_collision";
+            s.n_comp = 1;
+            acc(ids[0], false);
+            break;
     }
     for (uint32_t i = 0; i < s.n_comp; ++i) s.comp[i] = ids[i];
 }
@@ -652,6 +739,8 @@ uint32_t kind_components(int kind) {
             return 2;
         case RECS_SYS_RAIN_GRAVITY:
         case RECS_SYS_RAIN_WIND:
+        case RECS_SYS_NBODY_COLLISION:
+        case RECS_SYS_RAIN_GROUND_COLLISION:
             return 1;
         case RECS_SYS_RAIN_WIND_DIRECTION:
             return 0;
@@ -683,6 +772,8 @@ void recs_gpu_default_config(recs_gpu_config* cfg) {
     cfg->rain_terminal = 9.0f;           // :60
     cfg->rain_wind_accel = 10.0f;        // :72
     cfg->rain_wind_deg_per_s = 10.0f;    // :76
+    cfg->rain_ground_height = 0.0f;      // :150
+    cfg->nbody_collision_radius = 0.1f;  // crates/n-body/examples/n_body_demo.rs:16
 }
 
 int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
@@ -739,6 +830,12 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
         drop_graph(c);
         for (auto& kv : c->columns)
             if (kv.second.dev) cudaFree(kv.second.dev);
+        for (auto& sys : c->systems)
+            for (auto& kv : sys.removals) {
+                if (kv.second.flags) cudaFree(kv.second.flags);
+                if (kv.second.rows) cudaFree(kv.second.rows);
+                if (kv.second.counter) cudaFree(kv.second.counter);
+            }
         if (c->posm) cudaFree(c->posm);
         if (c->frags) cudaFree(c->frags);
         if (c->l2_flush) cudaFree(c->l2_flush);
@@ -898,6 +995,28 @@ int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* c, uint32_t id, const
     return RECS_OK;
 }
 
+int32_t recs_gpu_system_removals(recs_gpu_ctx* c, uint32_t id, uint32_t arch, uint32_t* out_rows, uint32_t cap,
+                                 uint32_t* out_count) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || !out_count) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_removals: bad argument");
+    System& s = c->systems[id];
+    auto it = s.removals.find(arch);
+    if (it == s.removals.end() || !it->second.valid)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_removals: the system has not run over this archetype");
+    System::Removals& r = it->second;
+    uint32_t n = 0;
+    RECS_CUDA(c, cudaMemcpyAsync(&n, r.counter, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    *out_count = n;
+    if (out_rows && n) {
+        std::vector<uint32_t> rows(n);
+        RECS_CUDA(c, cudaMemcpy(rows.data(), r.rows, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::sort(rows.begin(), rows.end());  // playback order: ascending component index
+        for (uint32_t i = 0; i < n && i < cap; ++i) out_rows[i] = rows[i];
+    }
+    return RECS_OK;
+}
+
 int32_t recs_gpu_run_system(recs_gpu_ctx* c, uint32_t id, uint32_t flags) {
     RECS_ENTER(c);
     int32_t st = run_system_locked(c, id);
@@ -1036,6 +1155,7 @@ int32_t recs_gpu_get_timing(recs_gpu_ctx* c, recs_gpu_timing* out) {
     RECS_ENTER(c);
     if (!out) return fail(c, RECS_ERR_INVALID_ARGUMENT, "get_timing: null");
     RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    RECS_CUDA(c, cudaStreamSynchronize(c->comm_stream));
     float acc[T_COUNT] = {0};
     for (auto& s : c->spans) {
         float ms = 0.f;
@@ -1051,6 +1171,7 @@ int32_t recs_gpu_get_timing(recs_gpu_ctx* c, recs_gpu_timing* out) {
     out->acceleration_ms = acc[T_ACCEL];
     out->pack_ms = acc[T_PACK];
     out->other_ms = acc[T_OTHER];
+    out->gather_ms = acc[T_GATHER];
     out->kernel_launches = c->kernel_launches;
     out->gravity_launches = c->gravity_launches;
     return RECS_OK;

@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include <map>
+#include <set>
 
 #include "host.h"
 
@@ -64,13 +65,27 @@ std::vector<recs_param_token> gpu_kind_tokens(recs_gpu_system_kind kind, const u
             return {tok(RECS_PARAM_WRITE, c[0])};
         case RECS_SYS_RAIN_WIND_DIRECTION:  // :78
             return {};
+        case RECS_SYS_NBODY_COLLISION:  // crates/n-body/examples/n_body_demo.rs:54-59
+            return {tok(RECS_PARAM_ENTITY), tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_QUERY_BEGIN), tok(RECS_PARAM_ENTITY),
+                    tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_QUERY_END), tok(RECS_PARAM_COMMANDS)};
+        case RECS_SYS_RAIN_GROUND_COLLISION:  // crates/rain-simulation/src/lib.rs:152
+            return {tok(RECS_PARAM_ENTITY), tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_COMMANDS)};
     }
     return {};
 }
 
 }  // namespace
 
+struct CreateCommand {
+    std::vector<uint64_t> ids;
+    std::vector<std::vector<uint8_t>> values;
+};
+
 struct recs_app {
+    std::vector<CreateCommand> creates;   // EntityCommand::Create, record order
+    std::vector<recs_entity> removes;     // EntityCommand::Remove, record order
+    std::vector<std::pair<uint32_t, std::vector<uint32_t>>> gpu_removal_sources;  // (system index, outer archetypes) run this tick
+    uint64_t last_created = 0, last_removed = 0;
     recs_gpu_ctx* gpu = nullptr;
     recs_world* world = nullptr;
     std::vector<AppSystem> systems;
@@ -148,6 +163,8 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
         if ((st = recs_gpu_system_set_query_archetypes(app->gpu, s.gpu_id, qarchs.data(), (uint32_t)qarchs.size())) != RECS_OK)
             return gpu_fail(app, st);
     if ((st = recs_gpu_run_system(app->gpu, s.gpu_id, RECS_GPU_ASYNC)) != RECS_OK) return gpu_fail(app, st);
+    if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION)
+        app->gpu_removal_sources.push_back(std::make_pair((uint32_t)(&s - app->systems.data()), archs));
     for (const Param& p : s.params)
         if (p.op == RECS_PARAM_WRITE)
             for (uint32_t a : archs) app->mirror[ColKey(a, p.comp)].device_dirty = true;
@@ -191,6 +208,50 @@ int32_t run_cpu_system(recs_app* app, AppSystem& s) {
             recs_world_release_column(app->world, a, p.comp, p.op == RECS_PARAM_WRITE);
             if (p.op == RECS_PARAM_WRITE) app->mirror[ColKey(a, p.comp)].host_dirty = true;
         }
+    }
+    return RECS_OK;
+}
+
+// CommandPlayer::playback_commands (crates/ecs/src/systems/command_buffers.rs:377-435): creates, then
+// removes (a set: duplicates collapse; entities that no longer exist are skipped like the reference's
+// logged-and-ignored removal errors).  Removal order here is record order (GPU systems: system order,
+// archetype order, ascending component index); the reference iterates a hash set, so the final row
+// ORDER inside an archetype after several removals in one playback is not pinned by it.
+int32_t playback_commands(recs_app* app) {
+    app->last_created = app->last_removed = 0;
+    std::vector<recs_entity> to_remove = app->removes;
+    for (auto& src : app->gpu_removal_sources) {
+        AppSystem& s = app->systems[src.first];
+        for (uint32_t arch : src.second) {
+            uint32_t n = 0;
+            int32_t st = recs_gpu_system_removals(app->gpu, s.gpu_id, arch, nullptr, 0, &n);
+            if (st != RECS_OK) return gpu_fail(app, st);
+            if (!n) continue;
+            std::vector<uint32_t> rows(n);
+            if ((st = recs_gpu_system_removals(app->gpu, s.gpu_id, arch, rows.data(), n, &n)) != RECS_OK) return gpu_fail(app, st);
+            const Archetype& a = app->world->archetypes[arch];
+            for (uint32_t r : rows)
+                if (r < a.entities.size()) to_remove.push_back(a.entities[r]);
+        }
+    }
+    app->gpu_removal_sources.clear();
+    app->removes.clear();
+    if (app->creates.empty() && to_remove.empty()) return RECS_OK;
+    // structural change: the host copy must be current before rows move
+    int32_t st = recs_app_sync_to_host(app);
+    if (st != RECS_OK) return st;
+    for (CreateCommand& cmd : app->creates) {
+        std::vector<const void*> ptrs(cmd.ids.size());
+        for (size_t i = 0; i < cmd.ids.size(); ++i) ptrs[i] = cmd.values[i].empty() ? nullptr : cmd.values[i].data();
+        st = recs_world_create_entity(app->world, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
+        if (st != RECS_OK) return app->fail(st, recs_world_last_error(app->world));
+        app->last_created++;
+    }
+    app->creates.clear();
+    std::set<uint64_t> seen;
+    for (recs_entity e : to_remove) {
+        if (!seen.insert(entity_key(e)).second) continue;
+        if (recs_world_delete_entity(app->world, e) == RECS_OK) app->last_removed++;
     }
     return RECS_OK;
 }
@@ -300,7 +361,37 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
             for (uint32_t i = 0; i < got; ++i) recs_schedule_complete(app->schedule, batch[i]);
             ++batch_no;
         }
+        // loop { runner.tick(); runner.playback_commands(); } (lib.rs:321-323)
+        if ((st = playback_commands(app)) != RECS_OK) return st;
     }
+    return RECS_OK;
+}
+
+int32_t recs_app_command_create(recs_app* app, const uint64_t* ids, const void* const* values, uint32_t n) {
+    if (!app || (n && !ids)) return RECS_ERR_INVALID_ARGUMENT;
+    CreateCommand cmd;
+    for (uint32_t i = 0; i < n; ++i) {
+        auto it = app->world->registry.find(ids[i]);
+        if (it == app->world->registry.end()) return app->fail(RECS_ERR_INVALID_ARGUMENT, "command_create: component is not registered");
+        cmd.ids.push_back(ids[i]);
+        std::vector<uint8_t> bytes(it->second.elem);
+        if (it->second.elem && values && values[i]) memcpy(bytes.data(), values[i], it->second.elem);
+        cmd.values.push_back(bytes);
+    }
+    app->creates.push_back(cmd);
+    return RECS_OK;
+}
+
+int32_t recs_app_command_remove(recs_app* app, recs_entity entity) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    app->removes.push_back(entity);
+    return RECS_OK;
+}
+
+int32_t recs_app_last_playback(recs_app* app, uint64_t* out_created, uint64_t* out_removed) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (out_created) *out_created = app->last_created;
+    if (out_removed) *out_removed = app->last_removed;
     return RECS_OK;
 }
 

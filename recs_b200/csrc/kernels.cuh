@@ -108,6 +108,16 @@ cudaError_t launch_rain_wind(float* vel, uint64_t n, float wx, float wy, float w
 cudaError_t launch_rain_fused(float* vel, float* pos, uint64_t n, float wx, float wy, float wz,
                               float gravity_dt, float terminal, float dt, cudaStream_t s);
 
+// ---- removal-deciding systems (select.cu) --------------------------------------------------------
+// flags[row] |= 1 if another row of `qpos` is closer than sqrt(radius2) (crates/n-body/examples/n_body_demo.rs:54-71)
+cudaError_t launch_collision_flags(const float* qpos, uint32_t n_q, const float* ipos, uint32_t n_rows,
+                                   int same_archetype, float radius2, uint32_t* flags, cudaStream_t s);
+// flags[row] = pos[row].field <= threshold (crates/rain-simulation/src/lib.rs:152-156)
+cudaError_t launch_below_flags(const float* pos, uint32_t n_rows, uint32_t field, float threshold, uint32_t* flags,
+                               cudaStream_t s);
+cudaError_t launch_compact_flags(const uint32_t* flags, uint32_t n_rows, uint32_t* out, uint32_t* counter, uint32_t cap,
+                                 cudaStream_t s);
+
 // ---- measurement ---------------------------------------------------------------------------------
 cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
                              unsigned long long* cycles, cudaStream_t s);

@@ -91,6 +91,9 @@ ECS_SYMBOLS = {
     "recs_app_add_gpu_system": (C.c_int32, [_a, C.c_int32, _u64p, C.c_uint32, _u32p]),
     "recs_app_add_cpu_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SYSTEM_FN, C.c_void_p, _u32p]),
     "recs_app_run": (C.c_int32, [_a, C.c_uint32, C.c_int32]),
+    "recs_app_command_create": (C.c_int32, [_a, _u64p, _vpp, C.c_uint32]),
+    "recs_app_command_remove": (C.c_int32, [_a, Entity]),
+    "recs_app_last_playback": (C.c_int32, [_a, _u64p, _u64p]),
     "recs_app_last_tick_order": (C.c_int32, [_a, _u32p, _u32p, C.c_uint32, _u32p]),
     "recs_app_sync_to_host": (C.c_int32, [_a]),
     "recs_app_mark_host_dirty": (C.c_int32, [_a, C.c_uint32]),
@@ -480,6 +483,19 @@ class Application:
         self._check(lib.recs_app_add_cpu_system(self._h, name.encode(), arr, n, cb, None, C.byref(idx)), "recs_app_add_cpu_system")
         self.system_names.append(name)
         return int(idx.value)
+
+    def command_create(self, components: dict) -> None:
+        """`commands.create(...)` from inside a CPU system."""
+        ids, ptrs, keep = self.world._marshal(components)
+        self._check(lib.recs_app_command_create(self._h, ids, ptrs, len(components)), "recs_app_command_create")
+
+    def command_remove(self, entity: Entity) -> None:
+        self._check(lib.recs_app_command_remove(self._h, entity), "recs_app_command_remove")
+
+    def last_playback(self):
+        c, r = C.c_uint64(), C.c_uint64()
+        self._check(lib.recs_app_last_playback(self._h, C.byref(c), C.byref(r)), "recs_app_last_playback")
+        return int(c.value), int(r.value)
 
     def run(self, n_ticks: int = 1, ordered: bool = False) -> None:
         self._check(lib.recs_app_run(self._h, n_ticks, 1 if ordered else 0), "recs_app_run")

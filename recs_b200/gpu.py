@@ -138,6 +138,14 @@ class GpuContext:
             lib.recs_gpu_system_set_query_archetypes(self._ctx, system, arr, n), "recs_gpu_system_set_query_archetypes"
         )
 
+    def system_removals(self, system: int, archetype: int) -> np.ndarray:
+        """Rows (ascending component indices) the system's last run asked to remove."""
+        n = C.c_uint32()
+        self._check(lib.recs_gpu_system_removals(self._ctx, system, archetype, None, 0, C.byref(n)), "recs_gpu_system_removals")
+        out = (C.c_uint32 * max(n.value, 1))()
+        self._check(lib.recs_gpu_system_removals(self._ctx, system, archetype, out, n.value, C.byref(n)), "recs_gpu_system_removals")
+        return np.array(out[: n.value], dtype=np.uint32)
+
     def run_system(self, system: int, sync: bool = True) -> None:
         self._check(
             lib.recs_gpu_run_system(self._ctx, system, _lib.GPU_SYNC if sync else _lib.GPU_ASYNC), "recs_gpu_run_system"

@@ -1,0 +1,227 @@
+"""Removal-deciding GPU systems + command playback against the host World:
+the n-body demo's `collision` system (crates/n-body/examples/n_body_demo.rs:54-71) and the complete
+rain-simulation tick (crates/rain-simulation/src/lib.rs:62-160, registration order of
+crates/ecs_bench_suite/src/recs/rain_simulation.rs:56-65), compared with the Python/C oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import ecs_oracle as O
+from recs_b200 import _lib, ecs
+from tests.util import rel_err_rows
+
+pytestmark = pytest.mark.gpu
+F3 = np.dtype((np.float32, 3))
+f32 = np.float32
+
+
+def _arr(ptr, count, width):
+    return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(count, width) if width > 1 else (count,))
+
+
+# ---------------------------------------------------------------------------------------------------
+# collision kernel alone
+# ---------------------------------------------------------------------------------------------------
+def _collision_mask(pos, radius=f32(0.1)):
+    d = pos[None, :, :] - pos[:, None, :]  # other - self, f32
+    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    np.fill_diagonal(d2, np.inf)
+    return (d2 < radius * radius).any(axis=1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 257, 1500])
+def test_collision_flags_match_oracle_bit_exact(gpu_ctx, n):
+    POS = 1
+    rng = np.random.default_rng(n)
+    pos = (rng.random((n, 3), dtype=np.float32) * f32(1.5)).astype(np.float32)
+    if n >= 2:
+        pos[1] = pos[0]  # coincident distinct entities do collide (only the entity itself is skipped)
+    gpu_ctx.bind_column(1, POS, pos)
+    gpu_ctx.upload(1, POS)
+    sid = gpu_ctx.create_system(_lib.SYS_NBODY_COLLISION, [POS])
+    gpu_ctx.set_archetypes(sid, [1])
+    gpu_ctx.set_query_archetypes(sid, [1])
+    gpu_ctx.run_system(sid)
+    rows = gpu_ctx.system_removals(sid, 1)
+    want = np.flatnonzero(_collision_mask(pos)).astype(np.uint32)
+    assert np.array_equal(rows, want)
+    if n >= 2:
+        assert 0 in rows and 1 in rows
+
+
+def test_ground_collision_flags(gpu_ctx):
+    POS = 1
+    pos = np.array([[0, 1, 0], [0, 0, 0], [0, -0.0, 5], [1, -3, 1], [2, 1e-9, 2]], np.float32)
+    gpu_ctx.bind_column(2, POS, pos)
+    gpu_ctx.upload(2, POS)
+    sid = gpu_ctx.create_system(_lib.SYS_RAIN_GROUND_COLLISION, [POS])
+    gpu_ctx.set_archetypes(sid, [2])
+    gpu_ctx.run_system(sid)
+    assert list(gpu_ctx.system_removals(sid, 2)) == [1, 2, 3]  # y <= 0 (crates/rain-simulation/src/lib.rs:153)
+
+
+# ---------------------------------------------------------------------------------------------------
+# n-body demo system set through the Application: gravity, collision -> acceleration -> movement
+# ---------------------------------------------------------------------------------------------------
+def test_nbody_demo_with_collision_through_application(gpu_ctx, nbody_oracle):
+    POS, MASS, VEL, ACC = 1, 2, 3, 4
+    n, ticks = 240, 4
+    rng = np.random.default_rng(42)
+    pos = (rng.random((n, 3), dtype=np.float32) * f32(1.2)).astype(np.float32)
+    mass = np.full(n, 1.0e3, np.float32)  # light bodies: gravity barely moves them within a few ticks
+    vel = ((rng.random((n, 3), dtype=np.float32) - f32(0.5)) * f32(200.0)).astype(np.float32)
+    acc = np.zeros((n, 3), np.float32)
+
+    app = ecs.Application(gpu=gpu_ctx)
+    w = app.world
+    for c, dt, name in ((POS, F3, "Position"), (MASS, np.float32, "Mass"), (VEL, F3, "Velocity"), (ACC, F3, "Acceleration")):
+        w.register_component(c, dt, name)
+    # registration order of the demo (n_body_demo.rs:39-42)
+    app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+    app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+    app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+    app.add_gpu_system(_lib.SYS_NBODY_COLLISION, [POS], "collision")
+    w.create_entities(n, {POS: pos, MASS: mass, VEL: vel, ACC: acc})
+
+    # oracle: same World operations + the CPU systems in the order the schedule produces
+    ow = O.World()
+    ents = [ow.create_entity({POS: tuple(pos[k]), MASS: float(mass[k]), VEL: tuple(vel[k]), ACC: tuple(acc[k])}) for k in range(n)]
+    removed_total = 0
+    for tick in range(ticks):
+        app.run(1)
+        order, batches = app.last_tick_order()
+        names = [app.system_names[i] for i in order]
+        # {gravity, collision} -> {acceleration} -> {movement}
+        assert names.index("gravity") < names.index("acceleration") < names.index("movement")
+        assert names.index("collision") < names.index("movement")
+
+        cols = ow.archetypes[1].columns
+        p = np.array(cols[POS], np.float32).reshape(-1, 3)
+        m = np.array(cols[MASS], np.float32)
+        v = np.array(cols[VEL], np.float32).reshape(-1, 3)
+        a = nbody_oracle.gravity(np.ascontiguousarray(p), np.ascontiguousarray(m))
+        mask = _collision_mask(p)
+        v = np.ascontiguousarray(v)
+        p = np.ascontiguousarray(p)
+        nbody_oracle.axpy(v, a, nbody_oracle.dt)  # acceleration
+        nbody_oracle.axpy(p, v, nbody_oracle.dt)  # movement
+        cols[POS] = [tuple(r) for r in p]
+        cols[VEL] = [tuple(r) for r in v]
+        cols[ACC] = [tuple(r) for r in a]
+        doomed = [ow.archetypes[1].entities[i] for i in np.flatnonzero(mask)]  # ascending component index
+        for e in doomed:
+            ow.delete_entity(e)
+        removed_total += len(doomed)
+
+        created, removed = app.last_playback()
+        assert (created, removed) == (0, len(doomed))
+        app.sync_to_host()
+        assert w.archetype_entities(1) == [(e.id, e.generation) for e in ow.archetypes[1].entities]
+        op = np.array(ow.archetypes[1].columns[POS], np.float32).reshape(-1, 3)
+        ov = np.array(ow.archetypes[1].columns[VEL], np.float32).reshape(-1, 3)
+        assert rel_err_rows(w.column(1, POS), op, floor=1.0).max() <= 1e-5
+        assert rel_err_rows(w.column(1, VEL), ov, floor=1.0).max() <= 1e-4
+    assert removed_total > 10  # the scene does collide
+
+
+# ---------------------------------------------------------------------------------------------------
+# the complete rain tick: clouds spawn drops (CPU, Commands::create), drops fall (GPU), drops that
+# reach the ground are removed (GPU decides, host plays back)
+# ---------------------------------------------------------------------------------------------------
+def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle):
+    VEL, POS, MASS, CLOUD = 20, 21, 22, 23
+    n_clouds, ticks = 9, 60
+    app = ecs.Application(gpu=gpu_ctx)
+    w = app.world
+    for c, dt, name in ((VEL, F3, "Velocity"), (POS, F3, "Position"), (MASS, np.float32, "Mass"), (CLOUD, F3, "Cloud")):
+        w.register_component(c, dt, name)
+    DT, MASS_PER_DROP = f32(0.05), f32(0.1)
+
+    def rain(arch, count, cols):  # rain(Read<Cloud>, Read<Position>, Write<Mass>, Commands)   lib.rs:128-148
+        pos, mass = _arr(cols[1], count, 3), _arr(cols[2], count, 1)
+        for k in range(count):
+            while mass[k] > MASS_PER_DROP:
+                app.command_create({VEL: np.zeros(3, np.float32), MASS: MASS_PER_DROP, POS: pos[k].copy()})
+                mass[k] = mass[k] - MASS_PER_DROP
+
+    def vapor(arch, count, cols):  # vapor_accumulation(Read<Cloud>, Write<Mass>)   lib.rs:158-160
+        cloud, mass = _arr(cols[0], count, 3), _arr(cols[1], count, 1)
+        mass += cloud[:, 0] * DT
+
+    ticks_seen = []
+    # registration order of the benchmark (recs/rain_simulation.rs:56-65)
+    app.add_gpu_system(_lib.SYS_RAIN_GRAVITY, [VEL], "gravity")
+    app.add_gpu_system(_lib.SYS_RAIN_WIND, [VEL], "wind")
+    app.add_gpu_system(_lib.SYS_RAIN_WIND_DIRECTION, [], "wind_direction")
+    app.add_gpu_system(_lib.SYS_RAIN_MOVEMENT, [POS, VEL], "movement")
+    app.add_cpu_system("rain", [("read", CLOUD), ("read", POS), ("write", MASS), ("commands",)], rain)
+    app.add_gpu_system(_lib.SYS_RAIN_GROUND_COLLISION, [POS], "ground_collision")
+    app.add_cpu_system("vapor_accumulation", [("read", CLOUD), ("write", MASS)], vapor)
+    app.add_cpu_system("benchmark_system", [], lambda a, c, cols: ticks_seen.append(1))
+    # create_evenly_interspersed_clouds (crates/rain-simulation/src/scene.rs:27-54); low clouds so drops land soon
+    side = int(np.sqrt(n_clouds))
+    ow = O.World()
+    for x in range(side):
+        for z in range(side):
+            comps = {CLOUD: (1.0, 10.0, 10.0), POS: (x * 10.0, 2.0, z * 10.0), MASS: 0.0}
+            w.create_entity({k: np.asarray(v, np.float32) for k, v in comps.items()})
+            ow.create_entity(dict(comps))
+
+    direction = np.array([1.0, 0.0, 0.0], np.float32)
+    total_created = total_removed = 0
+    for tick in range(ticks):
+        app.run(1)
+        order, _ = app.last_tick_order()
+        names = [app.system_names[i] for i in order]
+        for before, after in (("wind", "gravity"), ("gravity", "movement"), ("rain", "movement"),
+                              ("ground_collision", "movement"), ("vapor_accumulation", "rain")):
+            assert names.index(before) < names.index(after)
+        # ---- oracle tick in the same order: wind, wind_direction, ground_collision, vapor, [gravity, rain], movement
+        drops = ow.archetypes[2] if len(ow.archetypes) > 2 else None
+        clouds = ow.archetypes[1]
+        to_remove = []
+        if drops is not None and drops.entities:
+            v = np.array(drops.columns[VEL], np.float32).reshape(-1, 3)
+            p = np.array(drops.columns[POS], np.float32).reshape(-1, 3)
+            nbody_oracle.rain_wind(v, direction)
+        direction = nbody_oracle.rain_wind_direction(direction)
+        # ground_collision over every archetype with a Position, ascending archetype / row
+        for ai in (1, 2):
+            if ai < len(ow.archetypes):
+                arch = ow.archetypes[ai]
+                pp = p if (ai == 2 and drops is not None and drops.entities) else np.array(arch.columns[POS], np.float32).reshape(-1, 3)
+                to_remove += [arch.entities[i] for i in range(len(arch.entities)) if pp[i, 1] <= 0.0]
+        cm = np.array(clouds.columns[MASS], np.float32)
+        cm = (cm + np.array([c[0] for c in clouds.columns[CLOUD]], np.float32) * DT).astype(np.float32)
+        if drops is not None and drops.entities:
+            nbody_oracle.rain_gravity(v)
+        creates = []
+        for k in range(len(cm)):
+            while cm[k] > MASS_PER_DROP:
+                creates.append({VEL: (0.0, 0.0, 0.0), MASS: float(MASS_PER_DROP), POS: clouds.columns[POS][k]})
+                cm[k] = cm[k] - MASS_PER_DROP
+        clouds.columns[MASS] = [float(x) for x in cm]
+        if drops is not None and drops.entities:
+            nbody_oracle.rain_movement(p, v)
+            drops.columns[VEL] = [tuple(r) for r in v]
+            drops.columns[POS] = [tuple(r) for r in p]
+        for comps in creates:  # playback: creates first, then removes
+            ow.create_entity(dict(comps))
+        for e in to_remove:
+            ow.delete_entity(e)
+        total_created += len(creates)
+        total_removed += len(to_remove)
+        assert app.last_playback() == (len(creates), len(to_remove)), tick
+
+    app.sync_to_host()
+    assert len(ticks_seen) == ticks and total_created > 20 and total_removed > 5
+    assert w.archetype_count() == len(ow.archetypes) == 3
+    assert w.archetype_components(2) == sorted([VEL, MASS, POS])
+    for ai in (1, 2):
+        assert w.archetype_entities(ai) == [(e.id, e.generation) for e in ow.archetypes[ai].entities]
+    # every streaming system is bit-exact, so the whole state is
+    d = ow.archetypes[2]
+    assert np.array_equal(w.column(2, POS).view(np.uint32), np.array(d.columns[POS], np.float32).reshape(-1, 3).view(np.uint32))
+    assert np.array_equal(w.column(2, VEL).view(np.uint32), np.array(d.columns[VEL], np.float32).reshape(-1, 3).view(np.uint32))
+    assert np.array_equal(w.column(1, MASS).view(np.uint32), np.array(ow.archetypes[1].columns[MASS], np.float32).view(np.uint32))
