@@ -78,6 +78,7 @@ struct recs_gpu_ctx {
     int sm_count = 148;
     int grav_ctas_per_sm[kGravVariantCount] = {0};
     bool grav_variant_forced = false;
+    bool posm_scaled = false;
     int grav_variant = kGravVariantDefault;
 
     std::map<ColKey, Column> columns;
@@ -269,15 +270,31 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     int32_t st = ensure(c, &c->posm, &c->posm_cap, std::max<size_t>(n_jpad, kGravTile) * 16);
     if (st != RECS_OK) return st;
 
+    // kernel shape by outer-row count (profiles/r01_gravity_small_n_sweep.txt, r01_gravity_variant_sweep5.txt):
+    // small i-blocks give the stream-K split more units, and below 16 384 rows the redo of the tile that holds a
+    // warp's own bodies is a large enough share that masking every pair exactly is cheaper
+    int variant = c->grav_variant;
+    if (!c->grav_variant_forced) {
+        uint64_t max_rows = 0;
+        for (uint32_t a : sys.archs) {
+            Column* p = find_column(c, a, POS);
+            if (p) max_rows = std::max<uint64_t>(max_rows, sharded ? re - rb : p->count);
+        }
+        if (max_rows <= kGravSmallRows) variant = kGravVariantSmall;
+        else if (max_rows <= kGravMediumRows) variant = kGravVariantMedium;
+    }
+    const bool scaled = gravity_variant(variant).scaled;
+    const float pscale = scaled ? kGravPosScale : 1.f;
+
     // 2. refresh the posm mirror if any source column changed since it was packed
-    const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad;
+    const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad || c->posm_scaled != scaled;
     if (dirty) {
         Timed t(c, T_PACK);
         if (!sharded) {
             uint64_t off = 0;
             for (auto& pm : q) {
                 RECS_CUDA(c, launch_pack_posm((const float*)pm.first->dev, (const float*)pm.second->dev,
-                                              c->cfg.nbody_g, c->posm, 0, pm.first->count, off, c->stream));
+                                              c->cfg.nbody_g, c->posm, 0, pm.first->count, off, pscale, c->stream));
                 off += pm.first->count;
                 c->kernel_launches += pm.first->count ? 1 : 0;
             }
@@ -286,13 +303,14 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         } else {
             // own rows only; the other slices arrive through the all-gather below
             RECS_CUDA(c, launch_pack_posm((const float*)q[0].first->dev, (const float*)q[0].second->dev,
-                                          c->cfg.nbody_g, c->posm, rb, re - rb, rb, c->stream));
+                                          c->cfg.nbody_g, c->posm, rb, re - rb, rb, pscale, c->stream));
             const uint64_t own_end = slice * ((uint64_t)c->cfg.rank + 1);
             RECS_CUDA(c, launch_pad_posm(c->posm, re, own_end, c->stream));
             c->kernel_launches += (re > rb ? 1 : 0) + (own_end > re ? 1 : 0);
         }
         c->posm_sources = sources;
         c->posm_bodies = n_jpad;
+        c->posm_scaled = scaled;
     }
     if (sharded && !c->comm) return fail(c, RECS_ERR_NCCL, "world_size > 1 but recs_gpu_comm_init was not called");
     // The all-gather is enqueued further down, AFTER launch A: an NCCL kernel that is resident
@@ -320,18 +338,6 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     };
 
     // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
-    // kernel shape: up to 24 576 outer rows the small-i-block / exact-mask shape wins (more stream-K
-    // units, and the detector's redo of self tiles is a large share of a small problem); measured in
-    // profiles/r01_gravity_small_n_sweep.txt
-    int variant = c->grav_variant;
-    if (!c->grav_variant_forced) {
-        uint64_t max_rows = 0;
-        for (uint32_t a : sys.archs) {
-            Column* p = find_column(c, a, POS);
-            if (p) max_rows = std::max<uint64_t>(max_rows, sharded ? re - rb : p->count);
-        }
-        if (max_rows <= 24576) variant = kGravVariantSmall;
-    }
     const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm[variant]);
     const uint32_t kGravRows = (uint32_t)gravity_variant(variant).rows();
     for (uint32_t a : sys.archs) {
@@ -407,6 +413,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             ra.tail.vel = (float*)tail_vel->dev;
             ra.tail.dt = c->cfg.nbody_dt;
             ra.tail.g = c->cfg.nbody_g;
+            ra.tail.pscale = pscale;
             // refresh the mirror in place when this archetype is part of the nested query
             uint64_t off = 0;
             for (size_t qi = 0; qi < sys.qarchs.size(); ++qi) {

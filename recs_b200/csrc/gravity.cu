@@ -107,7 +107,79 @@ __device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const fl
     }
 }
 
-template <int RI, int MIN_CTAS, int UNROLL, bool DETECT, int CW = 8>
+// The same interaction with the roles of the f32x2 lanes swapped ("i-packed"): the lanes are two bodies i
+// of this thread, body j is a scalar that every packed instruction takes in the broadcast-operand form.
+// One LDS.128 pair (two bodies j) then feeds 2 x RI/2 pair-interactions, i.e. per pair-interaction half
+// the shared-memory reads of the j-packed form at the same number of accumulator registers.
+// nx/ny/nz hold the NEGATED positions of the two rows.
+template <bool MASKED, int ABL = 0>
+__device__ __forceinline__ void ipair_interaction(const float xj, const float yj, const float zj, const float gm,
+                                                  const f32x2 nx, const f32x2 ny, const f32x2 nz, const float eps,
+                                                  f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {
+    const f32x2 dx = ptx::add2(nx, ptx::pack(xj, xj));
+    const f32x2 dy = ptx::add2(ny, ptx::pack(yj, yj));
+    const f32x2 dz = ptx::add2(nz, ptx::pack(zj, zj));
+    f32x2 d2 = ptx::mul2(dx, dx);
+    d2 = ptx::fma2(dy, dy, d2);
+    d2 = ptx::fma2(dz, dz, d2);
+    float d2a, d2b;
+    ptx::unpack(d2, d2a, d2b);
+    float ra, rb;
+    if (ABL & 4) {  // timing ablation: no MUFU
+        ra = d2a;
+        rb = d2b;
+    } else {
+        ra = ptx::rsqrt_approx(d2a);
+        rb = ptx::rsqrt_approx(d2b);
+    }
+    if (MASKED) {
+        ra = d2a > eps ? ra : 0.f;
+        rb = d2b > eps ? rb : 0.f;
+    } else if (!(ABL & 17)) {
+        dmin_a = fminf(dmin_a, d2a);
+        dmin_b = fminf(dmin_b, d2b);
+    }
+    const f32x2 rinv = ptx::pack(ra, rb);
+    const f32x2 rinv2 = ptx::mul2(rinv, rinv);
+    f32x2 s;
+    if (ABL & 24) {
+        // r^-3 first, mass last: on range-shifted data r^-3 overflows for every pair the reference masks, whatever
+        // its mass.  (Unshifted, r^-3 is denormal beyond 2e12 m: the exact path keeps the (G*m*r^-1)*r^-2 order.)
+        s = ptx::mul2(rinv2, rinv);
+        s = ptx::mul2(s, ptx::pack(gm, gm));
+    } else {
+        s = ptx::mul2(rinv, ptx::pack(gm, gm));
+        s = ptx::mul2(s, rinv2);
+    }
+    ax = ptx::fma2(s, dx, ax);
+    ay = ptx::fma2(s, dy, ay);
+    az = ptx::fma2(s, dz, az);
+}
+
+template <int RP, int UNROLL, bool MASKED, int ABL = 0, bool UNSCALE = false>
+__device__ __forceinline__ void itile_loop(const float4* __restrict__ t, const f32x2 (&nx)[RP], const f32x2 (&ny)[RP],
+                                           const f32x2 (&nz)[RP], const float eps, f32x2 (&ax)[RP], f32x2 (&ay)[RP],
+                                           f32x2 (&az)[RP], float& dmin_a, float& dmin_b) {
+#pragma unroll UNROLL
+    for (int p = 0; p < kGravTile / 2; ++p) {
+        float4 lo = t[2 * p];      // x0 x1 y0 y1
+        float4 hi = t[2 * p + 1];  // z0 z1 gm0 gm1
+        if (UNSCALE) {  // tile stored range-shifted (see kGravPosScale): exact powers of two, undone exactly
+            lo.x *= kGravPosUnscale, lo.y *= kGravPosUnscale, lo.z *= kGravPosUnscale, lo.w *= kGravPosUnscale;
+            hi.x *= kGravPosUnscale, hi.y *= kGravPosUnscale;
+        }
+#pragma unroll
+        for (int q = 0; q < RP; ++q)
+            ipair_interaction<MASKED, ABL>(lo.x, lo.z, hi.x, hi.z, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin_a,
+                                      dmin_b);
+#pragma unroll
+        for (int q = 0; q < RP; ++q)
+            ipair_interaction<MASKED, ABL>(lo.y, lo.w, hi.y, hi.w, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin_a,
+                                      dmin_b);
+    }
+}
+
+template <int RI, int MIN_CTAS, int UNROLL, bool DETECT, int CW = 8, bool IPACK = false, int ABL = 0>
 __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(const GravityArgs a) {
     constexpr int kGravRowsPerThread = RI;
     constexpr int kGravConsumerWarps = CW;
@@ -165,10 +237,15 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
 
     float nxi[kGravRowsPerThread], nyi[kGravRowsPerThread], nzi[kGravRowsPerThread];
 
+    // row of the i-block that register slot r of this thread holds.  i-packed shapes give a warp RI*32 consecutive
+    // rows, so the warp's own bodies sit in ONE j tile (one exact-path redo per i-block instead of RI).
+    auto row_in_block = [&](int r) -> uint32_t {
+        return IPACK ? (warp * (32u * RI) + r * 32u + lane) : (r * kGravConsumerThreads + tid);
+    };
     auto load_rows = [&](uint32_t iblock) {
 #pragma unroll
         for (int r = 0; r < kGravRowsPerThread; ++r) {
-            const uint32_t local = iblock * kGravRows + r * kGravConsumerThreads + tid;
+            const uint32_t local = iblock * kGravRows + row_in_block(r);
             float x = 0.f, y = 0.f, z = 0.f;
             if (local < a.row_count) {
                 const float* p = a.ipos + 3ull * (a.row_begin + local);
@@ -176,6 +253,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                 y = __ldg(p + 1);
                 z = __ldg(p + 2);
             }
+            if ((ABL & 16) != 0) x *= kGravPosScale, y *= kGravPosScale, z *= kGravPosScale;
             nxi[r] = x;  // kept positive; negated at the use (see pair_interaction)
             nyi[r] = y;
             nzi[r] = z;
@@ -187,7 +265,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
         float4* dst = a.frags + static_cast<size_t>(a.launch.frag_base + blockIdx.x + iblock) * kGravRows;
 #pragma unroll
         for (int r = 0; r < kGravRowsPerThread; ++r)
-            dst[r * kGravConsumerThreads + tid] = run[r * kGravConsumerThreads + tid];
+            dst[row_in_block(r)] = run[r * kGravConsumerThreads + tid];
     };
 
     load_rows(b);
@@ -199,10 +277,82 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
         ptx::mbar_wait(&full_bar[stage], phase);
         const float4* t = tiles + stage * kGravTile;
 
+        float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
+        if constexpr (IPACK) {
+            // lanes = rows (2q, 2q+1) of this thread
+            constexpr int RP = RI / 2;
+            f32x2 nx[RP], ny[RP], nz[RP], ax[RP], ay[RP], az[RP];
+#pragma unroll
+            for (int q = 0; q < RP; ++q) {
+                nx[q] = ptx::pack(-nxi[2 * q], -nxi[2 * q + 1]);
+                ny[q] = ptx::pack(-nyi[2 * q], -nyi[2 * q + 1]);
+                nz[q] = ptx::pack(-nzi[2 * q], -nzi[2 * q + 1]);
+                ax[q] = ay[q] = az[q] = 0ull;
+            }
+            if constexpr ((ABL & 16) != 0) {
+                // Range-shifted fast path: tile and row positions are stored times 2^-32 (an exact scaling; G*m is
+                // stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
+                // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the tile sums, which come out times 2^64.
+                // No per-pair detector instruction at all: one finiteness test per tile, then the exact masked
+                // path on true-scale values.  A tile in which G*m/d^3 of some pair reaches 2^32 s^-2 (a density
+                // above 1e19 kg/m^3) or whose sums reach 2^64 m/s^2 takes the exact path as well.
+                itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                float chk = 0.f;
+#pragma unroll
+                for (int q = 0; q < RP; ++q) {
+                    const f32x2 sc = ptx::pack(kGravOutScale, kGravOutScale);
+                    ax[q] = ptx::mul2(ax[q], sc);
+                    ay[q] = ptx::mul2(ay[q], sc);
+                    az[q] = ptx::mul2(az[q], sc);
+                    float u0, u1, v0, v1, w0, w1;
+                    ptx::unpack(ax[q], u0, u1);
+                    ptx::unpack(ay[q], v0, v1);
+                    ptx::unpack(az[q], w0, w1);
+                    chk += fabsf(u0) + fabsf(u1) + fabsf(v0) + fabsf(v1) + fabsf(w0) + fabsf(w1);
+                }
+                if (!(chk < 3.0e38f)) {  // inf or NaN somewhere
+                    f32x2 ux[RP], uy[RP], uz[RP];
+                    const f32x2 un = ptx::pack(kGravPosUnscale, kGravPosUnscale);
+#pragma unroll
+                    for (int q = 0; q < RP; ++q) {
+                        ux[q] = ptx::mul2(nx[q], un);
+                        uy[q] = ptx::mul2(ny[q], un);
+                        uz[q] = ptx::mul2(nz[q], un);
+                        ax[q] = ay[q] = az[q] = 0ull;
+                    }
+                    itile_loop<RP, 1, true, 0, true>(t, ux, uy, uz, eps, ax, ay, az, dmin_a, dmin_b);
+                }
+            } else if (DETECT) {
+                itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                if (fminf(dmin_a, dmin_b) <= eps) {
+#pragma unroll
+                    for (int q = 0; q < RP; ++q) ax[q] = ay[q] = az[q] = 0ull;
+                    itile_loop<RP, 1, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                }
+            } else {
+                itile_loop<RP, UNROLL, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+            }
+#pragma unroll
+            for (int q = 0; q < RP; ++q) {
+                float x0, x1, y0, y1, z0, z1;
+                ptx::unpack(ax[q], x0, x1);
+                ptx::unpack(ay[q], y0, y1);
+                ptx::unpack(az[q], z0, z1);
+                float4 acc0 = run[(2 * q) * kGravConsumerThreads + tid];
+                float4 acc1 = run[(2 * q + 1) * kGravConsumerThreads + tid];
+                acc0.x += x0;
+                acc0.y += y0;
+                acc0.z += z0;
+                acc1.x += x1;
+                acc1.y += y1;
+                acc1.z += z1;
+                run[(2 * q) * kGravConsumerThreads + tid] = acc0;
+                run[(2 * q + 1) * kGravConsumerThreads + tid] = acc1;
+            }
+        } else {
         f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
 #pragma unroll
         for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
-        float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
         if (DETECT) {
             tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
             if (fminf(dmin_a, dmin_b) <= eps) {
@@ -227,6 +377,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             acc.y += y0 + y1;
             acc.z += z0 + z1;
             run[r * kGravConsumerThreads + tid] = acc;
+        }
         }
 
         __syncwarp();
@@ -289,9 +440,9 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
         if (a.tail.posm) {
             const uint64_t J = a.tail.posm_offset + row;
             float* d = a.tail.posm + (J >> 1) * 8 + (J & 1);
-            d[0] = px;
-            d[2] = py;
-            d[4] = pz;
+            d[0] = px * a.tail.pscale;
+            d[2] = py * a.tail.pscale;
+            d[4] = pz * a.tail.pscale;
             d[6] = __fmul_rn(a.tail.g, a.tail.mass[row]);
         }
     }
@@ -300,15 +451,15 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
 __global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict__ pos,
                                                         const float* __restrict__ mass, float g,
                                                         float* __restrict__ posm, uint64_t row_begin,
-                                                        uint64_t n, uint64_t dst_offset) {
+                                                        uint64_t n, uint64_t dst_offset, float pscale) {
     const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (k >= n) return;
     const uint64_t row = row_begin + k;
     const uint64_t J = dst_offset + k;
     float* d = posm + (J >> 1) * 8 + (J & 1);
-    d[0] = pos[3 * row + 0];
-    d[2] = pos[3 * row + 1];
-    d[4] = pos[3 * row + 2];
+    d[0] = pos[3 * row + 0] * pscale;
+    d[2] = pos[3 * row + 1] * pscale;
+    d[4] = pos[3 * row + 2] * pscale;
     d[6] = __fmul_rn(g, mass[row]);
 }
 
@@ -327,37 +478,43 @@ __global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm,
 
 namespace {
 typedef void (*GravityKernel)(const GravityArgs);
-// Compiled shapes (profiles/r01_gravity_variant_sweep*.txt has the full sweep they were picked from).
-//                                                 rows/thread, CTAs/SM, consumer warps
+// Compiled shapes.  profiles/r01_gravity_variant_sweep*.txt hold the sweeps they were picked from (sweep5 maps the
+// numbering used while sweeping to this table).
+//                    rows/thread, CTAs/SM, consumer warps, range-shifted posm
 const GravityVariant kVariants[kGravVariantCount] = {
-    {2, 1, 12},  // 0  default: detector fast path, unroll 8, <= 120 registers
-    {2, 1, 12},  // 1  same shape, exact mask on every pair (A/B of the detector)
-    {2, 3, 4},   // 2  small problems: 256-row i-blocks, 3 CTAs/SM (more work units for the stream-K split), exact
-                 //    mask everywhere (the detector's redo of self tiles is a large share of a small problem)
-    {2, 3, 4},   // 3  small i-blocks with the detector
-    {4, 1, 8},   // 4  4 rows/thread, 8 warps, up to 224 registers
-    {2, 1, 16},  // 5
-    {4, 1, 16},  // 6  4 rows/thread: half the LDS cost, worse ptxas schedule
-    {4, 2, 8},   // 7  the first version's shape with the exact mask
+    {4, 1, 12, true},   // 0  default: i-packed, overflow detector on range-shifted data, unroll 8
+    {2, 1, 12, false},  // 1  j-packed, FMNMX detector (the default before the i-packed rewrite; A/B)
+    {2, 3, 4, false},   // 2  small problems: j-packed, 256-row i-blocks, exact mask on every pair
+    {2, 4, 4, true},    // 3  medium problems: i-packed overflow detector, 256-row i-blocks, 4 CTAs/SM
+    {4, 1, 12, false},  // 4  i-packed, FMNMX detector, same operation order as 0: must equal 0 bit for bit
+    {4, 1, 12, false},  // 5  i-packed, exact mask on every pair
+    {4, 1, 8, true},    // 6  as 0 with 8 consumer warps
+    {8, 1, 8, true},    // 7  as 0 with 4 row pairs per thread (half the LDS, worse ptxas schedule)
+    {4, 1, 12, true},   // 8  TIMING ONLY: 0 without MUFU.RSQ (wrong results)
+    {4, 1, 12, false},  // 9  TIMING ONLY: 4 without the detector (wrong results for coincident bodies)
 };
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
-            return nbody_gravity_kernel<2, 1, 8, true, 12>;
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, 16>;
         case 1:
-            return nbody_gravity_kernel<2, 1, 8, false, 12>;
+            return nbody_gravity_kernel<2, 1, 8, true, 12>;
         case 2:
             return nbody_gravity_kernel<2, 3, 8, false, 4>;
         case 3:
-            return nbody_gravity_kernel<2, 3, 8, true, 4>;
+            return nbody_gravity_kernel<2, 4, 8, true, 4, true, 16>;
         case 4:
-            return nbody_gravity_kernel<4, 1, 8, true, 8>;
+            return nbody_gravity_kernel<4, 1, 4, true, 12, true, 8>;
         case 5:
-            return nbody_gravity_kernel<2, 1, 8, true, 16>;
+            return nbody_gravity_kernel<4, 1, 4, false, 12, true>;
         case 6:
-            return nbody_gravity_kernel<4, 1, 8, true, 16>;
+            return nbody_gravity_kernel<4, 1, 2, true, 8, true, 16>;
         case 7:
-            return nbody_gravity_kernel<4, 2, 2, false, 8>;
+            return nbody_gravity_kernel<8, 1, 2, true, 8, true, 16>;
+        case 8:
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, 16 + 4>;
+        case 9:
+            return nbody_gravity_kernel<4, 1, 4, true, 12, true, 8 + 1>;
     }
     return nullptr;
 }
@@ -398,11 +555,11 @@ cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s) {
 }
 
 cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
-                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, cudaStream_t s) {
+                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, float pscale, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const uint64_t grid = (n + 255) / 256;
     pack_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(pos, mass, g, posm, row_begin, n,
-                                                                dst_offset);
+                                                                dst_offset, pscale);
     return cudaGetLastError();
 }
 

@@ -8,7 +8,7 @@ namespace recs {
 
 // ---- gravity (crates/n-body/src/lib.rs:104-135) ------------------------------------------------
 constexpr int kGravMaxConsumerWarps = 31;                      // consumer warps per CTA are variant dependent (8 or 16)
-constexpr int kGravMaxRowsPerThread = 4;                       // register blocking over i (variant dependent)
+constexpr int kGravMaxRowsPerThread = 8;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
 constexpr int kGravTileBytes = kGravTile * 16;                 // 4 KiB
@@ -21,14 +21,24 @@ struct GravityVariant {
     int rows_per_thread;  // bodies i per consumer thread
     int min_ctas;         // __launch_bounds__ residency target
     int consumer_warps;   // 8 or 16 (+ 1 TMA producer warp)
+    bool scaled = false;  // posm is stored range-shifted (kGravPosScale), see gravity.cu
     int consumer_threads() const { return 32 * consumer_warps; }
     int threads() const { return consumer_threads() + 32; }
     int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
-constexpr int kGravVariantCount = 8;
+constexpr int kGravVariantCount = 10;
 constexpr int kGravVariantDefault = 0;
-constexpr int kGravVariantSmall = 2;
+constexpr int kGravVariantSmall = 2;    // up to kGravSmallRows outer rows
+constexpr int kGravVariantMedium = 3;   // up to kGravMediumRows outer rows
+constexpr uint64_t kGravSmallRows = 16384;
+constexpr uint64_t kGravMediumRows = 49152;
 GravityVariant gravity_variant(int index);
+
+// Range shift of the overflow-detector variants: positions x 2^-32 (exact power-of-two scaling, G*m unscaled);
+// tile sums come out x 2^64 and are scaled back before they join the running sums.
+constexpr float kGravPosScale = 2.3283064365386963e-10f;   // 2^-32
+constexpr float kGravPosUnscale = 4294967296.f;            // 2^32
+constexpr float kGravOutScale = 5.4210108624275222e-20f;   // 2^-64 = pos_scale^2
 
 struct GravityLaunch {
     uint32_t grid;        // persistent CTAs (stream-K workers)
@@ -60,6 +70,7 @@ struct GravityTail {
     uint32_t posm_offset; // posm body index of row 0 of this column
     float dt;
     float g;
+    float pscale;         // range shift of the posm mirror (1 for the unscaled variants)
 };
 
 struct GravityReduceArgs {
@@ -83,7 +94,7 @@ cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
 // Position(12 B) + Mass(4 B) rows [0, n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
 // gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`.
 cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
-                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, cudaStream_t s);
+                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, float pscale, cudaStream_t s);
 // Null bodies (gm = 0) for [begin, end) so partially filled tiles contribute nothing.
 cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s);
 

@@ -240,12 +240,129 @@ def test_other_tick_orders_follow_the_oracle(gpu_ctx, nbody_oracle, order):
     assert rel_err_rows(app.acc, acc).max() <= 1e-4
 
 
-@pytest.mark.parametrize("n", [24576, 24577])
+@pytest.mark.parametrize("n", [16384, 16385, 49152, 49153])
 def test_kernel_shape_switch_sizes(gpu_ctx, nbody_oracle, n):
-    """Sizes on both sides of the small-problem / default kernel-shape switch."""
+    """Sizes on both sides of the small / medium / default kernel-shape switches."""
     app, (pos, mass, vel, acc) = _app(gpu_ctx, n, seed=3)
     app.run("gravity")
     app.download()
     rows = np.random.default_rng(1).choice(n, size=64, replace=False)
     ref32, _ = nbody_oracle.gravity_sample(pos, mass, rows, f64=False)
     assert rel_err_rows(app.acc[rows], ref32).max() <= ACC_TOL
+
+
+# ---- kernel shapes (recs_b200/csrc/gravity.cu, kVariants) --------------------------------------------------------
+RESULT_VARIANTS = [0, 1, 2, 3, 4, 5, 6, 7]  # 8 and 9 are timing-only ablations with wrong results by design
+
+
+def _forced_variant_ctx(monkeypatch, variant):
+    from recs_b200 import GpuContext
+
+    monkeypatch.setenv("RECS_GPU_GRAVITY_VARIANT", str(variant))
+    return GpuContext(device=0, use_cuda_graph=False)
+
+
+def _bodies_with_close_pairs(n, seed):
+    pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), seed)
+    if n >= 64:
+        k = n // 8
+        pos[k : 2 * k] = pos[:k]  # coincident twins
+        pos[2 * k : 3 * k] = pos[:k] + np.array([1e-4, 0, 0], np.float32)  # sub-epsilon neighbours
+        pos[3 * k : 4 * k] = pos[:k] + np.array([0, 7e-4, 0], np.float32)  # just above epsilon where f32 resolves it
+    return np.ascontiguousarray(pos), mass, vel, acc
+
+
+@pytest.mark.parametrize("variant", RESULT_VARIANTS)
+@pytest.mark.parametrize("n", [5, 257, 1537, 4097])
+def test_every_kernel_shape_matches_oracle(monkeypatch, nbody_oracle, variant, n):
+    """Each compiled shape, forced for every size (i-block / tile edges included), with coincident,
+    sub-epsilon and just-above-epsilon pairs spread over other tiles."""
+    from recs_b200.nbody import NBodyGpuApp
+
+    pos, mass, vel, acc = _bodies_with_close_pairs(n, seed=11)
+    with _forced_variant_ctx(monkeypatch, variant) as ctx:
+        app = NBodyGpuApp(ctx, pos.copy(), mass, vel, acc)
+        app.upload()
+        app.run("gravity")
+        app.download()
+    ref = nbody_oracle.gravity(pos, mass)
+    assert np.all(np.isfinite(app.acc))
+    assert rel_err_rows(app.acc, ref).max() <= ACC_TOL
+
+
+def test_range_shift_is_bit_exact(monkeypatch):
+    """Variant 0 works on positions scaled by 2^-32 and detects d2 <= epsilon through the overflow of r^-3;
+    variant 4 is the same operation order on unscaled data with an explicit min-d2 detector.  Power-of-two
+    scalings commute with every rounding involved, so wherever both take the exact path for the same tiles
+    (coincident and sub-epsilon pairs; light bodies, so that G*m/d^3 stays below 2^32) they must agree bit for
+    bit -- several ticks of the fused tail, which refreshes the shifted mirror, included."""
+    from recs_b200.nbody import NBodyGpuApp
+
+    outs = []
+    for variant in (0, 4):
+        scene = scenes.replace(scenes.EVERYTHING_LIGHT, body_count=20000)
+        pos, mass, vel, acc = scenes.spawn_bodies(scene, 12)
+        k = 2500
+        pos[k : 2 * k] = pos[:k]  # coincident twins
+        pos[2 * k : 3 * k] = pos[:k] + np.array([1e-4, 0, 0], np.float32)  # sub-epsilon neighbours
+        with _forced_variant_ctx(monkeypatch, variant) as ctx:
+            app = NBodyGpuApp(ctx, np.ascontiguousarray(pos), mass, vel, acc)
+            app.upload()
+            app.run("gravity")
+            app.download()
+            first = app.acc.copy()
+            app.tick(3)
+            app.download()
+            outs.append((first, app.pos.copy(), app.vel.copy(), app.acc.copy()))
+    assert np.all(np.isfinite(outs[0][0])) and np.any(outs[0][0] != 0)
+    for a, b in zip(*outs):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+@pytest.mark.parametrize(
+    "name,pos_scale,mass_lo,mass_hi",
+    [
+        ("light", 1.0, 100.0, 1000.0),  # EVERYTHING_LIGHT (crates/n-body/src/scenes.rs:23-27)
+        ("dust", 1.0, 1e-30, 1e-28),  # G*m around 1e-40: denormal in the reference as well
+        ("grains", 1e-3, 1e-12, 1e-9),
+        ("stars", 1e12, 1e29, 1e31),
+        ("galactic", 1e16, 1e36, 1e37),  # d2 up to ~1e37, close to the f32 limit
+        ("superdense", 1e-2, 1e20, 1e21),  # G*m/d^3 >= 2^32: every tile takes the exact path
+        ("mixed", 1.0, 1e-6, 1e24),
+    ],
+)
+@pytest.mark.parametrize("variant", [0, 3])
+def test_range_extremes(monkeypatch, nbody_oracle, variant, name, pos_scale, mass_lo, mass_hi):
+    """The shifted kernels over the dynamic range of f32 inputs: no input may silently lose accuracy --
+    whatever does not fit the shifted range must reach the exact path.  (Not covered: separations beyond
+    1.8e19 m, where the reference's d2 overflows to +inf and it drops the pair; the shifted path keeps the pair's
+    true, tiny contribution -- DESIGN.md 3.1.)"""
+    from recs_b200.nbody import NBodyGpuApp
+
+    n = 3000
+    rng = np.random.default_rng(21)
+    pos = (rng.uniform(-100.0, 100.0, size=(n, 3)) * pos_scale).astype(np.float32)
+    if name == "mixed":
+        mass = np.exp(rng.uniform(np.log(mass_lo), np.log(mass_hi), size=n)).astype(np.float32)
+        mass[::17] = 0.0  # massless bodies are legal rows
+    else:
+        mass = rng.uniform(mass_lo, mass_hi, size=n).astype(np.float32)
+    vel = np.zeros((n, 3), np.float32)
+    acc = np.zeros((n, 3), np.float32)
+    with _forced_variant_ctx(monkeypatch, variant) as ctx:
+        app = NBodyGpuApp(ctx, pos.copy(), mass, vel, acc)
+        app.upload()
+        app.run("gravity")
+        app.download()
+    ref = nbody_oracle.gravity(pos, mass)
+    ref64 = nbody_oracle.gravity_f64(pos, mass)
+    assert np.all(np.isfinite(app.acc)) or not np.all(np.isfinite(ref))
+    # judged like everywhere else: norm-wise per body against the reference-order f32 oracle, with the f64
+    # sum as arbiter where the reference's own f32 result is further from the truth than 1e-4
+    # ... and an absolute floor where the reference itself works in denormals: there `(G*m/d2)/|d|` is quantised
+    # to 2^-149 before it multiplies to_body, so n * 2^-149 * max|to_body| is the reference's own error bound
+    floor = n * 2.0**-149 * 2.0 * float(np.abs(pos).max()) / ACC_TOL
+    err32 = rel_err_rows(app.acc, ref, floor=floor)
+    err64 = rel_err_rows(app.acc, ref64, floor=floor)
+    ok = (err32 <= ACC_TOL) | (err64 <= ACC_TOL)
+    assert ok.all(), f"{name}: {np.count_nonzero(~ok)} rows off, worst {np.minimum(err32, err64).max():.3e}"
