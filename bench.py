@@ -43,7 +43,7 @@ FMA_LANE_OPS_PER_INTERACTION = 12.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one interaction-kernel launch on one GPU, from ncu
 # (profiles/r01_gravity_traffic_1M.csv, profiles/r01_gravity_default_ncu_summary.txt); the kernel is
 # FP32-bound, the figure only shows there are no wasted re-reads (posm + outer positions = 28 MB at 1 M)
-KERNEL_DRAM_TRAFFIC_BYTES = {1_048_576: 29_822_464 + 18_688, 65_536: 1_848_320}
+KERNEL_DRAM_TRAFFIC_BYTES = {1_048_576: 29_457_664 + 49_920, 65_536: 1_854_208}
 DEFAULT_BODIES = 1_048_576
 SEED = 1
 
