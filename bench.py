@@ -435,7 +435,7 @@ def run_gpu_arm(args) -> None:
                 "bodies": n,
                 "systems": "gravity->movement->acceleration",
                 "parallelism": f"index-sharded x{world}, NCCL all-gather of positions per tick" if world > 1 else "single GPU",
-                "l2": "flushed between timed ticks (256 MiB write outside the event bracket)",
+                "l2": "flushed between timed ticks (256 MiB write + 256 MiB read sweep outside the event bracket)",
                 "seed": SEED,
             },
             "clocks": clocks,
@@ -481,14 +481,31 @@ def streaming_extras(ctx) -> dict:
     ctx.set_archetypes(sid, [ARCH])
     for _ in range(3):
         ctx.run_system(sid, sync=False)
+    # (a) steady state: 20 passes back to back in one event bracket.  One pass touches 240 MB, more than the
+    #     126 MB L2, so every pass is cold and also pays for the write-backs the previous one left in L2.
+    passes = 20
+    ctx.synchronize()
+    ctx.timer_start()
+    for _ in range(passes):
+        ctx.run_system(sid, sync=False)
+    steady_ms = ctx.timer_stop() / passes
+    # (b) single passes after an L2 flush that leaves clean lines
     ms = []
     for _ in range(20):
         ctx.flush_l2()
         ctx.timer_start()
         ctx.run_system(sid, sync=False)
         ms.append(ctx.timer_stop())
-    gbs = 36.0 * n / (np.median(ms) * 1e-3) / 1e9
-    out["simple_iter_10M"] = {"GBps": gbs, "frac_of_measured_hbm": gbs / peak, "ms": float(np.median(ms)), "bytes_per_entity": 36}
+    gbs = 36.0 * n / (steady_ms * 1e-3) / 1e9
+    out["simple_iter_10M"] = {
+        "GBps": gbs,
+        "frac_of_measured_hbm": gbs / peak,
+        "ms": float(steady_ms),
+        "bytes_per_entity": 36,
+        "how": "20 passes back to back in one CUDA-event bracket; inputs (240 MB) larger than L2",
+        "single_pass_after_flush_ms": float(np.median(ms)),
+        "single_pass_after_flush_GBps": 36.0 * n / (np.median(ms) * 1e-3) / 1e9,
+    }
     # rain: 4 Mi drops, fused wind -> gravity -> movement, 48 B / entity / tick
     n = 4 * 1024 * 1024
     VEL, POS, ARCH2 = 201, 202, 8
@@ -512,7 +529,20 @@ def streaming_extras(ctx) -> dict:
         ctx.tick(1)
         ms.append(ctx.timer_stop())
     gbs = 48.0 * n / (np.median(ms) * 1e-3) / 1e9
-    out["rain_4Mi_fused"] = {"GBps": gbs, "frac_of_measured_hbm": gbs / peak, "ms": float(np.median(ms)), "bytes_per_entity": 48}
+    ctx.synchronize()
+    ctx.timer_start()
+    for _ in range(20):
+        ctx.tick(1)
+    resident_ms = ctx.timer_stop() / 20
+    out["rain_4Mi_fused"] = {
+        "GBps": gbs,
+        "frac_of_measured_hbm": gbs / peak,
+        "ms": float(np.median(ms)),
+        "bytes_per_entity": 48,
+        "how": "single ticks, L2 flushed before each (write 256 MiB, then stream 256 MiB of loads so no dirty lines remain)",
+        "back_to_back_ms": float(resident_ms),
+        "back_to_back_note": "the two 50 MB columns fit the 126 MB L2, so consecutive ticks run L2-resident: not an HBM figure",
+    }
     out["hbm_peak_GBps"] = peak
     return out
 

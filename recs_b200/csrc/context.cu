@@ -118,6 +118,7 @@ struct recs_gpu_ctx {
     cudaEvent_t timer_a = nullptr, timer_b = nullptr;
     float* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
+    bool l2_flush_zeroed = false;
 };
 
 namespace {
@@ -1259,10 +1260,19 @@ int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* c, int32_t packed, float* out_t
 
 int32_t recs_gpu_flush_l2(recs_gpu_ctx* c) {
     RECS_ENTER(c);
-    const size_t bytes = 256u << 20;  // > 126 MB L2
-    int32_t st = ensure(c, &c->l2_flush, &c->l2_flush_bytes, bytes);
+    // Write a buffer larger than the 126 MB L2, then stream a second one through it with loads: everything a
+    // previous pass left is evicted, and the lines that remain are CLEAN -- after the write alone the next (timed)
+    // kernel would pay for writing back up to 126 MB of the flush's own dirty lines.
+    const size_t bytes = 256u << 20;
+    int32_t st = ensure(c, &c->l2_flush, &c->l2_flush_bytes, 2 * bytes + 16);
     if (st != RECS_OK) return st;
+    if (!c->l2_flush_zeroed) {
+        RECS_CUDA(c, cudaMemsetAsync(c->l2_flush, 0, 2 * bytes + 16, c->stream));
+        c->l2_flush_zeroed = true;
+    }
+    float* second = c->l2_flush + bytes / 4;
     RECS_CUDA(c, launch_fill(c->l2_flush, bytes / 4, 0.f, c->stream));
+    RECS_CUDA(c, launch_read_sweep(second, bytes / 4, second + bytes / 4, c->stream));
     return RECS_OK;
 }
 

@@ -133,5 +133,6 @@ cudaError_t launch_compact_flags(const uint32_t* flags, uint32_t n_rows, uint32_
 cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
                              unsigned long long* cycles, cudaStream_t s);
 cudaError_t launch_fill(float* p, uint64_t n, float v, cudaStream_t s);
+cudaError_t launch_read_sweep(const float* p, uint64_t n, float* sink, cudaStream_t s);
 
 }  // namespace recs

@@ -402,7 +402,24 @@ __global__ void fill_kernel(float* p, uint64_t n, float v) {
     for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
         p[i] = v;
 }
+// Streams n floats through L2 without leaving dirty lines behind (the sum is stored only if it is NaN,
+// which a zero-filled buffer never produces).
+__global__ void read_sweep_kernel(const float4* __restrict__ p, uint64_t n4, float* sink) {
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    float acc = 0.f;
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+        const float4 v = __ldcg(p + i);
+        acc += (v.x + v.y) + (v.z + v.w);
+    }
+    if (acc != acc) *sink = acc;
+}
 }  // namespace
+
+cudaError_t launch_read_sweep(const float* p, uint64_t n, float* sink, cudaStream_t s) {
+    if (n < 4) return cudaSuccess;
+    read_sweep_kernel<<<stream_grid(n / 4, 256 * 4), 256, 0, s>>>(reinterpret_cast<const float4*>(p), n / 4, sink);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
                              unsigned long long* cycles, cudaStream_t s) {
