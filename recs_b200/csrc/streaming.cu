@@ -7,6 +7,8 @@
 // Arithmetic is kept bit-identical to the Rust code: rustc never contracts `a + b * c` into an
 // FMA, so every mul/add below is an explicit round-to-nearest intrinsic.
 #include "kernels.cuh"
+#include "ptx.cuh"
+#include <stdlib.h>
 
 namespace recs {
 namespace {
@@ -258,6 +260,118 @@ __global__ void __launch_bounds__(kStreamThreads)
 }
 
 
+// TMA-pipelined form of the same systems (the default for whole 1024-entity chunks): a persistent CTA per SM slot,
+// a 3-stage ring of {velocity chunk, position chunk} in shared memory, one producer thread issuing 1-D bulk loads
+// (cp.async.bulk -> UBLKCP) against full barriers, eight consumer warps updating the chunk in place in shared
+// memory, and one store thread writing it back with bulk stores (shared -> global) before it recycles the stage.
+// Loads of chunks k+1 and k+2 and the store of chunk k-1 are in flight while chunk k is computed, with no
+// __syncthreads and no register staging; 72 KiB of shared memory per CTA, two CTAs per SM.
+constexpr int kRainStages = 3;
+constexpr int kRainCtasPerSm = 3;  // 1: 32.8 us, 2: 31.7 us, 3: 30.7 us per fused tick of 4 Mi drops
+constexpr int kRainChunkBytes = kRainChunkVec * 16;  // 12 KiB per column per chunk
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads + 64)
+    rain_tma_kernel(float4* __restrict__ vel, float4* __restrict__ pos, uint64_t n_chunks, float wx, float wy, float wz,
+                    float k_gravity, float terminal, float dt) {
+    constexpr int kCols = MODE == 2 ? 2 : 1;
+    extern __shared__ __align__(128) unsigned char rain_smem[];
+    float4* ring = reinterpret_cast<float4*>(rain_smem);  // [stage][column][kRainChunkVec]
+    __shared__ __align__(8) uint64_t full_bar[kRainStages];
+    __shared__ __align__(8) uint64_t done_bar[kRainStages];
+    __shared__ __align__(8) uint64_t empty_bar[kRainStages];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < kRainStages; ++s) {
+            ptx::mbar_init(&full_bar[s], 1);
+            ptx::mbar_init(&done_bar[s], kStreamThreads / 32);
+            ptx::mbar_init(&empty_bar[s], 1);
+        }
+        ptx::mbar_fence_init();
+    }
+    __syncthreads();
+    const uint64_t first = blockIdx.x;
+    const uint64_t my_chunks = first < n_chunks ? (n_chunks - first + gridDim.x - 1) / gridDim.x : 0;
+
+    if (warp == kStreamThreads / 32) {  // ---- load producer
+        if (lane == 0) {
+            for (uint64_t k = 0; k < my_chunks; ++k) {
+                const uint32_t stage = k % kRainStages, phase = (k / kRainStages) & 1u;
+                const uint64_t chunk = first + k * gridDim.x;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                float4* dst = ring + stage * kCols * kRainChunkVec;
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], kCols * kRainChunkBytes);
+                ptx::bulk_g2s(dst, vel + chunk * kRainChunkVec, kRainChunkBytes, &full_bar[stage]);
+                if (MODE == 2) ptx::bulk_g2s(dst + kRainChunkVec, pos + chunk * kRainChunkVec, kRainChunkBytes, &full_bar[stage]);
+            }
+        }
+        return;
+    }
+    if (warp == kStreamThreads / 32 + 1) {  // ---- store thread
+        if (lane == 0) {
+            for (uint64_t k = 0; k < my_chunks; ++k) {
+                const uint32_t stage = k % kRainStages, phase = (k / kRainStages) & 1u;
+                const uint64_t chunk = first + k * gridDim.x;
+                ptx::mbar_wait(&done_bar[stage], phase);
+                const float4* src = ring + stage * kCols * kRainChunkVec;
+                ptx::bulk_s2g(vel + chunk * kRainChunkVec, src, kRainChunkBytes);
+                if (MODE == 2) ptx::bulk_s2g(pos + chunk * kRainChunkVec, src + kRainChunkVec, kRainChunkBytes);
+                ptx::bulk_commit();
+                ptx::bulk_wait_read0();
+                ptx::mbar_arrive(&empty_bar[stage]);
+            }
+            ptx::bulk_wait0();
+        }
+        return;
+    }
+    // ---- consumers: thread t owns entities 4t..4t+3 of the chunk = float4 3t..3t+2 of each column
+    const int t = threadIdx.x;
+    for (uint64_t k = 0; k < my_chunks; ++k) {
+        const uint32_t stage = k % kRainStages, phase = (k / kRainStages) & 1u;
+        ptx::mbar_wait(&full_bar[stage], phase);
+        float4* sv = ring + stage * kCols * kRainChunkVec;
+        float4* sp = sv + kRainChunkVec;
+        Vec3x4 v, p;
+        v.a = sv[3 * t];
+        v.b = sv[3 * t + 1];
+        v.c = sv[3 * t + 2];
+        if (MODE == 2) {
+            p.a = sp[3 * t];
+            p.b = sp[3 * t + 1];
+            p.c = sp[3 * t + 2];
+        }
+        float o[12], q[12];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x, y, z;
+            get3(v, e, x, y, z);
+            if (MODE == 1 || MODE == 2) rain_wind_1(x, y, z, wx, wy, wz, terminal);
+            if (MODE == 0 || MODE == 2) rain_gravity_1(x, y, z, k_gravity, terminal);
+            o[3 * e] = x;
+            o[3 * e + 1] = y;
+            o[3 * e + 2] = z;
+            if (MODE == 2) {
+                float px, py, pz;
+                get3(p, e, px, py, pz);
+                q[3 * e] = __fadd_rn(px, __fmul_rn(x, dt));
+                q[3 * e + 1] = __fadd_rn(py, __fmul_rn(y, dt));
+                q[3 * e + 2] = __fadd_rn(pz, __fmul_rn(z, dt));
+            }
+        }
+        sv[3 * t] = make_float4(o[0], o[1], o[2], o[3]);
+        sv[3 * t + 1] = make_float4(o[4], o[5], o[6], o[7]);
+        sv[3 * t + 2] = make_float4(o[8], o[9], o[10], o[11]);
+        if (MODE == 2) {
+            sp[3 * t] = make_float4(q[0], q[1], q[2], q[3]);
+            sp[3 * t + 1] = make_float4(q[4], q[5], q[6], q[7]);
+            sp[3 * t + 2] = make_float4(q[8], q[9], q[10], q[11]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&done_bar[stage]);
+    }
+}
+
 // Grid for a grid-stride streaming kernel: at most `cap` resident-ish CTAs, and every CTA gets the
 // same number of chunks (a ragged last pass would leave most SMs idle for a whole chunk time).
 inline uint32_t stream_grid(uint64_t work_items, uint32_t per_block) {
@@ -317,11 +431,28 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
-        const uint64_t passes = (n_chunks + cap - 1) / cap;   // same number of chunks for every CTA
-        const uint32_t grid = static_cast<uint32_t>((n_chunks + passes - 1) / passes);
-        rain_staged_kernel<MODE><<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(vel), reinterpret_cast<float4*>(pos),
-                                                                 n_chunks, wx, wy, wz, k_gravity, terminal, dt);
+        static const bool staged = getenv("RECS_GPU_RAIN_STAGED") != nullptr;  // A/B knob: the pre-TMA kernel
+        if (staged) {
+            const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
+            const uint64_t passes = (n_chunks + cap - 1) / cap;   // same number of chunks for every CTA
+            const uint32_t grid = static_cast<uint32_t>((n_chunks + passes - 1) / passes);
+            rain_staged_kernel<MODE><<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(vel),
+                                                                     reinterpret_cast<float4*>(pos), n_chunks, wx, wy, wz,
+                                                                     k_gravity, terminal, dt);
+        } else {
+            constexpr int smem = kRainStages * (MODE == 2 ? 2 : 1) * kRainChunkBytes;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(rain_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+                attr_set = true;
+            }
+            static const int ctas_per_sm = getenv("RECS_GPU_RAIN_CTAS") ? atoi(getenv("RECS_GPU_RAIN_CTAS")) : kRainCtasPerSm;
+            const uint64_t cap = static_cast<uint64_t>(sms) * ctas_per_sm;
+            const uint32_t grid = static_cast<uint32_t>(n_chunks < cap ? n_chunks : cap);
+            rain_tma_kernel<MODE><<<grid, kStreamThreads + 64, smem, s>>>(reinterpret_cast<float4*>(vel),
+                                                                          reinterpret_cast<float4*>(pos), n_chunks, wx, wy,
+                                                                          wz, k_gravity, terminal, dt);
+        }
     }
     const uint64_t done = n_chunks * kRainChunk;
     if (done < n) {  // tail (< 1024 entities, or everything when unaligned)
