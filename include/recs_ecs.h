@@ -206,6 +206,14 @@ recs_world* recs_app_world(recs_app* app);
 /* ApplicationBuilder::add_system (lib.rs:76-81).  Returns the registration index. */
 int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const uint64_t* component_ids,
                                 uint32_t n_component_ids, uint32_t* out_index);
+/* A generic GPU system (recs_gpu_system_create_kernel) behind the same registration path: `tokens` is the
+ * parameter list of the function -- Read / Write / Entity become the arguments of `body` in order, With / Not /
+ * And / Or / Xor only filter the archetype match (crates/ecs/src/filter.rs) -- and type_names[i] is the C++
+ * type of the i-th argument in `source`.  Element sizes come from the component registry. */
+int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
+                                       const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
+                                       const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index);
+int32_t recs_app_set_system_uniform(recs_app* app, uint32_t system_index, const void* data, uint32_t bytes);
 int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
                                 recs_cpu_system_fn fn, void* user, uint32_t* out_index);
 /* Application::run for `n_ticks` ticks (lib.rs:314-341): schedule generation on first use

@@ -49,7 +49,8 @@ enum {
                                        (crates/ecs/src/archetypes.rs:145-151)                  */
     RECS_ERR_SCHEDULE = 9,          /* ScheduleError (crates/ecs/src/lib.rs:470-493)           */
     RECS_ERR_WORLD = 10,            /* WorldError (crates/ecs/src/lib.rs:600-645)              */
-    RECS_ERR_UNSUPPORTED = 11
+    RECS_ERR_UNSUPPORTED = 11,
+    RECS_ERR_COMPILE = 12           /* the body of a generic GPU system did not compile (NVRTC log in last_error) */
 };
 
 typedef struct recs_gpu_ctx recs_gpu_ctx;
@@ -146,7 +147,9 @@ typedef enum recs_gpu_system_kind {
     RECS_SYS_NBODY_COLLISION = 9,
     /* crates/rain-simulation/src/lib.rs:152-156 -- ground_collision(Entity, Read<Position>, Commands):
      * removed when position.y <= GROUND_HEIGHT.  components = {Position}                          */
-    RECS_SYS_RAIN_GROUND_COLLISION = 10
+    RECS_SYS_RAIN_GROUND_COLLISION = 10,
+    /* a generic system created with recs_gpu_system_create_kernel (not accepted by recs_gpu_system_create) */
+    RECS_SYS_KERNEL = 11
 } recs_gpu_system_kind;
 
 /* One entry of `System::component_accesses()` (crates/ecs/src/systems/mod.rs:88-94). */
@@ -183,6 +186,54 @@ int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* ctx, uint32_t system_
  * ascending component indices (rows) of one of its outer archetypes.  Synchronises the stream. */
 int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t archetype_index,
                                  uint32_t* out_rows, uint32_t cap, uint32_t* out_count);
+
+/* ------------------------------------------------------------------------------------------
+ * Generic GPU systems: any per-entity function over `Read<T>` / `Write<T>` / `Entity` parameters
+ * (crates/ecs/src/systems/mod.rs:457-566 Read, 627-739 Write, 868-912 Entity), iterated over the
+ * concatenation of its matched archetypes' columns exactly once per entity -- the contract of
+ * `SequentiallyIterable::run` / `SegmentIterable::segments` (crates/ecs/src/systems/iteration.rs:26-57,
+ * 151-245; segments may span archetypes, crates/ecs/src/systems/mod.rs:473-540, 645-710).
+ *
+ * The body is CUDA C++ source defining the component types and one function
+ *     void body(Write params as T&, Read/Entity params as const T&, ... [, const Uniform& u]);
+ * in parameter order.  It is compiled for sm_100a with NVRTC when the system is registered
+ * (--fmad=false: rustc never contracts a*b+c), wrapped in a kernel that finds each entity's
+ * archetype through a prefix table and, when the rows fit, stages every column chunk through
+ * shared memory so that HBM sees only 128-bit accesses whatever sizeof(T) is.  Archetype
+ * membership (filters included) stays with the host: recs_gpu_system_set_archetypes.
+ * ---------------------------------------------------------------------------------------- */
+#define RECS_KPARAM_READ 0u
+#define RECS_KPARAM_WRITE 1u
+#define RECS_KPARAM_ENTITY 2u
+/* Component id under which the host binds an archetype's entity column for `Entity` parameters:
+ * one uint64 per row, generation << 32 | id, the value `Entity::hash` feeds
+ * (crates/ecs/src/lib.rs:918-927). */
+#define RECS_GPU_ENTITY_COMPONENT 0xFFFFFFFFFFFFFFFEull
+typedef struct recs_gpu_kernel_param {
+    uint64_t component_id; /* ignored for RECS_KPARAM_ENTITY (RECS_GPU_ENTITY_COMPONENT is used)  */
+    uint32_t elem_size;    /* sizeof(T) on the host == sizeof(type_name) in `source`              */
+    uint32_t kind;         /* RECS_KPARAM_READ / RECS_KPARAM_WRITE / RECS_KPARAM_ENTITY              */
+    const char* type_name; /* C++ type of this parameter in `source`                              */
+} recs_gpu_kernel_param;
+/* Registers a generic system.  `uniform_type` (may be NULL) names a POD struct of at most 256 bytes
+ * passed by value to every call, set with recs_gpu_system_set_uniform (the per-tick scalars a Rust
+ * closure would capture, e.g. a time step or the wind direction).  Compile errors return
+ * RECS_ERR_COMPILE with the NVRTC log in recs_gpu_last_error. */
+int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* ctx, const char* name, const char* source,
+                                      const char* body, const recs_gpu_kernel_param* params,
+                                      uint32_t n_params, const char* uniform_type,
+                                      uint32_t uniform_bytes, uint32_t* out_system_id);
+int32_t recs_gpu_system_set_uniform(recs_gpu_ctx* ctx, uint32_t system_id, const void* data,
+                                    uint32_t bytes);
+/* Generation + compilation only: needs neither a context nor a GPU (NVRTC cross-compiles), so a
+ * host can validate its systems at build time.  `force_direct` != 0 selects the unstaged kernel
+ * form.  Writes the NVRTC log (NUL terminated, truncated to log_cap), the cubin size and the
+ * staged chunk size (0 = direct form). */
+int32_t recs_gpu_kernel_system_compile(const char* source, const char* body,
+                                       const recs_gpu_kernel_param* params, uint32_t n_params,
+                                       const char* uniform_type, int32_t force_direct, char* log,
+                                       uint32_t log_cap, uint64_t* out_cubin_bytes,
+                                       uint32_t* out_staged_chunk);
 
 #define RECS_GPU_ASYNC 0u /* enqueue only: every dependent is a GPU system of this context    */
 #define RECS_GPU_SYNC 1u  /* return after the system's writes are visible to the host thread  */
@@ -246,7 +297,8 @@ int32_t recs_gpu_timer_stop(recs_gpu_ctx* ctx, float* out_ms);
  * out_tflops = 2 * FMAs / s; out_sm_mhz = the SM clock derived from clock64 over the run. */
 int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* ctx, int32_t packed, float* out_tflops,
                                    float* out_sm_mhz);
-/* Writes a buffer larger than L2 (timing hygiene between iterations). */
+/* Writes a buffer larger than L2, then streams a second one through it with loads so that no dirty
+ * lines are left for the next kernel to write back (timing hygiene between iterations). */
 int32_t recs_gpu_flush_l2(recs_gpu_ctx* ctx);
 /* Pinned host memory for the end-to-end path. */
 int32_t recs_gpu_host_alloc(recs_gpu_ctx* ctx, size_t bytes, void** out_ptr);

@@ -25,6 +25,7 @@ ERR_NAMES = {
     9: "RECS_ERR_SCHEDULE",
     10: "RECS_ERR_WORLD",
     11: "RECS_ERR_UNSUPPORTED",
+    12: "RECS_ERR_COMPILE",
 }
 RECS_ERR_NO_DEVICE = 2
 
@@ -39,6 +40,13 @@ SYS_RAIN_WIND_DIRECTION = 7
 SYS_QUERY_ADD = 8
 SYS_NBODY_COLLISION = 9
 SYS_RAIN_GROUND_COLLISION = 10
+SYS_KERNEL = 11
+
+# recs_gpu_kernel_param.kind
+KPARAM_READ = 0
+KPARAM_WRITE = 1
+KPARAM_ENTITY = 2
+ENTITY_COMPONENT = 0xFFFFFFFFFFFFFFFE
 
 GPU_ASYNC = 0
 GPU_SYNC = 1
@@ -73,6 +81,10 @@ class SystemDesc(C.Structure):
     _fields_ = [("name", C.c_char_p), ("n_access", C.c_uint32), ("access", Access * MAX_ACCESSES)]
 
 
+class KernelParam(C.Structure):
+    _fields_ = [("component_id", C.c_uint64), ("elem_size", C.c_uint32), ("kind", C.c_uint32), ("type_name", C.c_char_p)]
+
+
 class Timing(C.Structure):
     _fields_ = [
         ("last_tick_chain_ms", C.c_float),
@@ -104,6 +116,16 @@ GPU_SYMBOLS = {
     "recs_gpu_invalidate": (C.c_int32, [_ctx, C.c_uint32]),
     "recs_gpu_column_device_ptr": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "recs_gpu_system_create": (C.c_int32, [_ctx, C.c_int32, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32)]),
+    "recs_gpu_system_create_kernel": (
+        C.c_int32,
+        [_ctx, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KernelParam), C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)],
+    ),
+    "recs_gpu_system_set_uniform": (C.c_int32, [_ctx, C.c_uint32, C.c_void_p, C.c_uint32]),
+    "recs_gpu_kernel_system_compile": (
+        C.c_int32,
+        [C.c_char_p, C.c_char_p, C.POINTER(KernelParam), C.c_uint32, C.c_char_p, C.c_int32, C.c_char_p, C.c_uint32,
+         C.POINTER(C.c_uint64), C.POINTER(C.c_uint32)],
+    ),
     "recs_gpu_system_describe": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(SystemDesc)]),
     "recs_gpu_system_set_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_system_set_query_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),

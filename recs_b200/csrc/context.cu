@@ -11,12 +11,14 @@
 
 #include <algorithm>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
 
 #include "../../include/recs_gpu.h"
+#include "host/kernel_gen.h"
 #include "kernels.cuh"
 #include "nccl_dyn.h"
 
@@ -33,8 +35,31 @@ struct Column {
     uint64_t version = 0;  // bumped on every write (upload or system)
 };
 
+// State of a generic (NVRTC-compiled) system, recs_gpu_system_create_kernel.
+struct KernelSys {
+    std::vector<KernelParamSpec> params;
+    std::vector<uint64_t> comp;            // component id per parameter
+    KernelPlan plan;
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    std::vector<unsigned char> uniform;    // bytes passed by value to every launch
+    bool has_uniform = false;
+    // archetype table on the device, rebuilt when bindings / membership change
+    unsigned long long* table = nullptr;
+    size_t table_cap = 0;
+    std::vector<unsigned long long> table_host;
+    uint64_t table_epoch = ~0ull;
+    uint64_t n_items = 0;
+    uint32_t n_arch = 0;
+    ~KernelSys() {
+        if (table) cudaFree(table);
+        if (lib) cudaLibraryUnload(lib);
+    }
+};
+
 struct System {
     recs_gpu_system_kind kind;
+    std::shared_ptr<KernelSys> ks;
     uint64_t comp[3] = {0, 0, 0};
     uint32_t n_comp = 0;
     std::string name;
@@ -561,6 +586,73 @@ int32_t run_removal_system(recs_gpu_ctx* c, System& sys) {
     return RECS_OK;
 }
 
+// Generic system: one launch over the concatenation of the matched archetypes.
+int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
+    KernelSys& k = *sys.ks;
+    const size_t n_params = k.params.size();
+    if (k.table_epoch != c->epoch) {
+        // (re)build the table: work-item prefix, entity counts, column base pointers per parameter
+        if (c->capturing) return fail(c, RECS_ERR_CUDA, "archetype table rebuild during graph capture");
+        std::vector<uint32_t> archs;
+        std::vector<std::vector<Column*>> cols;
+        for (uint32_t a : sys.archs) {
+            std::vector<Column*> row(n_params, nullptr);
+            int32_t st;
+            for (size_t p = 0; p < n_params; ++p)
+                if ((st = need_column(c, a, k.comp[p], k.params[p].elem_size, &row[p])) != RECS_OK) return st;
+            for (size_t p = 1; p < n_params; ++p)
+                if ((st = same_count(c, row[0], row[p])) != RECS_OK) return st;
+            if (n_params == 0 || row[0]->count == 0) continue;  // empty archetypes take no work items
+            archs.push_back(a);
+            cols.push_back(row);
+        }
+        const size_t n_arch = archs.size();
+        std::vector<unsigned long long>& t = k.table_host;
+        t.assign(2 * n_arch + 1 + n_params * n_arch, 0ull);
+        unsigned long long items = 0;
+        for (size_t i = 0; i < n_arch; ++i) {
+            const unsigned long long count = cols[i][0]->count;
+            t[i] = items;
+            items += k.plan.staged ? (count + k.plan.chunk - 1) / k.plan.chunk : count;
+            t[n_arch + 1 + i] = count;
+            for (size_t p = 0; p < n_params; ++p)
+                t[2 * n_arch + 1 + p * n_arch + i] = (unsigned long long)(uintptr_t)cols[i][p]->dev;
+        }
+        t[n_arch] = items;
+        int32_t st = ensure(c, &k.table, &k.table_cap, std::max<size_t>(t.size() * sizeof(unsigned long long), 64));
+        if (st != RECS_OK) return st;
+        RECS_CUDA(c, cudaMemcpyAsync(k.table, t.data(), t.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
+                                     c->stream));
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // t is pageable host memory
+        k.n_items = items;
+        k.n_arch = (uint32_t)n_arch;
+        k.table_epoch = c->epoch;
+    }
+    if (k.n_items == 0) return RECS_OK;
+    // grid: one resident wave of chunk-sized CTAs (grid-stride / chunk-stride loops inside)
+    const uint64_t per_cta = k.plan.staged ? 1 : k.plan.chunk;
+    const uint64_t ctas = (k.n_items + per_cta - 1) / per_cta;
+    const uint64_t cap = (uint64_t)c->sm_count * (2048 / k.plan.chunk);
+    const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cap);
+    const unsigned long long* table = k.table;
+    unsigned n_arch = k.n_arch;
+    unsigned long long n_items = k.n_items;
+    void* args[4] = {(void*)&table, (void*)&n_arch, (void*)&n_items, k.has_uniform ? (void*)k.uniform.data() : nullptr};
+    {
+        Timed t(c, T_OTHER);
+        RECS_CUDA(c, cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(k.plan.chunk), args, k.plan.smem_bytes,
+                                      c->stream));
+    }
+    c->kernel_launches++;
+    for (uint32_t a : sys.archs)
+        for (size_t p = 0; p < n_params; ++p)
+            if (k.params[p].kind == RECS_KPARAM_WRITE) {
+                Column* col = find_column(c, a, k.comp[p]);
+                if (col) col->version++;
+            }
+    return RECS_OK;
+}
+
 int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
     if (id >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system id");
     System& s = c->systems[id];
@@ -586,6 +678,8 @@ int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
         case RECS_SYS_NBODY_COLLISION:
         case RECS_SYS_RAIN_GROUND_COLLISION:
             return run_removal_system(c, s);
+        case RECS_SYS_KERNEL:
+            return run_kernel_system(c, s);
     }
     return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system kind");
 }
@@ -731,6 +825,8 @@ void fill_system(System& s, recs_gpu_system_kind kind, const uint64_t* ids) {
             s.name = "ground_collision";
             s.n_comp = 1;
             acc(ids[0], false);
+            break;
+        case RECS_SYS_KERNEL:  // described by recs_gpu_system_create_kernel itself
             break;
     }
     for (uint32_t i = 0; i < s.n_comp; ++i) s.comp[i] = ids[i];
@@ -968,6 +1064,67 @@ int32_t recs_gpu_system_create(recs_gpu_ctx* c, recs_gpu_system_kind kind, const
     c->systems.push_back(s);
     *out_id = (uint32_t)c->systems.size() - 1;
     c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* c, const char* name, const char* source, const char* body,
+                                      const recs_gpu_kernel_param* params, uint32_t n_params, const char* uniform_type,
+                                      uint32_t uniform_bytes, uint32_t* out_id) {
+    RECS_ENTER(c);
+    if (!name || !source || !body || !out_id || (n_params && !params) || n_params == 0 ||
+        n_params > RECS_GPU_MAX_ACCESSES)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: bad argument");
+    if ((uniform_type != nullptr && uniform_type[0]) != (uniform_bytes != 0) || uniform_bytes > 256)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: uniform type / size (<= 256 bytes) mismatch");
+    auto ks = std::make_shared<KernelSys>();
+    System s;
+    s.kind = RECS_SYS_KERNEL;
+    s.name = name;
+    s.n_comp = 0;
+    for (uint32_t i = 0; i < n_params; ++i) {
+        const recs_gpu_kernel_param& p = params[i];
+        if (!p.type_name || !p.type_name[0] || p.elem_size == 0 || p.kind > RECS_KPARAM_ENTITY)
+            return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: bad parameter description");
+        if (p.kind == RECS_KPARAM_ENTITY && p.elem_size != 8)
+            return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: Entity parameters are 8 bytes (generation << 32 | id)");
+        ks->params.push_back({p.type_name, p.elem_size, p.kind});
+        const uint64_t comp = p.kind == RECS_KPARAM_ENTITY ? RECS_GPU_ENTITY_COMPONENT : p.component_id;
+        ks->comp.push_back(comp);
+        if (p.kind != RECS_KPARAM_ENTITY) {  // `Entity` is no component access (crates/ecs/src/systems/mod.rs:893-895)
+            recs_gpu_access a;
+            a.component_id = comp;
+            a.is_write = p.kind == RECS_KPARAM_WRITE ? 1 : 0;
+            s.access.push_back(a);
+        }
+    }
+    static const bool force_direct = getenv("RECS_GPU_KERNEL_DIRECT") != nullptr;  // A/B knob
+    ks->plan = plan_kernel_system(source, body, ks->params, uniform_type ? uniform_type : "", force_direct ? 1 : 0);
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_kernel_system(ks->plan.source, &cubin, &log))
+        return fail(c, RECS_ERR_COMPILE, std::string("system '") + name + "' did not compile:\n" + log);
+    RECS_CUDA(c, cudaLibraryLoadData(&ks->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    RECS_CUDA(c, cudaLibraryGetKernel(&ks->kernel, ks->lib, "recs_generic_system"));
+    ks->has_uniform = uniform_bytes != 0;
+    ks->uniform.assign(std::max<uint32_t>(uniform_bytes, 1), 0);
+    s.ks = ks;
+    c->systems.push_back(s);
+    *out_id = (uint32_t)c->systems.size() - 1;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_set_uniform(recs_gpu_ctx* c, uint32_t id, const void* data, uint32_t bytes) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || !c->systems[id].ks || !data)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_uniform: not a generic system");
+    KernelSys& k = *c->systems[id].ks;
+    if (!k.has_uniform || bytes != k.uniform.size())
+        return fail(c, RECS_ERR_SIZE_MISMATCH, "system_set_uniform: size differs from the registered uniform type");
+    if (memcmp(k.uniform.data(), data, bytes) != 0) {
+        memcpy(k.uniform.data(), data, bytes);
+        drop_graph(c);  // a captured tick holds the old value
+    }
     return RECS_OK;
 }
 

@@ -70,6 +70,8 @@ std::vector<recs_param_token> gpu_kind_tokens(recs_gpu_system_kind kind, const u
                     tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_QUERY_END), tok(RECS_PARAM_COMMANDS)};
         case RECS_SYS_RAIN_GROUND_COLLISION:  // crates/rain-simulation/src/lib.rs:152
             return {tok(RECS_PARAM_ENTITY), tok(RECS_PARAM_READ, c[0]), tok(RECS_PARAM_COMMANDS)};
+        case RECS_SYS_KERNEL:  // generic systems bring their own parameter list (recs_app_add_gpu_kernel_system)
+            return {};
     }
     return {};
 }
@@ -94,6 +96,12 @@ struct recs_app {
     size_t scheduled_systems = 0;
     std::vector<uint32_t> last_order, last_batch;
     std::map<ColKey, Mirror> mirror;
+    // entity columns for `Entity` parameters of generic GPU systems: generation << 32 | id per row
+    struct EntityColumn {
+        std::vector<uint64_t> keys;
+        uint64_t version = ~0ull;
+    };
+    std::map<uint32_t, EntityColumn> entity_columns;
     std::string error;
 
     int32_t fail(int32_t code, const std::string& msg) {
@@ -139,6 +147,22 @@ int32_t ensure_on_host(recs_app* app, uint32_t arch, uint64_t comp) {
     return RECS_OK;
 }
 
+// `Entity` parameter of a generic GPU system: the archetype's entity list as a device column.
+int32_t ensure_entities_on_device(recs_app* app, uint32_t arch) {
+    recs_world* w = app->world;
+    if (arch >= w->archetypes.size()) return app->fail(RECS_ERR_WORLD, "could not find archetype with the given index");
+    const Archetype& a = w->archetypes[arch];
+    recs_app::EntityColumn& col = app->entity_columns[arch];
+    if (col.version == a.version) return RECS_OK;
+    col.keys.resize(a.entities.size());
+    for (size_t i = 0; i < a.entities.size(); ++i) col.keys[i] = entity_key(a.entities[i]);
+    int32_t st = recs_gpu_bind_column(app->gpu, arch, RECS_GPU_ENTITY_COMPONENT, col.keys.data(), 8, col.keys.size());
+    if (st != RECS_OK) return gpu_fail(app, st);
+    if ((st = recs_gpu_upload(app->gpu, arch, RECS_GPU_ENTITY_COMPONENT)) != RECS_OK) return gpu_fail(app, st);
+    col.version = a.version;
+    return RECS_OK;
+}
+
 // Query membership of the system + residency of every column it touches, then the launch.
 int32_t run_gpu_system(recs_app* app, AppSystem& s) {
     if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "GPU system registered on an application without a GPU context");
@@ -151,6 +175,9 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
         if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE)
             for (uint32_t a : archs)
                 if ((st = ensure_on_device(app, a, p.comp)) != RECS_OK) return st;
+        if (p.op == RECS_PARAM_ENTITY && s.kind == RECS_SYS_KERNEL)
+            for (uint32_t a : archs)
+                if ((st = ensure_entities_on_device(app, a)) != RECS_OK) return st;
         if (p.op == RECS_PARAM_QUERY_BEGIN)
             for (const Param& q : p.children)
                 if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
@@ -318,6 +345,54 @@ int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const 
     app->systems.push_back(s);
     if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
     return RECS_OK;
+}
+
+int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
+                                       const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
+                                       const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index) {
+    if (!app || !name || !source || !body || (n_tokens && !tokens) || !type_names) return RECS_ERR_INVALID_ARGUMENT;
+    if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "no GPU context: GPU systems cannot be registered (there is no CPU fallback)");
+    AppSystem s;
+    s.gpu = true;
+    s.kind = RECS_SYS_KERNEL;
+    s.name = name;
+    std::string err;
+    if (!parse_params(tokens, n_tokens, &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
+    // Read / Write / Entity become kernel arguments in order; filters only shape the archetype match
+    std::vector<recs_gpu_kernel_param> kp;
+    for (const Param& p : s.params) {
+        recs_gpu_kernel_param k;
+        k.component_id = p.comp;
+        k.type_name = type_names[kp.size()];
+        if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE) {
+            auto it = app->world->registry.find(p.comp);
+            if (it == app->world->registry.end()) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: component is not registered");
+            k.elem_size = it->second.elem;
+            k.kind = p.op == RECS_PARAM_WRITE ? RECS_KPARAM_WRITE : RECS_KPARAM_READ;
+        } else if (p.op == RECS_PARAM_ENTITY) {
+            k.elem_size = 8;
+            k.kind = RECS_KPARAM_ENTITY;
+        } else if (p.op == RECS_PARAM_QUERY_BEGIN || p.op == RECS_PARAM_COMMANDS) {
+            return app->fail(RECS_ERR_UNSUPPORTED, "kernel system: Query<...> and Commands parameters are not available in generic GPU systems");
+        } else {
+            continue;  // With / Not / And / Or / Xor
+        }
+        if (!k.type_name) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: missing type name");
+        kp.push_back(k);
+    }
+    int32_t st = recs_gpu_system_create_kernel(app->gpu, name, source, body, kp.data(), (uint32_t)kp.size(), uniform_type,
+                                               uniform_bytes, &s.gpu_id);
+    if (st != RECS_OK) return gpu_fail(app, st);
+    params_accesses(s.params, &s.access);
+    app->systems.push_back(s);
+    if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
+    return RECS_OK;
+}
+
+int32_t recs_app_set_system_uniform(recs_app* app, uint32_t index, const void* data, uint32_t bytes) {
+    if (!app || index >= app->systems.size() || !app->systems[index].gpu) return RECS_ERR_INVALID_ARGUMENT;
+    int32_t st = recs_gpu_system_set_uniform(app->gpu, app->systems[index].gpu_id, data, bytes);
+    return st == RECS_OK ? RECS_OK : gpu_fail(app, st);
 }
 
 int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,

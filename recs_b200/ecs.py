@@ -89,6 +89,11 @@ ECS_SYMBOLS = {
     "recs_app_last_error": (C.c_char_p, [_a]),
     "recs_app_world": (_w, [_a]),
     "recs_app_add_gpu_system": (C.c_int32, [_a, C.c_int32, _u64p, C.c_uint32, _u32p]),
+    "recs_app_add_gpu_kernel_system": (
+        C.c_int32,
+        [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32, _u32p],
+    ),
+    "recs_app_set_system_uniform": (C.c_int32, [_a, C.c_uint32, C.c_void_p, C.c_uint32]),
     "recs_app_add_cpu_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SYSTEM_FN, C.c_void_p, _u32p]),
     "recs_app_run": (C.c_int32, [_a, C.c_uint32, C.c_int32]),
     "recs_app_command_create": (C.c_int32, [_a, _u64p, _vpp, C.c_uint32]),
@@ -469,6 +474,26 @@ class Application:
         self._check(lib.recs_app_add_gpu_system(self._h, kind, ids, len(components), C.byref(idx)), "recs_app_add_gpu_system")
         self.system_names.append(name or f"gpu:{kind}")
         return int(idx.value)
+
+    def add_gpu_kernel_system(self, name: str, source: str, body: str, params, type_names: Sequence[str],
+                              uniform_type: str | None = None, uniform_bytes: int = 0) -> int:
+        """A generic GPU system: `params` is the function's parameter list (same grammar as CPU systems, filters
+        included); `type_names` are the C++ types of its Read / Write / Entity arguments in `source`, in order."""
+        arr, n = tokens(params)
+        names = (C.c_char_p * max(len(type_names), 1))(*[t.encode() for t in type_names])
+        idx = C.c_uint32()
+        self._check(
+            lib.recs_app_add_gpu_kernel_system(
+                self._h, name.encode(), source.encode(), body.encode(), arr, n, names,
+                uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(idx)),
+            "recs_app_add_gpu_kernel_system",
+        )
+        self.system_names.append(name)
+        return int(idx.value)
+
+    def set_system_uniform(self, system: int, data: bytes) -> None:
+        buf = C.create_string_buffer(bytes(data), len(data))
+        self._check(lib.recs_app_set_system_uniform(self._h, system, buf, len(data)), "recs_app_set_system_uniform")
 
     def add_cpu_system(self, name: str, params, fn) -> int:
         """fn(archetype, count, columns) with columns = list of raw host pointers in parameter order."""

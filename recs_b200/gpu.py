@@ -122,6 +122,24 @@ class GpuContext:
         self._check(lib.recs_gpu_system_create(self._ctx, kind, ids, len(components), C.byref(out)), "recs_gpu_system_create")
         return int(out.value)
 
+    def create_kernel_system(self, name: str, source: str, body: str, params, uniform_type: str | None = None,
+                             uniform_bytes: int = 0) -> int:
+        """Registers a generic system (recs_gpu_system_create_kernel).  `params` is a sequence of
+        (component_id, elem_size, kind, type_name) with kind in {"read", "write", "entity"}."""
+        arr = kernel_params(params)
+        out = C.c_uint32()
+        self._check(
+            lib.recs_gpu_system_create_kernel(
+                self._ctx, name.encode(), source.encode(), body.encode(), arr, len(arr),
+                uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(out)),
+            "recs_gpu_system_create_kernel",
+        )
+        return int(out.value)
+
+    def set_system_uniform(self, system: int, data: bytes) -> None:
+        buf = C.create_string_buffer(bytes(data), len(data))
+        self._check(lib.recs_gpu_system_set_uniform(self._ctx, system, buf, len(data)), "recs_gpu_system_set_uniform")
+
     def describe_system(self, system: int) -> tuple[str, list[tuple[int, bool]]]:
         desc = _lib.SystemDesc()
         self._check(lib.recs_gpu_system_describe(self._ctx, system, C.byref(desc)), "recs_gpu_system_describe")
@@ -223,3 +241,31 @@ class GpuContext:
         buf = (C.c_uint8 * max(nbytes, 1)).from_address(ptr.value)
         arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
         return arr
+
+
+_KPARAM_KINDS = {"read": _lib.KPARAM_READ, "write": _lib.KPARAM_WRITE, "entity": _lib.KPARAM_ENTITY}
+
+
+def kernel_params(params):
+    """ctypes array of recs_gpu_kernel_param from (component_id, elem_size, kind, type_name) tuples."""
+    arr = (_lib.KernelParam * max(len(params), 1))()
+    for i, (comp, elem, kind, type_name) in enumerate(params):
+        arr[i].component_id = comp
+        arr[i].elem_size = elem
+        arr[i].kind = _KPARAM_KINDS[kind]
+        arr[i].type_name = type_name.encode()
+    arr._n = len(params)
+    return arr
+
+
+def compile_kernel_system(source: str, body: str, params, uniform_type: str | None = None, force_direct: bool = False):
+    """recs_gpu_kernel_system_compile: generation + NVRTC only (no GPU needed).
+    Returns (status, log, cubin_bytes, staged_chunk)."""
+    arr = kernel_params(params)
+    log = C.create_string_buffer(16384)
+    size = C.c_uint64()
+    chunk = C.c_uint32()
+    st = lib.recs_gpu_kernel_system_compile(
+        source.encode(), body.encode(), arr, len(params), uniform_type.encode() if uniform_type else None,
+        1 if force_direct else 0, log, len(log), C.byref(size), C.byref(chunk))
+    return int(st), log.value.decode(errors="replace"), int(size.value), int(chunk.value)

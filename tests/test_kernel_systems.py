@@ -1,0 +1,259 @@
+"""Generic GPU systems (recs_gpu_system_create_kernel): any per-entity function over Read / Write / Entity
+parameters, iterated over the concatenation of its matched archetypes' columns -- the par-iter query
+contract of crates/ecs/src/systems/mod.rs:457-566, 627-739 and iteration.rs:26-57, 151-245.
+
+CPU part: source generation + NVRTC compilation for sm_100a (needs no GPU).  GPU part: the reference's
+frag_iter / simple_iter benchmark systems and filter / Entity / uniform cases, bit-exact against numpy
+restatements of the Rust bodies (mul-then-add, never fused)."""
+import struct
+
+import numpy as np
+import pytest
+
+from recs_b200.gpu import compile_kernel_system
+
+VEC3 = "struct Position { float x, y, z; };\nstruct Velocity { float x, y, z; };\n"
+# crates/ecs_bench_suite/src/recs/simple_iter.rs:47-49
+SIMPLE_ITER = VEC3 + "void movement(Position& p, const Velocity& v) { p.x += v.x; p.y += v.y; p.z += v.z; }\n"
+# crates/ecs_bench_suite/src/recs/frag_iter.rs:40-42
+FRAG_ITER = "struct Data { float v; };\nvoid doubling(Data& d) { d.v *= 2.0f; }\n"
+# crates/n-body/src/lib.rs:87-93 with the time step as a uniform
+MOVEMENT_DT = VEC3 + (
+    "struct Dt { float dt; };\n"
+    "void movement(Position& p, const Velocity& v, const Dt& u) {\n"
+    "    p.x += v.x * u.dt; p.y += v.y * u.dt; p.z += v.z * u.dt;\n}\n"
+)
+POS, VEL, DATA, KEY, TAG_A, TAG_B = 11, 12, 13, 14, 15, 16
+
+
+# ---- CPU: generation + compilation ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("direct", [False, True])
+def test_kernel_system_compiles_for_sm100a_without_a_gpu(direct):
+    st, log, cubin, chunk = compile_kernel_system(
+        SIMPLE_ITER, "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")], force_direct=direct
+    )
+    assert st == 0, log
+    assert cubin > 1000
+    assert chunk == (0 if direct else 256)
+
+
+def test_wide_rows_shrink_the_staged_chunk_or_go_direct():
+    src = "struct M { float m[16]; };\nstruct Big { float b[1024]; };\nvoid f(M& m) { m.m[0] += 1.0f; }\nvoid g(Big& b) { b.b[0] += 1.0f; }\n"
+    st, log, _, chunk = compile_kernel_system(src, "f", [(1, 64, "write", "M")])
+    assert st == 0, log
+    assert chunk == 256  # 256 x 64 B = 16 KiB
+    st, log, _, chunk = compile_kernel_system(src, "g", [(1, 4096, "write", "Big")])
+    assert st == 0, log
+    assert chunk == 0  # 32 x 4 KiB does not fit 48 KiB: direct global references
+
+
+def test_compile_errors_come_back_with_the_nvrtc_log():
+    st, log, cubin, _ = compile_kernel_system(
+        SIMPLE_ITER.replace("p.z += v.z;", "p.w += v.z;"), "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")]
+    )
+    assert st == 12 and cubin == 0  # RECS_ERR_COMPILE
+    assert "has no member" in log and "w" in log
+
+
+def test_element_size_mismatch_is_a_compile_error():
+    st, log, _, _ = compile_kernel_system(SIMPLE_ITER, "movement", [(POS, 16, "write", "Position"), (VEL, 12, "read", "Velocity")])
+    assert st == 12
+    assert "sizeof(Position) differs from the bound column's element size" in log
+
+
+def test_read_parameters_are_const():
+    # a system that writes through a Read<T> must not compile (Read derefs to &T, systems/mod.rs:106-118)
+    src = VEC3 + "void bad(Position& p, Velocity& v) { v.x = p.x; }\n"
+    st, log, _, _ = compile_kernel_system(src, "bad", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")])
+    assert st == 12
+
+
+# ---- GPU -----------------------------------------------------------------------------------------------------------
+def _bind(ctx, arch, comp, array):
+    ctx.bind_column(arch, comp, array)
+    ctx.upload(arch, comp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 255, 256, 257, 10000])
+@pytest.mark.parametrize("direct", [False, True])
+def test_simple_iter_as_a_generic_system(gpu_ctx, monkeypatch, n, direct):
+    """crates/ecs_bench_suite/src/recs/simple_iter.rs:28-36, 47-52 (10 000 entities there)."""
+    from recs_b200 import GpuContext
+
+    if direct:
+        monkeypatch.setenv("RECS_GPU_KERNEL_DIRECT", "1")
+    rng = np.random.default_rng(n)
+    pos = rng.standard_normal((n, 3)).astype(np.float32)
+    vel = rng.standard_normal((n, 3)).astype(np.float32)
+    want = pos.copy()
+    with GpuContext(device=0) as ctx:
+        _bind(ctx, 1, POS, pos)
+        _bind(ctx, 1, VEL, vel)
+        sid = ctx.create_kernel_system("movement", SIMPLE_ITER, "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")])
+        assert ctx.describe_system(sid) == ("movement", [(POS, True), (VEL, False)])
+        ctx.set_archetypes(sid, [1])
+        for _ in range(3):
+            ctx.run_system(sid)
+            want = want + vel
+        ctx.download(1, POS)
+        ctx.download(1, VEL)
+    assert np.array_equal(pos.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_frag_iter_26_archetypes(gpu_ctx):
+    """crates/ecs_bench_suite/src/recs/frag_iter.rs:6-43: 26 archetypes x 20 entities share `Data`; the system
+    doubles every value exactly once per run.  Ragged counts and an empty archetype are added here."""
+    ctx = gpu_ctx
+    counts = [20] * 26 + [0, 1, 300, 257]
+    cols = []
+    for a, c in enumerate(counts):
+        col = (np.arange(c, dtype=np.float32) + 1000.0 * a + 1.0).reshape(c, 1)
+        cols.append(col)
+        _bind(ctx, a + 1, DATA, col)
+    want = [c.copy() for c in cols]
+    sid = ctx.create_kernel_system("doubling", FRAG_ITER, "doubling", [(DATA, 4, "write", "Data")])
+    ctx.set_archetypes(sid, list(range(1, len(counts) + 1)))
+    ctx.reset_timing()
+    for _ in range(2):
+        ctx.run_system(sid)
+    assert ctx.timing()["kernel_launches"] == 2  # one launch for all archetypes
+    for a in range(len(counts)):
+        ctx.download(a + 1, DATA)
+        assert np.array_equal(cols[a], want[a] * np.float32(4.0)), a
+
+
+@pytest.mark.gpu
+def test_uniform_and_unfused_arithmetic(gpu_ctx):
+    """`p += v * dt` must round like Rust (mul, then add): the generated kernels are compiled with --fmad=false."""
+    ctx = gpu_ctx
+    n = 5000
+    rng = np.random.default_rng(3)
+    pos = (rng.standard_normal((n, 3)) * 100).astype(np.float32)
+    vel = (rng.standard_normal((n, 3)) * 1e4).astype(np.float32)
+    dt = np.float32(1.0 / 20000.0)
+    want = pos + vel * dt  # numpy: two roundings
+    fused = (pos.astype(np.float64) + vel.astype(np.float64) * np.float64(dt)).astype(np.float32)
+    assert not np.array_equal(want, fused)  # the data distinguishes the two
+    _bind(ctx, 1, POS, pos)
+    _bind(ctx, 1, VEL, vel)
+    sid = ctx.create_kernel_system(
+        "movement", MOVEMENT_DT, "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")], "Dt", 4
+    )
+    ctx.set_archetypes(sid, [1])
+    ctx.set_system_uniform(sid, struct.pack("f", dt))
+    ctx.run_system(sid)
+    ctx.download(1, POS)
+    assert np.array_equal(pos.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_generic_system_in_a_captured_tick_and_uniform_change(gpu_ctx):
+    ctx = gpu_ctx
+    n = 1000
+    pos = np.zeros((n, 3), np.float32)
+    vel = np.ones((n, 3), np.float32)
+    _bind(ctx, 1, POS, pos)
+    _bind(ctx, 1, VEL, vel)
+    sid = ctx.create_kernel_system(
+        "movement", MOVEMENT_DT, "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")], "Dt", 4
+    )
+    ctx.set_archetypes(sid, [1])
+    ctx.set_tick_order([sid])
+    ctx.set_system_uniform(sid, struct.pack("f", 0.5))
+    ctx.tick(4)  # eager tick + captured graph
+    ctx.set_system_uniform(sid, struct.pack("f", 0.25))
+    ctx.tick(4)  # must not replay the old uniform
+    ctx.download(1, POS)
+    assert np.array_equal(pos, np.full((n, 3), 3.0, np.float32))
+
+
+@pytest.mark.gpu
+def test_entity_parameter(gpu_ctx):
+    """`Entity` parameter (crates/ecs/src/systems/mod.rs:868-912): the body sees generation << 32 | id of its row."""
+    from recs_b200 import _lib
+
+    ctx = gpu_ctx
+    src = "struct Key { unsigned long long k; };\nvoid stamp(const unsigned long long& e, Key& out) { out.k = e * 2ull + 1ull; }\n"
+    keys = [np.arange(5, dtype=np.uint64) + (7 << 32), np.arange(400, dtype=np.uint64) + 100]
+    outs = [np.zeros(5, np.uint64), np.zeros(400, np.uint64)]
+    for a in range(2):
+        _bind(ctx, a + 1, _lib.ENTITY_COMPONENT, keys[a])
+        _bind(ctx, a + 1, KEY, outs[a])
+    sid = ctx.create_kernel_system("stamp", src, "stamp", [(0, 8, "entity", "unsigned long long"), (KEY, 8, "write", "Key")])
+    assert ctx.describe_system(sid) == ("stamp", [(KEY, True)])  # Entity is no component access (mod.rs:893-895)
+    ctx.set_archetypes(sid, [1, 2])
+    ctx.run_system(sid)
+    for a in range(2):
+        ctx.download(a + 1, KEY)
+        assert np.array_equal(outs[a], keys[a] * 2 + 1)
+
+
+@pytest.mark.gpu
+def test_missing_column_and_size_mismatch_are_reported(gpu_ctx):
+    from recs_b200 import RecsGpuError
+
+    ctx = gpu_ctx
+    pos = np.zeros((10, 3), np.float32)
+    _bind(ctx, 1, POS, pos)
+    sid = ctx.create_kernel_system("movement", SIMPLE_ITER, "movement", [(POS, 12, "write", "Position"), (VEL, 12, "read", "Velocity")])
+    ctx.set_archetypes(sid, [1])
+    with pytest.raises(RecsGpuError) as e:
+        ctx.run_system(sid)
+    assert e.value.code == 5  # RECS_ERR_MISSING_PARAMETER
+    ctx.clear_error()
+    with pytest.raises(RecsGpuError) as e:
+        ctx.create_kernel_system("broken", "void f(int& x) { x = ; }", "f", [(POS, 4, "write", "int")])
+    assert e.value.code == 12 and "expected an expression" in str(e.value)
+    ctx.clear_error()
+
+
+@pytest.mark.gpu
+def test_application_runs_generic_systems_with_filters(gpu_ctx):
+    """Through the Application: archetype membership with filters is computed by the host layer
+    (crates/ecs/src/filter.rs, systems/mod.rs:986-1000), the schedule sees the component accesses, and a
+    structural change re-binds.  Checked against the Python ECS oracle's membership."""
+    from oracle import ecs_oracle
+    from recs_b200.ecs import Application
+
+    app = Application(gpu_ctx)
+    w = app.world
+    w.register_component(DATA, np.dtype(np.float32), "Data")
+    w.register_component(TAG_A, np.dtype(np.float32), "A")
+    w.register_component(TAG_B, np.dtype(np.float32), "B")
+    ow = ecs_oracle.World()
+    layouts = [(DATA,), (DATA, TAG_A), (DATA, TAG_B), (DATA, TAG_A, TAG_B), (TAG_A,)]
+    ents = []
+    for k, comps in enumerate(layouts):
+        for i in range(3 + 50 * k):
+            vals = {c: np.float32(100 * k + i + 1) for c in comps}
+            ents.append(w.create_entity(vals))
+            ow.create_entity({c: float(v) for c, v in vals.items()})
+    params = [("write", DATA), ("with", TAG_A), ("not", ("with", TAG_B))]
+    app.add_gpu_kernel_system("doubling", FRAG_ITER, "doubling", params, ["Data"])
+    matched = sorted(w.query_archetypes(params))
+    assert matched == sorted(ecs_oracle.get_archetype_indices(ow, params)) and len(matched) == 1
+    app.run(2)
+    app.sync_to_host()
+    for arch in range(w.archetype_count()):
+        comps = w.archetype_components(arch)
+        if DATA not in comps:
+            continue
+        col = w.column(arch, DATA)
+        n = len(w.archetype_entities(arch))
+        k = [set(l) for l in layouts].index(set(comps))
+        base = np.array([100 * k + i + 1 for i in range(n)], np.float32)
+        factor = np.float32(4.0) if arch in matched else np.float32(1.0)
+        assert np.array_equal(col[:n].reshape(-1), base * factor), (arch, comps)
+    # structural change: a DATA+A entity gains B and leaves the match; the rest keeps doubling
+    moved = ents[3 + 1]  # second entity of layout 1 (DATA, TAG_A)
+    w.add_components(moved, {TAG_B: np.float32(0.0)})
+    app.run(1)
+    app.sync_to_host()
+    arch = matched[0]
+    col = w.column(arch, DATA)
+    n = len(w.archetype_entities(arch))
+    assert n == 53 - 1
+    assert np.all(col[:n].reshape(-1) % np.float32(8.0) == 0)
+    app.close()
