@@ -629,10 +629,17 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         k.table_epoch = c->epoch;
     }
     if (k.n_items == 0) return RECS_OK;
-    // grid: one resident wave of chunk-sized CTAs (grid-stride / chunk-stride loops inside)
-    const uint64_t per_cta = k.plan.staged ? 1 : k.plan.chunk;
-    const uint64_t ctas = (k.n_items + per_cta - 1) / per_cta;
-    const uint64_t cap = (uint64_t)c->sm_count * (2048 / k.plan.chunk);
+    // grid: persistent CTAs for the pipelined form (three per SM while shared memory allows), one resident wave of
+    // grid-stride CTAs for the direct form
+    uint64_t ctas, cap;
+    if (k.plan.staged) {
+        const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(3, (227u * 1024u) / (k.plan.smem_bytes + 2048u)));
+        ctas = k.n_items;
+        cap = (uint64_t)c->sm_count * per_sm;
+    } else {
+        ctas = (k.n_items + k.plan.threads - 1) / k.plan.threads;
+        cap = (uint64_t)c->sm_count * (2048 / k.plan.threads);
+    }
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cap);
     const unsigned long long* table = k.table;
     unsigned n_arch = k.n_arch;
@@ -640,7 +647,7 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
     void* args[4] = {(void*)&table, (void*)&n_arch, (void*)&n_items, k.has_uniform ? (void*)k.uniform.data() : nullptr};
     {
         Timed t(c, T_OTHER);
-        RECS_CUDA(c, cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(k.plan.chunk), args, k.plan.smem_bytes,
+        RECS_CUDA(c, cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(k.plan.threads), args, k.plan.smem_bytes,
                                       c->stream));
     }
     c->kernel_launches++;
@@ -1105,6 +1112,9 @@ int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* c, const char* name, const c
         return fail(c, RECS_ERR_COMPILE, std::string("system '") + name + "' did not compile:\n" + log);
     RECS_CUDA(c, cudaLibraryLoadData(&ks->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
     RECS_CUDA(c, cudaLibraryGetKernel(&ks->kernel, ks->lib, "recs_generic_system"));
+    if (ks->plan.smem_bytes > 32u * 1024u)  // dynamic + the static barrier words must stay under the 48 KiB default
+        RECS_CUDA(c, cudaFuncSetAttribute((const void*)ks->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)ks->plan.smem_bytes));
     ks->has_uniform = uniform_bytes != 0;
     ks->uniform.assign(std::max<uint32_t>(uniform_bytes, 1), 0);
     s.ks = ks;

@@ -20,9 +20,10 @@ struct KernelParamSpec {
 };
 
 struct KernelPlan {
-    bool staged = false;       // columns staged through shared memory in chunks of `chunk` entities
-    uint32_t chunk = 256;      // entities per CTA iteration (== threads per CTA)
-    uint32_t smem_bytes = 0;   // dynamic shared memory of the staged form
+    bool staged = false;       // pipelined form: column chunks of `chunk` entities cross HBM as TMA bulk copies
+    uint32_t chunk = 256;      // entities per work item (pipelined) / per CTA pass (direct)
+    uint32_t threads = 256;    // CTA size
+    uint32_t smem_bytes = 0;   // dynamic shared memory of the pipelined form (all stages)
     std::vector<uint32_t> smem_offset;  // per parameter
     std::string source;        // user source + generated kernel `recs_generic_system`
 };

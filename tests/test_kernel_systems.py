@@ -34,17 +34,17 @@ def test_kernel_system_compiles_for_sm100a_without_a_gpu(direct):
     )
     assert st == 0, log
     assert cubin > 1000
-    assert chunk == (0 if direct else 256)
+    assert chunk == (0 if direct else 1024)  # pipelined form: 1024-entity chunks, 3 stages x 24 KiB
 
 
 def test_wide_rows_shrink_the_staged_chunk_or_go_direct():
     src = "struct M { float m[16]; };\nstruct Big { float b[1024]; };\nvoid f(M& m) { m.m[0] += 1.0f; }\nvoid g(Big& b) { b.b[0] += 1.0f; }\n"
     st, log, _, chunk = compile_kernel_system(src, "f", [(1, 64, "write", "M")])
     assert st == 0, log
-    assert chunk == 256  # 256 x 64 B = 16 KiB
+    assert chunk == 256  # 3 stages x 256 x 64 B = 48 KiB fits the 72 KiB budget, 512 entities would not
     st, log, _, chunk = compile_kernel_system(src, "g", [(1, 4096, "write", "Big")])
     assert st == 0, log
-    assert chunk == 0  # 32 x 4 KiB does not fit 48 KiB: direct global references
+    assert chunk == 0  # 3 stages x 32 x 4 KiB does not fit: direct global references
 
 
 def test_compile_errors_come_back_with_the_nvrtc_log():
@@ -75,7 +75,7 @@ def _bind(ctx, arch, comp, array):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n", [1, 255, 256, 257, 10000])
+@pytest.mark.parametrize("n", [1, 255, 1023, 1024, 1025, 4096, 10000, 300001])
 @pytest.mark.parametrize("direct", [False, True])
 def test_simple_iter_as_a_generic_system(gpu_ctx, monkeypatch, n, direct):
     """crates/ecs_bench_suite/src/recs/simple_iter.rs:28-36, 47-52 (10 000 entities there)."""
@@ -106,7 +106,7 @@ def test_frag_iter_26_archetypes(gpu_ctx):
     """crates/ecs_bench_suite/src/recs/frag_iter.rs:6-43: 26 archetypes x 20 entities share `Data`; the system
     doubles every value exactly once per run.  Ragged counts and an empty archetype are added here."""
     ctx = gpu_ctx
-    counts = [20] * 26 + [0, 1, 300, 257]
+    counts = [20] * 26 + [0, 1, 300, 1024, 0, 2051, 257]
     cols = []
     for a, c in enumerate(counts):
         col = (np.arange(c, dtype=np.float32) + 1000.0 * a + 1.0).reshape(c, 1)
