@@ -108,6 +108,27 @@ int32_t recs_gpu_download(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t 
 /* Structural change happened on the host (command-buffer playback,
  * crates/ecs/src/lib.rs:321-323): all bindings of that archetype become stale. */
 int32_t recs_gpu_invalidate(recs_gpu_ctx* ctx, uint32_t archetype_index);
+/* Structural changes WITHOUT a round trip (command-buffer playback against resident columns,
+ * crates/ecs/src/systems/command_buffers.rs:377-435): the host World stays the authority on entity ids and
+ * row indices and replays on the device what it did to its own columns.
+ *  - recs_gpu_column_append: `Vec::push` of new rows (archetypes.rs:200-231).  Rows [old count, new_count) are
+ *    copied from host_ptr (the column's possibly re-allocated base); earlier rows are NOT touched, the device
+ *    buffer grows geometrically with a device-to-device copy.
+ *  - recs_gpu_archetype_move_rows: a batch of `swap_remove`s (archetypes.rs:233-243) folded into
+ *    row[dst[k]] = row[src[k]] (sources as they were before the batch), applied to the listed resident columns
+ *    of the archetype, which then have new_count rows.
+ *  - recs_gpu_column_rebind_host: the host Vec moved (re-allocation) but its contents did not change.
+ *  - recs_gpu_get_transfer_bytes: column bytes copied host->device / device->host so far (tests assert that a
+ *    tick with structural changes moves only the new rows). */
+int32_t recs_gpu_column_append(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id,
+                               void* host_ptr, uint64_t new_count);
+int32_t recs_gpu_archetype_move_rows(recs_gpu_ctx* ctx, uint32_t archetype_index,
+                                     const uint64_t* component_ids, uint32_t n_components,
+                                     const uint32_t* dst_rows, const uint32_t* src_rows, uint32_t n_moves,
+                                     uint64_t new_count);
+int32_t recs_gpu_column_rebind_host(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id,
+                                    void* host_ptr);
+int32_t recs_gpu_get_transfer_bytes(recs_gpu_ctx* ctx, uint64_t* out_h2d_bytes, uint64_t* out_d2h_bytes);
 /* Raw device pointer of a column (for zero-copy interop, e.g. torch / NCCL plumbing). */
 int32_t recs_gpu_column_device_ptr(recs_gpu_ctx* ctx, uint32_t archetype_index,
                                    uint64_t component_id, void** out_dev_ptr, uint64_t* out_count);

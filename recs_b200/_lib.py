@@ -113,6 +113,13 @@ GPU_SYMBOLS = {
     "recs_gpu_bind_column": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64]),
     "recs_gpu_upload": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64]),
     "recs_gpu_download": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64]),
+    "recs_gpu_column_append": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
+    "recs_gpu_archetype_move_rows": (
+        C.c_int32,
+        [_ctx, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.c_uint64],
+    ),
+    "recs_gpu_column_rebind_host": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_void_p]),
+    "recs_gpu_get_transfer_bytes": (C.c_int32, [_ctx, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_invalidate": (C.c_int32, [_ctx, C.c_uint32]),
     "recs_gpu_column_device_ptr": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "recs_gpu_system_create": (C.c_int32, [_ctx, C.c_int32, C.POINTER(C.c_uint64), C.c_uint32, C.POINTER(C.c_uint32)]),

@@ -144,6 +144,12 @@ struct recs_gpu_ctx {
     float* l2_flush = nullptr;
     size_t l2_flush_bytes = 0;
     bool l2_flush_zeroed = false;
+    // structural changes on resident columns
+    uint32_t* move_idx = nullptr;
+    size_t move_idx_cap = 0;
+    unsigned char* move_tmp = nullptr;
+    size_t move_tmp_cap = 0;
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;  // component-column traffic over PCIe since create / reset
 };
 
 namespace {
@@ -950,6 +956,8 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
         if (c->posm) cudaFree(c->posm);
         if (c->frags) cudaFree(c->frags);
         if (c->l2_flush) cudaFree(c->l2_flush);
+        if (c->move_idx) cudaFree(c->move_idx);
+        if (c->move_tmp) cudaFree(c->move_tmp);
         for (auto& s : c->spans) {
             cudaEventDestroy(s.a);
             cudaEventDestroy(s.b);
@@ -1024,6 +1032,7 @@ int32_t recs_gpu_upload(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
     if (col->count)
         RECS_CUDA(c, cudaMemcpyAsync(col->dev, col->host, (size_t)col->elem * col->count, cudaMemcpyHostToDevice,
                                      c->stream));
+    c->h2d_bytes += (uint64_t)col->elem * col->count;
     col->version++;
     c->epoch++;  // a captured tick may have elided the posm re-pack: capture again after new host data
     return RECS_OK;
@@ -1037,7 +1046,95 @@ int32_t recs_gpu_download(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
     if (col->count)
         RECS_CUDA(c, cudaMemcpyAsync(col->host, col->dev, (size_t)col->elem * col->count, cudaMemcpyDeviceToHost,
                                      c->stream));
+    c->d2h_bytes += (uint64_t)col->elem * col->count;
     RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RECS_OK;
+}
+
+// ---- structural changes without a round trip ------------------------------------------------------------------------
+int32_t recs_gpu_archetype_move_rows(recs_gpu_ctx* c, uint32_t arch, const uint64_t* comps, uint32_t n_comps,
+                                     const uint32_t* dst, const uint32_t* src, uint32_t n_moves, uint64_t new_count) {
+    RECS_ENTER(c);
+    if ((n_moves && (!dst || !src)) || (n_comps && !comps))
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "archetype_move_rows: null list");
+    std::vector<Column*> cols;
+    uint32_t max_elem = 0;
+    for (uint32_t i = 0; i < n_comps; ++i) {
+        Column* col = find_column(c, arch, comps[i]);
+        if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "archetype_move_rows: column is not bound");
+        if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "archetype_move_rows: column binding is stale");
+        if (new_count > col->count)
+            return fail(c, RECS_ERR_SIZE_MISMATCH, "archetype_move_rows: new row count exceeds the bound column (append first)");
+        cols.push_back(col);
+        max_elem = std::max(max_elem, col->elem);
+    }
+    if (cols.empty()) return RECS_OK;
+    if (n_moves) {
+        int32_t st = ensure(c, &c->move_idx, &c->move_idx_cap, (size_t)n_moves * 2 * sizeof(uint32_t));
+        if (st != RECS_OK) return st;
+        if ((st = ensure(c, &c->move_tmp, &c->move_tmp_cap, (size_t)n_moves * max_elem)) != RECS_OK) return st;
+        RECS_CUDA(c, cudaMemcpyAsync(c->move_idx, dst, (size_t)n_moves * 4, cudaMemcpyHostToDevice, c->stream));
+        RECS_CUDA(c, cudaMemcpyAsync(c->move_idx + n_moves, src, (size_t)n_moves * 4, cudaMemcpyHostToDevice, c->stream));
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // the lists are pageable host memory
+        c->h2d_bytes += (uint64_t)n_moves * 8;
+    }
+    for (Column* col : cols) {
+        if (n_moves) {
+            RECS_CUDA(c, launch_rows_move(col->dev, col->elem, c->move_idx, c->move_idx + n_moves, n_moves, c->move_tmp, c->stream));
+            c->kernel_launches += 2;
+        }
+        col->count = new_count;
+        col->version++;
+    }
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_column_append(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void* host_ptr, uint64_t new_count) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "column_append: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "column_append: column binding is stale");
+    if (new_count < col->count || (new_count && !host_ptr))
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "column_append: rows can only be added (and need a host pointer)");
+    const size_t old_bytes = (size_t)col->elem * col->count, new_bytes = (size_t)col->elem * new_count;
+    if (new_bytes > col->cap) {
+        size_t cap = 256;
+        while (cap < new_bytes) cap <<= 1;
+        if (cap > new_bytes + (64u << 20)) cap = (new_bytes + (64u << 20) - 1) / (64u << 20) * (64u << 20);
+        void* grown = nullptr;
+        RECS_CUDA(c, cudaMalloc(&grown, cap));
+        if (old_bytes) RECS_CUDA(c, cudaMemcpyAsync(grown, col->dev, old_bytes, cudaMemcpyDeviceToDevice, c->stream));
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+        RECS_CUDA(c, cudaFree(col->dev));
+        col->dev = grown;
+        col->cap = cap;
+    }
+    if (new_bytes > old_bytes) {
+        RECS_CUDA(c, cudaMemcpyAsync((unsigned char*)col->dev + old_bytes, (const unsigned char*)host_ptr + old_bytes,
+                                     new_bytes - old_bytes, cudaMemcpyHostToDevice, c->stream));
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // the host rows may be pageable and short-lived
+        c->h2d_bytes += new_bytes - old_bytes;
+    }
+    col->host = host_ptr;
+    col->count = new_count;
+    col->version++;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_column_rebind_host(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void* host_ptr) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "column_rebind_host: column is not bound");
+    col->host = host_ptr;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_get_transfer_bytes(recs_gpu_ctx* c, uint64_t* out_h2d, uint64_t* out_d2h) {
+    RECS_ENTER(c);
+    if (out_h2d) *out_h2d = c->h2d_bytes;
+    if (out_d2h) *out_d2h = c->d2h_bytes;
     return RECS_OK;
 }
 

@@ -264,22 +264,101 @@ int32_t playback_commands(recs_app* app) {
     app->gpu_removal_sources.clear();
     app->removes.clear();
     if (app->creates.empty() && to_remove.empty()) return RECS_OK;
-    // structural change: the host copy must be current before rows move
-    int32_t st = recs_app_sync_to_host(app);
-    if (st != RECS_OK) return st;
+    // The host World stays the authority on entity ids and row indices; resident device columns follow it WITHOUT a
+    // round trip: appended rows are uploaded alone, swap-removes are replayed on the device as row moves.  A column
+    // whose newest copy is on the device therefore stays there (its host bytes are stale but structurally in step).
+    recs_world* w = app->world;
+    struct Touched {
+        uint64_t version_before = 0;
+        uint64_t len_before = 0;                       // rows before this playback
+        std::unordered_map<uint32_t, uint32_t> origin;  // current row -> row it held after the appends
+        bool removed = false;
+    };
+    std::map<uint32_t, Touched> touched;
+    auto touch = [&](uint32_t arch) -> Touched& {
+        auto it = touched.find(arch);
+        if (it == touched.end()) {
+            Touched t;
+            t.version_before = w->archetypes[arch].version;
+            t.len_before = w->archetypes[arch].entities.size();
+            it = touched.insert(std::make_pair(arch, t)).first;
+        }
+        return it->second;
+    };
+    int32_t st;
+    const uint32_t archetypes_before = (uint32_t)w->archetypes.size();
+    for (uint32_t a = 0; a < archetypes_before; ++a) touch(a);  // cheap: a handful of archetypes
     for (CreateCommand& cmd : app->creates) {
         std::vector<const void*> ptrs(cmd.ids.size());
         for (size_t i = 0; i < cmd.ids.size(); ++i) ptrs[i] = cmd.values[i].empty() ? nullptr : cmd.values[i].data();
-        st = recs_world_create_entity(app->world, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
-        if (st != RECS_OK) return app->fail(st, recs_world_last_error(app->world));
+        st = recs_world_create_entity(w, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
+        if (st != RECS_OK) return app->fail(st, recs_world_last_error(w));
         app->last_created++;
     }
     app->creates.clear();
+    // resident columns of grown archetypes: upload the new rows only
+    std::set<ColKey> resident;  // columns kept in step on the device during this playback
+    if (app->gpu)
+        for (auto& kv : touched) {
+            const uint32_t arch = kv.first;
+            Archetype& a = w->archetypes[arch];
+            for (auto& col : a.columns) {
+                auto mit = app->mirror.find(ColKey(arch, col.first));
+                if (mit == app->mirror.end() || mit->second.bound_version != kv.second.version_before || mit->second.host_dirty)
+                    continue;  // never bound, structurally out of date, or the host copy is the newer one: regular re-bind
+                resident.insert(ColKey(arch, col.first));
+                if (a.entities.size() > kv.second.len_before) {
+                    st = recs_gpu_column_append(app->gpu, arch, col.first, col.second.data.data(), a.entities.size());
+                    if (st != RECS_OK) return gpu_fail(app, st);
+                }
+            }
+        }
     std::set<uint64_t> seen;
     for (recs_entity e : to_remove) {
         if (!seen.insert(entity_key(e)).second) continue;
-        if (recs_world_delete_entity(app->world, e) == RECS_OK) app->last_removed++;
+        uint32_t arch = 0;
+        uint64_t row = 0;
+        if (recs_world_entity_archetype(w, e, &arch) != RECS_OK || recs_world_entity_component_index(w, e, &row) != RECS_OK)
+            continue;  // already gone: the reference logs and ignores removal errors
+        const uint32_t last = (uint32_t)w->archetypes[arch].entities.size() - 1;
+        if (recs_world_delete_entity(w, e) != RECS_OK) continue;
+        app->last_removed++;
+        if (arch >= archetypes_before) continue;  // archetype created in this playback: nothing resident yet
+        Touched& t = touch(arch);
+        t.removed = true;
+        // swap_remove(row): the last row takes its place (crates/ecs/src/archetypes.rs:233-243)
+        auto lit = t.origin.find(last);
+        const uint32_t from = lit == t.origin.end() ? last : lit->second;
+        if (lit != t.origin.end()) t.origin.erase(lit);
+        if ((uint32_t)row != last) t.origin[(uint32_t)row] = from;
     }
+    if (app->gpu)
+        for (auto& kv : touched) {
+            const uint32_t arch = kv.first;
+            Archetype& a = w->archetypes[arch];
+            if (a.version == kv.second.version_before) continue;
+            std::vector<uint64_t> comps;
+            for (auto& col : a.columns)
+                if (resident.count(ColKey(arch, col.first))) comps.push_back(col.first);
+            if (comps.empty()) continue;
+            if (kv.second.removed) {
+                std::vector<uint32_t> dst, src;
+                for (auto& m : kv.second.origin)
+                    if (m.first != m.second) {
+                        dst.push_back(m.first);
+                        src.push_back(m.second);
+                    }
+                st = recs_gpu_archetype_move_rows(app->gpu, arch, comps.data(), (uint32_t)comps.size(), dst.data(), src.data(),
+                                                  (uint32_t)dst.size(), a.entities.size());
+                if (st != RECS_OK) return gpu_fail(app, st);
+            }
+            for (auto& col : a.columns) {
+                if (!resident.count(ColKey(arch, col.first))) continue;
+                if ((st = recs_gpu_column_rebind_host(app->gpu, arch, col.first, col.second.data.data())) != RECS_OK)
+                    return gpu_fail(app, st);
+                app->mirror[ColKey(arch, col.first)].bound_version = a.version;
+            }
+        }
     return RECS_OK;
 }
 

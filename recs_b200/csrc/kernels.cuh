@@ -129,6 +129,10 @@ cudaError_t launch_below_flags(const float* pos, uint32_t n_rows, uint32_t field
 cudaError_t launch_compact_flags(const uint32_t* flags, uint32_t n_rows, uint32_t* out, uint32_t* counter, uint32_t cap,
                                  cudaStream_t s);
 
+// row[dst[k]] = row[src[k]] (sources read before any destination is written); tmp holds n_moves rows
+cudaError_t launch_rows_move(void* col, uint32_t elem, const uint32_t* dst, const uint32_t* src, uint32_t n_moves, void* tmp,
+                             cudaStream_t s);
+
 // ---- measurement ---------------------------------------------------------------------------------
 cudaError_t launch_fp32_peak(int packed, uint32_t iters, uint32_t grid, float* sink,
                              unsigned long long* cycles, cudaStream_t s);

@@ -104,4 +104,45 @@ cudaError_t launch_compact_flags(const uint32_t* flags, uint32_t n_rows, uint32_
     return cudaGetLastError();
 }
 
+// ---- structural changes on resident columns ------------------------------------------------------------------
+// Replay of a batch of swap-removes (crates/ecs/src/archetypes.rs:233-243, 315-328) on a device column:
+// row[dst[k]] = row[src[k]] for all k, every source taken from the column as it was BEFORE the batch.  A row can
+// be the source of one move and the destination of another, hence gather into a scratch buffer, then scatter.
+namespace {
+template <typename W>
+__global__ void __launch_bounds__(256) rows_gather_kernel(const W* __restrict__ col, const uint32_t* __restrict__ src,
+                                                          W* __restrict__ tmp, uint32_t words_per_row, uint64_t total) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t k = i / words_per_row, w = i % words_per_row;
+    tmp[i] = col[static_cast<uint64_t>(src[k]) * words_per_row + w];
+}
+template <typename W>
+__global__ void __launch_bounds__(256) rows_scatter_kernel(W* __restrict__ col, const uint32_t* __restrict__ dst,
+                                                           const W* __restrict__ tmp, uint32_t words_per_row, uint64_t total) {
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= total) return;
+    const uint64_t k = i / words_per_row, w = i % words_per_row;
+    col[static_cast<uint64_t>(dst[k]) * words_per_row + w] = tmp[i];
+}
+}  // namespace
+
+cudaError_t launch_rows_move(void* col, uint32_t elem, const uint32_t* dst, const uint32_t* src, uint32_t n_moves, void* tmp,
+                             cudaStream_t s) {
+    if (n_moves == 0) return cudaSuccess;
+    if (elem % 4 == 0) {
+        const uint32_t wpr = elem / 4;
+        const uint64_t total = static_cast<uint64_t>(n_moves) * wpr;
+        const uint32_t grid = static_cast<uint32_t>((total + 255) / 256);
+        rows_gather_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(col), src, static_cast<uint32_t*>(tmp), wpr, total);
+        rows_scatter_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<uint32_t*>(col), dst, static_cast<const uint32_t*>(tmp), wpr, total);
+    } else {
+        const uint64_t total = static_cast<uint64_t>(n_moves) * elem;
+        const uint32_t grid = static_cast<uint32_t>((total + 255) / 256);
+        rows_gather_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<const uint8_t*>(col), src, static_cast<uint8_t*>(tmp), elem, total);
+        rows_scatter_kernel<uint8_t><<<grid, 256, 0, s>>>(static_cast<uint8_t*>(col), dst, static_cast<const uint8_t*>(tmp), elem, total);
+    }
+    return cudaGetLastError();
+}
+
 }  // namespace recs

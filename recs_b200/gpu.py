@@ -210,6 +210,12 @@ class GpuContext:
         self._check(lib.recs_gpu_get_timing(self._ctx, C.byref(t)), "recs_gpu_get_timing")
         return {name: getattr(t, name) for name, _ in _lib.Timing._fields_}
 
+    def transfer_bytes(self) -> tuple[int, int]:
+        """Component-column bytes copied (host->device, device->host) since the context was created."""
+        h2d, d2h = C.c_uint64(), C.c_uint64()
+        self._check(lib.recs_gpu_get_transfer_bytes(self._ctx, C.byref(h2d), C.byref(d2h)), "recs_gpu_get_transfer_bytes")
+        return int(h2d.value), int(d2h.value)
+
     def reset_timing(self) -> None:
         self._check(lib.recs_gpu_reset_timing(self._ctx), "recs_gpu_reset_timing")
 

@@ -214,6 +214,12 @@ def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle):
         total_removed += len(to_remove)
         assert app.last_playback() == (len(creates), len(to_remove)), tick
 
+    # structural changes did not cost a round trip: the drop columns stayed on the device for all 60 ticks, only the
+    # rows of new drops (12 B velocity + 12 B position each), the swap-remove move lists (8 B per move) and the nine
+    # clouds' columns crossed PCIe, and nothing was downloaded before the final sync
+    h2d, d2h = gpu_ctx.transfer_bytes()
+    assert d2h == 0
+    assert h2d <= total_created * 24 + total_removed * 8 + 9 * 12 * 4, (h2d, total_created, total_removed)
     app.sync_to_host()
     assert len(ticks_seen) == ticks and total_created > 20 and total_removed > 5
     assert w.archetype_count() == len(ow.archetypes) == 3
@@ -225,3 +231,84 @@ def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle):
     assert np.array_equal(w.column(2, POS).view(np.uint32), np.array(d.columns[POS], np.float32).reshape(-1, 3).view(np.uint32))
     assert np.array_equal(w.column(2, VEL).view(np.uint32), np.array(d.columns[VEL], np.float32).reshape(-1, 3).view(np.uint32))
     assert np.array_equal(w.column(1, MASS).view(np.uint32), np.array(ow.archetypes[1].columns[MASS], np.float32).view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------
+# device-resident structural changes under random create / remove batches
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_resident_columns_follow_random_creates_and_removes(gpu_ctx, seed):
+    """Columns written by a GPU system every tick (so their newest copy is always on the device) must follow the
+    host World through batches of Commands::create / Commands::remove without a round trip: appended rows are
+    uploaded alone (recs_gpu_column_append), swap-removes are replayed as row moves
+    (recs_gpu_archetype_move_rows), for 12-byte, 8-byte and 6-byte (byte path) elements.  Oracle: the same
+    operations on the Python World (crates/ecs/src/archetypes.rs:200-243) + the body in numpy."""
+    A, B, SIX = 31, 32, 33
+    six_t = np.dtype((np.uint8, 6))
+    src = ("struct A { float x, y, z; };\nstruct B { unsigned long long k; };\nstruct Six { unsigned char v[6]; };\n"
+           "void bump(A& a, B& b, Six& s) { a.x += 1.0f; a.z -= 0.5f; b.k += 3ull; s.v[0] += 1; s.v[5] += 2; }\n")
+    rng = np.random.default_rng(seed)
+    app = ecs.Application(gpu=gpu_ctx)
+    w = app.world
+    w.register_component(A, F3, "A")
+    w.register_component(B, np.dtype(np.uint64), "B")
+    w.register_component(SIX, six_t, "Six")
+    app.add_gpu_kernel_system("bump", src, "bump", [("write", A), ("write", B), ("write", SIX)], ["A", "B", "Six"])
+    pending = {"creates": [], "removes": []}
+
+    def commands(arch, count, cols):  # a system with only Commands runs once per tick
+        for comps in pending["creates"]:
+            app.command_create(comps)
+        for e in pending["removes"]:
+            app.command_remove(e)
+
+    app.add_cpu_system("commands", [("commands",)], commands)
+    ow = O.World()
+    serial = [0]
+
+    def new_values():
+        serial[0] += 1
+        k = serial[0]
+        return {A: np.array([k, -k, 0.25 * k], np.float32), B: np.uint64(1000 * k), SIX: np.array([k % 200, 1, 2, 3, 4, k % 100], np.uint8)}
+
+    def oracle_create(vals):
+        ow.create_entity({A: tuple(float(x) for x in vals[A]), B: int(vals[B]), SIX: tuple(int(x) for x in vals[SIX])})
+
+    for _ in range(700):  # initial population, created directly
+        vals = new_values()
+        w.create_entity(vals)
+        oracle_create(vals)
+    for tick in range(25):
+        live = list(ow.archetypes[1].entities) if len(ow.archetypes) > 1 else []
+        n_remove = int(rng.integers(0, min(len(live), 120) + 1)) if tick % 5 != 4 else 0
+        victims = [live[i] for i in rng.choice(len(live), size=n_remove, replace=False)] if n_remove else []
+        if victims and tick % 3 == 0:
+            victims += victims[:3]  # duplicates collapse (the reference collects removals into a set)
+        creates = [new_values() for _ in range(int(rng.integers(0, 90)) if tick % 4 != 3 else 0)]
+        pending["creates"] = creates
+        pending["removes"] = [ecs.Entity(e.id, e.generation) for e in victims]
+        app.run(1)
+        # oracle: the body over every row alive during the tick, then playback (creates first, then removes)
+        arch = ow.archetypes[1]
+        arch.columns[A] = [(a[0] + 1.0, a[1], a[2] - 0.5) for a in arch.columns[A]]
+        arch.columns[B] = [b + 3 for b in arch.columns[B]]
+        arch.columns[SIX] = [((s[0] + 1) % 256, s[1], s[2], s[3], s[4], (s[5] + 2) % 256) for s in arch.columns[SIX]]
+        for vals in creates:
+            oracle_create(vals)
+        done = set()
+        for e in victims:
+            if (e.id, e.generation) not in done:
+                done.add((e.id, e.generation))
+                ow.delete_entity(e)
+        assert app.last_playback() == (len(creates), len(done)), tick
+    h2d, d2h = gpu_ctx.transfer_bytes()
+    assert d2h == 0  # nothing came back before the final sync
+    assert h2d <= (700 + serial[0]) * (12 + 8 + 6) + 25 * 120 * 8 + 1024
+    app.sync_to_host()
+    arch = ow.archetypes[1]
+    assert w.archetype_entities(1) == [(e.id, e.generation) for e in arch.entities]
+    n = len(arch.entities)
+    assert np.array_equal(w.column(1, A)[:n], np.array(arch.columns[A], np.float32).reshape(n, 3))
+    assert np.array_equal(w.column(1, B)[:n].reshape(-1), np.array(arch.columns[B], np.uint64))
+    assert np.array_equal(w.column(1, SIX)[:n].reshape(n, 6), np.array(arch.columns[SIX], np.uint8).reshape(n, 6))
+    app.close()
