@@ -528,13 +528,16 @@ int32_t run_rain_vel(recs_gpu_ctx* c, System& sys, bool wind) {
         Column* v;
         int32_t st;
         if ((st = need_column(c, arch, sys.comp[0], 12, &v)) != RECS_OK) return st;
-        if (v->count == 0) continue;
+        // independent rows, no exchange: every rank streams its own contiguous slice
+        uint64_t rb = 0, re = v->count, slice;
+        if (c->cfg.world_size > 1) shard_rows(c->cfg, v->count, &slice, &rb, &re);
+        if (re == rb) continue;
         Timed t(c, T_OTHER);
         if (wind)
-            RECS_CUDA(c, launch_rain_wind((float*)v->dev, v->count, cw * c->wind[0], cw * c->wind[1],
+            RECS_CUDA(c, launch_rain_wind((float*)v->dev + 3 * rb, re - rb, cw * c->wind[0], cw * c->wind[1],
                                           cw * c->wind[2], c->cfg.rain_terminal, c->stream));
         else
-            RECS_CUDA(c, launch_rain_gravity((float*)v->dev, v->count, k_gravity, c->cfg.rain_terminal, c->stream));
+            RECS_CUDA(c, launch_rain_gravity((float*)v->dev + 3 * rb, re - rb, k_gravity, c->cfg.rain_terminal, c->stream));
         c->kernel_launches++;
         v->version++;
     }
@@ -601,6 +604,7 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         if (c->capturing) return fail(c, RECS_ERR_CUDA, "archetype table rebuild during graph capture");
         std::vector<uint32_t> archs;
         std::vector<std::vector<Column*>> cols;
+        std::vector<std::pair<uint64_t, uint64_t>> ranges;
         for (uint32_t a : sys.archs) {
             std::vector<Column*> row(n_params, nullptr);
             int32_t st;
@@ -608,21 +612,26 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
                 if ((st = need_column(c, a, k.comp[p], k.params[p].elem_size, &row[p])) != RECS_OK) return st;
             for (size_t p = 1; p < n_params; ++p)
                 if ((st = same_count(c, row[0], row[p])) != RECS_OK) return st;
-            if (n_params == 0 || row[0]->count == 0) continue;  // empty archetypes take no work items
+            // sharded contexts: every rank runs the body over its own contiguous slice of each archetype
+            uint64_t rb = 0, re = row[0]->count, slice;
+            if (c->cfg.world_size > 1) shard_rows(c->cfg, row[0]->count, &slice, &rb, &re);
+            if (re == rb) continue;  // empty archetypes (or slices) take no work items
             archs.push_back(a);
             cols.push_back(row);
+            ranges.push_back(std::make_pair(rb, re));
         }
         const size_t n_arch = archs.size();
         std::vector<unsigned long long>& t = k.table_host;
         t.assign(2 * n_arch + 1 + n_params * n_arch, 0ull);
         unsigned long long items = 0;
         for (size_t i = 0; i < n_arch; ++i) {
-            const unsigned long long count = cols[i][0]->count;
+            const unsigned long long count = ranges[i].second - ranges[i].first;
             t[i] = items;
             items += k.plan.staged ? (count + k.plan.chunk - 1) / k.plan.chunk : count;
             t[n_arch + 1 + i] = count;
             for (size_t p = 0; p < n_params; ++p)
-                t[2 * n_arch + 1 + p * n_arch + i] = (unsigned long long)(uintptr_t)cols[i][p]->dev;
+                t[2 * n_arch + 1 + p * n_arch + i] =
+                    (unsigned long long)(uintptr_t)((unsigned char*)cols[i][p]->dev + ranges[i].first * k.params[p].elem_size);
         }
         t[n_arch] = items;
         int32_t st = ensure(c, &k.table, &k.table_cap, std::max<size_t>(t.size() * sizeof(unsigned long long), 64));
@@ -681,13 +690,13 @@ int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
         case RECS_SYS_RAIN_WIND:
             return run_rain_vel(c, s, true);
         case RECS_SYS_RAIN_MOVEMENT:
-            return run_axpy(c, s, s.comp[0], s.comp[1], c->cfg.rain_dt, T_OTHER, false);
+            return run_axpy(c, s, s.comp[0], s.comp[1], c->cfg.rain_dt, T_OTHER, true);
         case RECS_SYS_RAIN_WIND_DIRECTION:
             if (c->capturing) return fail(c, RECS_ERR_UNSUPPORTED, "wind_direction inside a captured tick");
             rotate_wind(c);
             return RECS_OK;
         case RECS_SYS_QUERY_ADD:
-            return run_axpy(c, s, s.comp[0], s.comp[1], 1.0f, T_OTHER, false);
+            return run_axpy(c, s, s.comp[0], s.comp[1], 1.0f, T_OTHER, true);
         case RECS_SYS_NBODY_COLLISION:
         case RECS_SYS_RAIN_GROUND_COLLISION:
             return run_removal_system(c, s);
@@ -715,9 +724,11 @@ bool try_fused_rain(recs_gpu_ctx* c, size_t i, int32_t* st) {
         if ((*st = need_column(c, arch, w.comp[0], 12, &v)) != RECS_OK) return true;
         if ((*st = need_column(c, arch, m.comp[0], 12, &p)) != RECS_OK) return true;
         if ((*st = same_count(c, v, p)) != RECS_OK) return true;
-        if (v->count == 0) continue;
+        uint64_t rb = 0, re = v->count, slice;
+        if (c->cfg.world_size > 1) shard_rows(c->cfg, v->count, &slice, &rb, &re);
+        if (re == rb) continue;
         Timed t(c, T_OTHER);
-        cudaError_t e = launch_rain_fused((float*)v->dev, (float*)p->dev, v->count, cw * c->wind[0], cw * c->wind[1],
+        cudaError_t e = launch_rain_fused((float*)v->dev + 3 * rb, (float*)p->dev + 3 * rb, re - rb, cw * c->wind[0], cw * c->wind[1],
                                           cw * c->wind[2], k_gravity, c->cfg.rain_terminal, c->cfg.rain_dt, c->stream);
         if (e != cudaSuccess) {
             *st = fail(c, RECS_ERR_CUDA, cudaGetErrorString(e));

@@ -31,3 +31,19 @@ def test_sharded_ticks_match_oracle(bodies, ticks):
            "--master-port", str(port), "tools/multi_gpu_check.py", str(bodies), str(ticks)]
     proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+
+
+def test_sharded_streaming_systems_need_no_exchange():
+    """Rain tick, simple_iter and a generic system: each rank streams its own contiguous slice of every archetype
+    (independent units, no data-path collective), bit-exact, other rows untouched."""
+    n_gpu = _gpu_count()
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n_gpu < 4 else 4
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), "tools/multi_gpu_stream_check.py", "100003"]
+    proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0 and "MULTI_GPU_STREAM_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
