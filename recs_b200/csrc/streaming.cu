@@ -441,11 +441,8 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
                                                                      k_gravity, terminal, dt);
         } else {
             constexpr int smem = kRainStages * (MODE == 2 ? 2 : 1) * kRainChunkBytes;
-            static bool attr_set = false;
-            if (!attr_set) {
-                cudaFuncSetAttribute(rain_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-                attr_set = true;
-            }
+            // per device and cheap: set on every launch rather than caching it per process
+            cudaFuncSetAttribute(rain_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             static const int ctas_per_sm = getenv("RECS_GPU_RAIN_CTAS") ? atoi(getenv("RECS_GPU_RAIN_CTAS")) : kRainCtasPerSm;
             const uint64_t cap = static_cast<uint64_t>(sms) * ctas_per_sm;
             const uint32_t grid = static_cast<uint32_t>(n_chunks < cap ? n_chunks : cap);
