@@ -5,23 +5,24 @@
 //                     d2 = |to_body|^2, pairs with d2 <= f32::EPSILON contribute zero (this is
 //                     what removes j == i).
 //
-// Design (B200-first, not a translation of the scalar Rust loop):
-//   * FP32-FMA-pipe bound, no tensor cores (not a contraction).  Two j bodies are packed into
-//     one f32x2 register pair so the whole pair interaction is FADD2/FMUL2/FFMA2: 12 FMA-pipe
-//     instructions per TWO interactions instead of 24, which leaves issue slots for the two
-//     MUFU.RSQ, the two FSETP/FSEL (epsilon mask) and the LDS.128 tile reads.
-//   * j tiles live in HBM already pair-interleaved ({x0 x1 y0 y1 | z0 z1 gm0 gm1}, 32 B per
-//     pair), so a tile is one contiguous 4 KiB block: a single elected thread of a producer
-//     warp moves it with a 1-D TMA bulk copy (cp.async.bulk -> UBLKCP) into a 4-stage
-//     shared-memory ring guarded by full/empty mbarriers.  Consumers read tiles with uniform
-//     (broadcast) LDS.128.
-//   * each consumer thread keeps 4 bodies i in registers (register blocking), so one LDS pair
-//     feeds 8 interactions.
-//   * stream-K work split: the (i-block, j-tile) units of a launch are cut into equal
-//     contiguous spans, one per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies
-//     (64 i-blocks) load all 148 SMs as evenly as 1 M bodies do.  A CTA writes one partial
-//     ("fragment") per i-block it touched; a tiny second kernel adds the fragments of each
-//     i-block in ascending j order -- deterministic, no float atomics.
+// Design (B200-first, not a translation of the scalar Rust loop; DESIGN.md 3.1 has the measurements):
+//   * FP32-FMA-pipe bound, no tensor cores (not a contraction).  The whole interaction is packed FP32
+//     (FADD2/FMUL2/FFMA2): 12 FMA-pipe instructions per TWO interactions.  In the default "i-packed" form the
+//     two f32x2 lanes are two bodies i of the thread and body j is a broadcast scalar operand; the older
+//     "j-packed" form (lanes = two bodies j) is kept as an A/B variant.
+//   * the reference's `d2 <= f32::EPSILON => zero` costs no instruction per pair: positions are stored
+//     scaled by 2^-32 (exact), so r^-3 overflows to +inf for every pair the reference masks (and a few
+//     more); one finiteness test per tile sends the thread to an exact masked redo of that tile.
+//   * j tiles live in HBM pair-interleaved ({x0 x1 y0 y1 | z0 z1 gm0 gm1}, 32 B per pair), so a tile is one
+//     contiguous 4 KiB block: a single elected thread of a producer warp moves it with a 1-D TMA bulk copy
+//     (cp.async.bulk -> UBLKCP) into a 4-stage shared-memory ring guarded by full/empty mbarriers.
+//     Consumers read tiles with uniform (broadcast) LDS.128.
+//   * register blocking: 4 bodies i per thread (2 row pairs), so one LDS.128 pair feeds 4 pair-interactions;
+//     a warp owns 128 consecutive rows, i.e. its own bodies sit in one j tile.
+//   * stream-K work split: the (i-block, j-tile) units of a launch are cut into equal contiguous spans, one
+//     per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies load all 148 SMs as evenly as 1 M
+//     bodies do.  A CTA writes one partial ("fragment") per i-block it touched; a second kernel adds the
+//     fragments of each i-block in ascending j order -- deterministic, no float atomics -- and integrates.
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -30,6 +31,12 @@ namespace recs {
 using ptx::f32x2;
 
 namespace {
+
+// Bits of the kernel's ABL template parameter (operation order / detector choice / timing-only ablations).
+constexpr int kAblNoDetector = 1;   // TIMING ONLY: no min-d2 tracking in the unmasked loop
+constexpr int kAblNoMufu = 4;       // TIMING ONLY: d2 stands in for rsqrt(d2)
+constexpr int kAblCubeFirst = 8;    // s = (r^-2 * r^-1) * G*m instead of (G*m * r^-1) * r^-2
+constexpr int kAblOverflow = 16;    // range-shifted data, overflow of r^-3 is the detector (implies cube first)
 
 struct Span {
     uint32_t begin;
@@ -125,7 +132,7 @@ __device__ __forceinline__ void ipair_interaction(const float xj, const float yj
     float d2a, d2b;
     ptx::unpack(d2, d2a, d2b);
     float ra, rb;
-    if (ABL & 4) {  // timing ablation: no MUFU
+    if (ABL & kAblNoMufu) {
         ra = d2a;
         rb = d2b;
     } else {
@@ -135,14 +142,14 @@ __device__ __forceinline__ void ipair_interaction(const float xj, const float yj
     if (MASKED) {
         ra = d2a > eps ? ra : 0.f;
         rb = d2b > eps ? rb : 0.f;
-    } else if (!(ABL & 17)) {
+    } else if (!(ABL & (kAblNoDetector | kAblOverflow))) {
         dmin_a = fminf(dmin_a, d2a);
         dmin_b = fminf(dmin_b, d2b);
     }
     const f32x2 rinv = ptx::pack(ra, rb);
     const f32x2 rinv2 = ptx::mul2(rinv, rinv);
     f32x2 s;
-    if (ABL & 24) {
+    if (ABL & (kAblCubeFirst | kAblOverflow)) {
         // r^-3 first, mass last: on range-shifted data r^-3 overflows for every pair the reference masks, whatever
         // its mass.  (Unshifted, r^-3 is denormal beyond 2e12 m: the exact path keeps the (G*m*r^-1)*r^-2 order.)
         s = ptx::mul2(rinv2, rinv);
@@ -253,7 +260,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                 y = __ldg(p + 1);
                 z = __ldg(p + 2);
             }
-            if ((ABL & 16) != 0) x *= kGravPosScale, y *= kGravPosScale, z *= kGravPosScale;
+            if ((ABL & kAblOverflow) != 0) x *= kGravPosScale, y *= kGravPosScale, z *= kGravPosScale;
             nxi[r] = x;  // kept positive; negated at the use (see pair_interaction)
             nyi[r] = y;
             nzi[r] = z;
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                 nz[q] = ptx::pack(-nzi[2 * q], -nzi[2 * q + 1]);
                 ax[q] = ay[q] = az[q] = 0ull;
             }
-            if constexpr ((ABL & 16) != 0) {
+            if constexpr ((ABL & kAblOverflow) != 0) {
                 // Range-shifted fast path: tile and row positions are stored times 2^-32 (an exact scaling; G*m is
                 // stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
                 // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the tile sums, which come out times 2^64.
@@ -496,25 +503,25 @@ const GravityVariant kVariants[kGravVariantCount] = {
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
-            return nbody_gravity_kernel<4, 1, 8, true, 12, true, 16>;
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow>;
         case 1:
             return nbody_gravity_kernel<2, 1, 8, true, 12>;
         case 2:
             return nbody_gravity_kernel<2, 3, 8, false, 4>;
         case 3:
-            return nbody_gravity_kernel<2, 4, 8, true, 4, true, 16>;
+            return nbody_gravity_kernel<2, 4, 8, true, 4, true, kAblOverflow>;
         case 4:
-            return nbody_gravity_kernel<4, 1, 4, true, 12, true, 8>;
+            return nbody_gravity_kernel<4, 1, 4, true, 12, true, kAblCubeFirst>;
         case 5:
             return nbody_gravity_kernel<4, 1, 4, false, 12, true>;
         case 6:
-            return nbody_gravity_kernel<4, 1, 2, true, 8, true, 16>;
+            return nbody_gravity_kernel<4, 1, 2, true, 8, true, kAblOverflow>;
         case 7:
-            return nbody_gravity_kernel<8, 1, 2, true, 8, true, 16>;
+            return nbody_gravity_kernel<8, 1, 2, true, 8, true, kAblOverflow>;
         case 8:
-            return nbody_gravity_kernel<4, 1, 8, true, 12, true, 16 + 4>;
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow | kAblNoMufu>;
         case 9:
-            return nbody_gravity_kernel<4, 1, 4, true, 12, true, 8 + 1>;
+            return nbody_gravity_kernel<4, 1, 4, true, 12, true, kAblCubeFirst | kAblNoDetector>;
     }
     return nullptr;
 }

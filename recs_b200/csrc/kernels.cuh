@@ -7,7 +7,7 @@
 namespace recs {
 
 // ---- gravity (crates/n-body/src/lib.rs:104-135) ------------------------------------------------
-constexpr int kGravMaxConsumerWarps = 31;                      // consumer warps per CTA are variant dependent (8 or 16)
+constexpr int kGravMaxConsumerWarps = 31;                      // consumer warps per CTA are variant dependent (4, 8 or 12)
 constexpr int kGravMaxRowsPerThread = 8;                       // register blocking over i (variant dependent)
 constexpr int kGravTile = 256;                                 // j bodies per smem tile
 constexpr int kGravStages = 4;
@@ -20,7 +20,7 @@ constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic
 struct GravityVariant {
     int rows_per_thread;  // bodies i per consumer thread
     int min_ctas;         // __launch_bounds__ residency target
-    int consumer_warps;   // 8 or 16 (+ 1 TMA producer warp)
+    int consumer_warps;   // 4, 8 or 12 (+ 1 TMA producer warp)
     bool scaled = false;  // posm is stored range-shifted (kGravPosScale), see gravity.cu
     int consumer_threads() const { return 32 * consumer_warps; }
     int threads() const { return consumer_threads() + 32; }
