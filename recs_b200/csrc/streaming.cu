@@ -431,7 +431,13 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        static const bool staged = getenv("RECS_GPU_RAIN_STAGED") != nullptr;  // A/B knob: the pre-TMA kernel
+        // Which kernel: measured on 4 / 16 / 32 Mi drops (profiles/r01_rain_sizes.txt).  While the columns fit the
+        // 126 MB L2 the TMA pipeline wins (30 vs 35 us at 4 Mi drops); once the tick is HBM-bound the LDG/STS staged
+        // kernel is 3 % ahead (6.15 vs 5.95 TB/s back to back).  RECS_GPU_RAIN_STAGED / RECS_GPU_RAIN_TMA force one.
+        static const bool force_staged = getenv("RECS_GPU_RAIN_STAGED") != nullptr;
+        static const bool force_tma = getenv("RECS_GPU_RAIN_TMA") != nullptr;
+        const uint64_t footprint = n * 12ull * (MODE == 2 ? 2 : 1);
+        const bool staged = force_staged || (!force_tma && footprint > (96ull << 20));
         if (staged) {
             const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
             const uint64_t passes = (n_chunks + cap - 1) / cap;   // same number of chunks for every CTA
