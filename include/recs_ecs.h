@@ -214,6 +214,12 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
                                        const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
                                        const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index);
 int32_t recs_app_set_system_uniform(recs_app* app, uint32_t system_index, const void* data, uint32_t bytes);
+/* The fold behind resident command playback, as a pure function: `rows[i]` is the row index passed to the i-th
+ * `swap_remove` (crates/ecs/src/archetypes.rs:233-243) of a column that had len_before rows.  The result is the
+ * equivalent set of moves "row dst[k] ends up holding what row src[k] held before the batch" (what
+ * recs_gpu_archetype_move_rows applies) and the final length. */
+int32_t recs_fold_swap_removes(uint64_t len_before, const uint32_t* rows, uint32_t n_rows, uint32_t* out_dst,
+                               uint32_t* out_src, uint32_t cap, uint32_t* out_n_moves, uint64_t* out_len_after);
 int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
                                 recs_cpu_system_fn fn, void* user, uint32_t* out_index);
 /* Application::run for `n_ticks` ticks (lib.rs:314-341): schedule generation on first use

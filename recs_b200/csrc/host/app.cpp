@@ -239,6 +239,25 @@ int32_t run_cpu_system(recs_app* app, AppSystem& s) {
     return RECS_OK;
 }
 
+// A batch of `swap_remove(row)` calls (crates/ecs/src/archetypes.rs:233-243) folded into row moves: `origin` maps a
+// current row to the row it held before the batch; rows that were never a target are absent.
+struct SwapRemoveFold {
+    std::unordered_map<uint32_t, uint32_t> origin;
+    void remove(uint32_t row, uint32_t last) {  // `last` = index of the final row at the time of this removal
+        auto lit = origin.find(last);
+        const uint32_t from = lit == origin.end() ? last : lit->second;
+        if (lit != origin.end()) origin.erase(lit);
+        if (row != last) origin[row] = from;
+    }
+    void moves(std::vector<uint32_t>* dst, std::vector<uint32_t>* src) const {
+        for (auto& m : origin)
+            if (m.first != m.second) {
+                dst->push_back(m.first);
+                src->push_back(m.second);
+            }
+    }
+};
+
 // CommandPlayer::playback_commands (crates/ecs/src/systems/command_buffers.rs:377-435): creates, then
 // removes (a set: duplicates collapse; entities that no longer exist are skipped like the reference's
 // logged-and-ignored removal errors).  Removal order here is record order (GPU systems: system order,
@@ -271,7 +290,7 @@ int32_t playback_commands(recs_app* app) {
     struct Touched {
         uint64_t version_before = 0;
         uint64_t len_before = 0;                       // rows before this playback
-        std::unordered_map<uint32_t, uint32_t> origin;  // current row -> row it held after the appends
+        SwapRemoveFold fold;                            // rows as they were after the appends
         bool removed = false;
     };
     std::map<uint32_t, Touched> touched;
@@ -326,11 +345,7 @@ int32_t playback_commands(recs_app* app) {
         if (arch >= archetypes_before) continue;  // archetype created in this playback: nothing resident yet
         Touched& t = touch(arch);
         t.removed = true;
-        // swap_remove(row): the last row takes its place (crates/ecs/src/archetypes.rs:233-243)
-        auto lit = t.origin.find(last);
-        const uint32_t from = lit == t.origin.end() ? last : lit->second;
-        if (lit != t.origin.end()) t.origin.erase(lit);
-        if ((uint32_t)row != last) t.origin[(uint32_t)row] = from;
+        t.fold.remove((uint32_t)row, last);
     }
     if (app->gpu)
         for (auto& kv : touched) {
@@ -343,11 +358,7 @@ int32_t playback_commands(recs_app* app) {
             if (comps.empty()) continue;
             if (kv.second.removed) {
                 std::vector<uint32_t> dst, src;
-                for (auto& m : kv.second.origin)
-                    if (m.first != m.second) {
-                        dst.push_back(m.first);
-                        src.push_back(m.second);
-                    }
+                kv.second.fold.moves(&dst, &src);
                 st = recs_gpu_archetype_move_rows(app->gpu, arch, comps.data(), (uint32_t)comps.size(), dst.data(), src.data(),
                                                   (uint32_t)dst.size(), a.entities.size());
                 if (st != RECS_OK) return gpu_fail(app, st);
@@ -465,6 +476,27 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
     params_accesses(s.params, &s.access);
     app->systems.push_back(s);
     if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
+    return RECS_OK;
+}
+
+int32_t recs_fold_swap_removes(uint64_t len_before, const uint32_t* rows, uint32_t n_rows, uint32_t* out_dst,
+                               uint32_t* out_src, uint32_t cap, uint32_t* out_n_moves, uint64_t* out_len_after) {
+    if ((n_rows && !rows) || !out_n_moves) return RECS_ERR_INVALID_ARGUMENT;
+    SwapRemoveFold fold;
+    uint64_t len = len_before;
+    for (uint32_t i = 0; i < n_rows; ++i) {
+        if (len == 0 || rows[i] >= len) return RECS_ERR_INVALID_ARGUMENT;
+        fold.remove(rows[i], (uint32_t)(len - 1));
+        --len;
+    }
+    std::vector<uint32_t> dst, src;
+    fold.moves(&dst, &src);
+    *out_n_moves = (uint32_t)dst.size();
+    if (out_len_after) *out_len_after = len;
+    for (uint32_t i = 0; i < dst.size() && i < cap; ++i) {
+        if (out_dst) out_dst[i] = dst[i];
+        if (out_src) out_src[i] = src[i];
+    }
     return RECS_OK;
 }
 

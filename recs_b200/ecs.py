@@ -94,6 +94,7 @@ ECS_SYMBOLS = {
         [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32, _u32p],
     ),
     "recs_app_set_system_uniform": (C.c_int32, [_a, C.c_uint32, C.c_void_p, C.c_uint32]),
+    "recs_fold_swap_removes": (C.c_int32, [C.c_uint64, _u32p, C.c_uint32, _u32p, _u32p, C.c_uint32, _u32p, C.POINTER(C.c_uint64)]),
     "recs_app_add_cpu_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SYSTEM_FN, C.c_void_p, _u32p]),
     "recs_app_run": (C.c_int32, [_a, C.c_uint32, C.c_int32]),
     "recs_app_command_create": (C.c_int32, [_a, _u64p, _vpp, C.c_uint32]),
@@ -537,3 +538,15 @@ class Application:
 
     def mark_host_dirty(self, archetype: int) -> None:
         self._check(lib.recs_app_mark_host_dirty(self._h, archetype), "recs_app_mark_host_dirty")
+
+
+def fold_swap_removes(len_before: int, rows: Sequence[int]):
+    """recs_fold_swap_removes: (dst, src, len_after) equivalent to swap_remove(rows[0]), swap_remove(rows[1]), ..."""
+    n = len(rows)
+    arr = (C.c_uint32 * max(n, 1))(*rows)
+    dst, src = (C.c_uint32 * max(n, 1))(), (C.c_uint32 * max(n, 1))()
+    n_moves, len_after = C.c_uint32(), C.c_uint64()
+    code = lib.recs_fold_swap_removes(len_before, arr, n, dst, src, max(n, 1), C.byref(n_moves), C.byref(len_after))
+    if code:
+        raise EcsError(code, "recs_fold_swap_removes")
+    return [int(dst[i]) for i in range(n_moves.value)], [int(src[i]) for i in range(n_moves.value)], int(len_after.value)

@@ -312,3 +312,39 @@ def test_resident_columns_follow_random_creates_and_removes(gpu_ctx, seed):
     assert np.array_equal(w.column(1, B)[:n].reshape(-1), np.array(arch.columns[B], np.uint64))
     assert np.array_equal(w.column(1, SIX)[:n].reshape(n, 6), np.array(arch.columns[SIX], np.uint8).reshape(n, 6))
     app.close()
+
+
+def test_resident_column_primitives_report_misuse(gpu_ctx):
+    """recs_gpu_column_append / recs_gpu_archetype_move_rows: status codes for unbound columns, shrinking appends and
+    moves that would need rows which were never appended; a correct call sequence is checked against numpy."""
+    import ctypes as C
+
+    from recs_b200 import RecsGpuError
+    from recs_b200._lib import lib
+
+    ctx = gpu_ctx
+    COMP, ARCH = 5, 3
+    store = np.arange(40, dtype=np.float32).reshape(10, 4)  # capacity 10 rows of 16 B
+    st = lib.recs_gpu_column_append(ctx._ctx, ARCH, COMP, store.ctypes.data_as(C.c_void_p), 4)
+    assert st == 5  # RECS_ERR_MISSING_PARAMETER: not bound
+    ctx.clear_error()
+    ctx.bind_column(ARCH, COMP, store[:6])
+    ctx.upload(ARCH, COMP)
+    assert lib.recs_gpu_column_append(ctx._ctx, ARCH, COMP, store.ctypes.data_as(C.c_void_p), 5) == 1  # rows can only be added
+    ctx.clear_error()
+    comps = (C.c_uint64 * 1)(COMP)
+    dst, src = (C.c_uint32 * 2)(0, 3), (C.c_uint32 * 2)(7, 6)
+    assert lib.recs_gpu_archetype_move_rows(ctx._ctx, ARCH, comps, 1, dst, src, 2, 8) == 7  # RECS_ERR_SIZE_MISMATCH: append first
+    ctx.clear_error()
+    # append rows 6..7, then fold of swap_remove(0), swap_remove(3): row 0 <- row 7, row 3 <- row 6, 6 rows remain
+    assert lib.recs_gpu_column_append(ctx._ctx, ARCH, COMP, store.ctypes.data_as(C.c_void_p), 8) == 0
+    assert lib.recs_gpu_archetype_move_rows(ctx._ctx, ARCH, comps, 1, dst, src, 2, 6) == 0
+    want = store[:8].copy()
+    want[0], want[3] = store[7], store[6]
+    out = np.zeros((6, 4), np.float32)
+    assert lib.recs_gpu_column_rebind_host(ctx._ctx, ARCH, COMP, out.ctypes.data_as(C.c_void_p)) == 0
+    ctx.download(ARCH, COMP)
+    assert np.array_equal(out, want[:6])
+    with pytest.raises(RecsGpuError):
+        ctx._check(lib.recs_gpu_column_rebind_host(ctx._ctx, ARCH, 99, None), "rebind")
+    ctx.clear_error()

@@ -430,3 +430,41 @@ def test_random_operations_host_matches_oracle(ops):
         assert o.entity_component_index(x) == h.entity_component_index(y)
     for sig in ([], [U32], [U32, I32], [F32, I64, USIZE]):
         assert o.get_archetype_indices(sig) == h.get_archetype_indices(sig)
+
+
+# ---- resident command playback: swap-removes folded into row moves ---------------------------------------------------
+@settings(max_examples=200, deadline=None)
+@given(st.data())
+def test_fold_swap_removes_equals_sequential_swap_removes(data):
+    """recs_fold_swap_removes (what recs_app replays on device columns through recs_gpu_archetype_move_rows) against
+    `Vec::swap_remove` applied one call at a time (crates/ecs/src/archetypes.rs:233-243)."""
+    from recs_b200.ecs import fold_swap_removes
+
+    n = data.draw(st.integers(min_value=1, max_value=60))
+    column = list(range(100, 100 + n))
+    rows = []
+    cur = list(column)
+    for _ in range(data.draw(st.integers(min_value=0, max_value=n))):
+        r = data.draw(st.integers(min_value=0, max_value=len(cur) - 1))
+        rows.append(r)
+        cur[r] = cur[-1]  # swap_remove
+        cur.pop()
+    dst, src, len_after = fold_swap_removes(n, rows)
+    assert len_after == len(cur)
+    assert len(set(dst)) == len(dst) and all(d < len_after for d in dst)
+    assert len(dst) <= len(rows)
+    got = list(column)
+    moved = {d: column[s] for d, s in zip(dst, src)}  # every source is read before any destination is written
+    for d, v in moved.items():
+        got[d] = v
+    assert got[:len_after] == cur
+
+
+def test_fold_swap_removes_rejects_rows_out_of_range():
+    from recs_b200.ecs import EcsError, fold_swap_removes
+
+    with pytest.raises(EcsError):
+        fold_swap_removes(3, [3])
+    with pytest.raises(EcsError):
+        fold_swap_removes(1, [0, 0])
+    assert fold_swap_removes(4, [3, 2]) == ([], [], 2)  # removing from the end moves nothing
