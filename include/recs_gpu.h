@@ -105,6 +105,13 @@ int32_t recs_gpu_bind_column(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64
  * returns). */
 int32_t recs_gpu_upload(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id);
 int32_t recs_gpu_download(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id);
+/* The same for rows [row_begin, row_end) only.  In an index-sharded run a rank owns the rows
+ * recs_gpu_shard_rows returns: it needs no other row of Velocity / Acceleration at all, and the other ranks'
+ * positions and masses reach it through the all-gather, not through its host. */
+int32_t recs_gpu_upload_rows(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id,
+                             uint64_t row_begin, uint64_t row_end);
+int32_t recs_gpu_download_rows(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id,
+                               uint64_t row_begin, uint64_t row_end);
 /* Structural change happened on the host (command-buffer playback,
  * crates/ecs/src/lib.rs:321-323): all bindings of that archetype become stale. */
 int32_t recs_gpu_invalidate(recs_gpu_ctx* ctx, uint32_t archetype_index);

@@ -113,6 +113,8 @@ GPU_SYMBOLS = {
     "recs_gpu_bind_column": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint64]),
     "recs_gpu_upload": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64]),
     "recs_gpu_download": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64]),
+    "recs_gpu_upload_rows": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "recs_gpu_download_rows": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_uint64, C.c_uint64]),
     "recs_gpu_column_append": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64, C.c_void_p, C.c_uint64]),
     "recs_gpu_archetype_move_rows": (
         C.c_int32,

@@ -1049,6 +1049,38 @@ int32_t recs_gpu_upload(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
     return RECS_OK;
 }
 
+// Rows [row_begin, row_end) only: what a rank of an index-sharded run owns (recs_gpu_shard_rows).
+int32_t recs_gpu_upload_rows(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, uint64_t row_begin, uint64_t row_end) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "upload_rows: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "upload_rows: column binding is stale");
+    if (row_begin > row_end || row_end > col->count) return fail(c, RECS_ERR_INVALID_ARGUMENT, "upload_rows: row range outside the column");
+    const size_t off = (size_t)col->elem * row_begin, bytes = (size_t)col->elem * (row_end - row_begin);
+    if (bytes)
+        RECS_CUDA(c, cudaMemcpyAsync((unsigned char*)col->dev + off, (const unsigned char*)col->host + off, bytes,
+                                     cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += bytes;
+    col->version++;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_download_rows(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, uint64_t row_begin, uint64_t row_end) {
+    RECS_ENTER(c);
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "download_rows: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "download_rows: column binding is stale");
+    if (row_begin > row_end || row_end > col->count) return fail(c, RECS_ERR_INVALID_ARGUMENT, "download_rows: row range outside the column");
+    const size_t off = (size_t)col->elem * row_begin, bytes = (size_t)col->elem * (row_end - row_begin);
+    if (bytes)
+        RECS_CUDA(c, cudaMemcpyAsync((unsigned char*)col->host + off, (const unsigned char*)col->dev + off, bytes,
+                                     cudaMemcpyDeviceToHost, c->stream));
+    c->d2h_bytes += bytes;
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    return RECS_OK;
+}
+
 int32_t recs_gpu_download(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
     RECS_ENTER(c);
     Column* col = find_column(c, arch, comp);

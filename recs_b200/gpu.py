@@ -99,6 +99,12 @@ class GpuContext:
     def upload(self, archetype: int, component: int) -> None:
         self._check(lib.recs_gpu_upload(self._ctx, archetype, component), "recs_gpu_upload")
 
+    def upload_rows(self, archetype: int, component: int, row_begin: int, row_end: int) -> None:
+        self._check(lib.recs_gpu_upload_rows(self._ctx, archetype, component, row_begin, row_end), "recs_gpu_upload_rows")
+
+    def download_rows(self, archetype: int, component: int, row_begin: int, row_end: int) -> None:
+        self._check(lib.recs_gpu_download_rows(self._ctx, archetype, component, row_begin, row_end), "recs_gpu_download_rows")
+
     def download(self, archetype: int, component: int) -> np.ndarray:
         self._check(lib.recs_gpu_download(self._ctx, archetype, component), "recs_gpu_download")
         return self._bound[(archetype, component)]

@@ -42,13 +42,20 @@ class NBodyGpuApp:
         self.tick_order = tuple(names)
         self.ctx.set_tick_order([self.systems[name] for name in names])
 
-    def upload(self) -> None:
+    def upload(self, rows=None) -> None:
+        """All four columns host -> device; `rows=(begin, end)` moves only that row range (a rank's own shard)."""
         for comp in (POSITION, MASS, VELOCITY, ACCELERATION):
-            self.ctx.upload(BODY_ARCHETYPE, comp)
+            if rows is None:
+                self.ctx.upload(BODY_ARCHETYPE, comp)
+            else:
+                self.ctx.upload_rows(BODY_ARCHETYPE, comp, rows[0], rows[1])
 
-    def download(self, comps=(POSITION, VELOCITY, ACCELERATION)) -> None:
+    def download(self, comps=(POSITION, VELOCITY, ACCELERATION), rows=None) -> None:
         for comp in comps:
-            self.ctx.download(BODY_ARCHETYPE, comp)
+            if rows is None:
+                self.ctx.download(BODY_ARCHETYPE, comp)
+            else:
+                self.ctx.download_rows(BODY_ARCHETYPE, comp, rows[0], rows[1])
 
     def run(self, name: str, sync: bool = True) -> None:
         self.ctx.run_system(self.systems[name], sync=sync)

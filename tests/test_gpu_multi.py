@@ -18,8 +18,10 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("bodies,ticks", [(10000, 1), (5000, 4), (300, 2)])
-def test_sharded_ticks_match_oracle(bodies, ticks):
+@pytest.mark.parametrize("bodies,ticks,mode", [(10000, 1, "full"), (5000, 4, "full"), (300, 2, "full"), (7000, 3, "own")])
+def test_sharded_ticks_match_oracle(bodies, ticks, mode):
+    """mode "own": every rank uploads / downloads only the rows it owns (recs_gpu_upload_rows) and its host copy of
+    every other row is NaN -- nothing outside the shard may be read from the host."""
     n_gpu = _gpu_count()
     if n_gpu < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -28,7 +30,7 @@ def test_sharded_ticks_match_oracle(bodies, ticks):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), "tools/multi_gpu_check.py", str(bodies), str(ticks)]
+           "--master-port", str(port), "tools/multi_gpu_check.py", str(bodies), str(ticks), mode]
     proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
 

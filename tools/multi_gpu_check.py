@@ -17,6 +17,7 @@ from recs_b200.nbody import NBodyGpuApp  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+own_rows_only = len(sys.argv) > 3 and sys.argv[3] == "own"  # every rank's host holds (and moves) only its own rows
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dist.init_process_group("gloo")
 ctx = GpuContext(device=local, rank=rank, world_size=world, use_cuda_graph=False)
@@ -26,10 +27,14 @@ ctx.comm_init(uid[0])
 rb, re = ctx.shard_rows(n)
 pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 5)
 ref = [a.copy() for a in (pos, mass, vel, acc)]
+if own_rows_only:  # poison what this rank does not own: it must never be read
+    for a in (pos, mass, vel, acc):
+        a[:rb] = np.nan
+        a[re:] = np.nan
 app = NBodyGpuApp(ctx, pos, mass, vel, acc)
-app.upload()
+app.upload(rows=(rb, re) if own_rows_only else None)
 app.tick(ticks)
-app.download()
+app.download(rows=(rb, re) if own_rows_only else None)
 ctx.synchronize()
 orc = oracle.load_nbody()
 orc.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks)
@@ -54,7 +59,8 @@ dist.all_gather_object(results, (rank, rb, re, errs, bool(ok)))
 if rank == 0:
     for r in results:
         print(r)
-    print("MULTI_GPU_CHECK", "OK" if all(r[4] for r in results) else "FAILED", f"bodies={n} ticks={ticks} world={world}")
+    print("MULTI_GPU_CHECK", "OK" if all(r[4] for r in results) else "FAILED",
+          f"bodies={n} ticks={ticks} world={world} own_rows_only={own_rows_only}")
 ctx.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
