@@ -366,3 +366,21 @@ def test_range_extremes(monkeypatch, nbody_oracle, variant, name, pos_scale, mas
     err64 = rel_err_rows(app.acc, ref64, floor=floor)
     ok = (err32 <= ACC_TOL) | (err64 <= ACC_TOL)
     assert ok.all(), f"{name}: {np.count_nonzero(~ok)} rows off, worst {np.minimum(err32, err64).max():.3e}"
+
+
+@pytest.mark.parametrize("n,ticks", [(16384, 100), (65536, 10)])
+def test_drift_bound_at_larger_sizes(nbody_oracle, n, ticks):
+    """SURVEY 8d drift gate beyond configs[0]: after `ticks` full ticks, max_i |p_gpu - p_ref| / max(|p_ref|, 1 m) <= 1e-4
+    and the same for velocity, against the oracle run with the reference's worker-pool policy on all host threads
+    (sizes chosen so that the CPU side stays within seconds)."""
+    import os
+
+    from recs_b200 import GpuContext
+
+    with GpuContext(device=0) as ctx:
+        app, (pos, mass, vel, acc) = _app(ctx, n, seed=8)
+        app.tick(ticks)
+        app.download()
+    nbody_oracle.run_pool(pos, mass, vel, acc, ticks, max(os.cpu_count() or 1, 1))
+    assert rel_err_rows(app.pos, pos, floor=1.0).max() <= 1e-4
+    assert rel_err_rows(app.vel, vel, floor=1.0).max() <= 1e-4
