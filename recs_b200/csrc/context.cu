@@ -51,6 +51,7 @@ struct KernelSys {
     uint64_t table_epoch = ~0ull;
     uint64_t n_items = 0;
     uint32_t n_arch = 0;
+    uint64_t footprint_bytes = 0;          // bytes of all columns one launch touches
     ~KernelSys() {
         if (table) cudaFree(table);
         if (lib) cudaLibraryUnload(lib);
@@ -634,6 +635,9 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
                     (unsigned long long)(uintptr_t)((unsigned char*)cols[i][p]->dev + ranges[i].first * k.params[p].elem_size);
         }
         t[n_arch] = items;
+        k.footprint_bytes = 0;
+        for (size_t i = 0; i < n_arch; ++i)
+            for (size_t p = 0; p < n_params; ++p) k.footprint_bytes += (ranges[i].second - ranges[i].first) * k.params[p].elem_size;
         int32_t st = ensure(c, &k.table, &k.table_cap, std::max<size_t>(t.size() * sizeof(unsigned long long), 64));
         if (st != RECS_OK) return st;
         RECS_CUDA(c, cudaMemcpyAsync(k.table, t.data(), t.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
@@ -648,7 +652,13 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
     // grid-stride CTAs for the direct form
     uint64_t ctas, cap;
     if (k.plan.staged) {
-        const uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(3, (227u * 1024u) / (k.plan.smem_bytes + 2048u)));
+        // Persistent CTAs per SM: three while the touched columns fit L2, ONE once the launch is HBM-bound -- fewer
+        // concurrent chunk streams keep DRAM pages open (simple_iter 10 M entities: 6.25 TB/s with one CTA per SM,
+        // 6.09 with two, 5.96 with three; profiles/r01_generic_systems.txt).
+        static const int forced = getenv("RECS_GPU_KERNEL_CTAS") ? atoi(getenv("RECS_GPU_KERNEL_CTAS")) : 0;  // tuning knob
+        uint64_t per_sm = std::max<uint64_t>(1, std::min<uint64_t>(3, (227u * 1024u) / (k.plan.smem_bytes + 2048u)));
+        if (k.footprint_bytes > kStreamL2Footprint) per_sm = 1;
+        if (forced > 0) per_sm = std::min<uint64_t>(per_sm, (uint64_t)forced);
         ctas = k.n_items;
         cap = (uint64_t)c->sm_count * per_sm;
     } else {

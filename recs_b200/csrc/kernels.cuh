@@ -98,6 +98,10 @@ cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float
 // Null bodies (gm = 0) for [begin, end) so partially filled tiles contribute nothing.
 cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s);
 
+// Above this many bytes touched per launch a streaming kernel is HBM-bound (the L2 is 126 MB); below it, its
+// columns stay L2-resident from one tick to the next.  Measured kernel choices hang on it (streaming.cu, context.cu).
+constexpr uint64_t kStreamL2Footprint = 96ull << 20;
+
 // ---- streaming systems ---------------------------------------------------------------------------
 // y[k] = y[k] + x[k] * a for k in [0, n): separate IEEE mul and add (no FMA contraction), the
 // arithmetic of `position.point += velocity * FIXED_TIME_STEP` (crates/n-body/src/lib.rs:92),

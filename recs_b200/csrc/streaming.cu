@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kStreamThreads)
 // Loads of chunks k+1 and k+2 and the store of chunk k-1 are in flight while chunk k is computed, with no
 // __syncthreads and no register staging; 72 KiB of shared memory per CTA, two CTAs per SM.
 constexpr int kRainStages = 3;
-constexpr int kRainCtasPerSm = 3;  // 1: 32.8 us, 2: 31.7 us, 3: 30.7 us per fused tick of 4 Mi drops
+constexpr int kRainCtasPerSm = 3;  // L2-resident sizes: 1: 32.8 us, 2: 31.7 us, 3: 30.7 us per fused tick of 4 Mi drops
 constexpr int kRainChunkBytes = kRainChunkVec * 16;  // 12 KiB per column per chunk
 template <int MODE>
 __global__ void __launch_bounds__(kStreamThreads + 64)
@@ -400,13 +400,15 @@ cudaError_t launch_axpy_rn(float* y, const float* x, float a, uint64_t n, cudaSt
     if (head) axpy_rn_scalar_kernel<<<1, 32, 0, s>>>(y, x, a, head);
     const uint64_t n4 = (n - head) / 4;
     if (n4) {
+        // (a TMA-pipelined version of this kernel was measured and dropped: 60.4 us with one CTA per SM, 63.8 with
+        // three, against 57.6 us for this LDG/STG kernel on 10 M entities; profiles/r01_rain_sizes.txt)
         const uint32_t grid = stream_grid(n4, kStreamThreads * kStreamUnroll);
         axpy_rn_vec_kernel<<<grid, kStreamThreads, 0, s>>>(reinterpret_cast<float4*>(y + head),
                                                           reinterpret_cast<const float4*>(x + head), a,
                                                           n4);
     }
     const uint64_t tail = n - head - 4 * n4;
-    if (tail) axpy_rn_scalar_kernel<<<1, 32, 0, s>>>(y + head + 4 * n4, x + head + 4 * n4, a, tail);
+    if (tail) axpy_rn_scalar_kernel<<<1, 32, 0, s>>>(y + (n - tail), x + (n - tail), a, tail);
     return cudaGetLastError();
 }
 
@@ -431,13 +433,12 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        // Which kernel: measured on 4 / 16 / 32 Mi drops (profiles/r01_rain_sizes.txt).  While the columns fit the
-        // 126 MB L2 the TMA pipeline wins (30 vs 35 us at 4 Mi drops); once the tick is HBM-bound the LDG/STS staged
-        // kernel is 3 % ahead (6.15 vs 5.95 TB/s back to back).  RECS_GPU_RAIN_STAGED / RECS_GPU_RAIN_TMA force one.
-        static const bool force_staged = getenv("RECS_GPU_RAIN_STAGED") != nullptr;
-        static const bool force_tma = getenv("RECS_GPU_RAIN_TMA") != nullptr;
+        // Measured on 4 / 16 / 32 Mi drops (profiles/r01_rain_sizes.txt): the TMA pipeline with three persistent CTAs
+        // per SM while the columns fit L2 (30 vs 35 us at 4 Mi drops), with ONE CTA per SM once the tick is HBM-bound
+        // (6.5-6.6 TB/s back to back at 16-32 Mi drops against 5.9 with three CTAs and 6.15 for the LDG/STS staged
+        // kernel): fewer concurrent chunk streams keep DRAM pages open.  RECS_GPU_RAIN_STAGED forces the staged kernel.
+        static const bool staged = getenv("RECS_GPU_RAIN_STAGED") != nullptr;
         const uint64_t footprint = n * 12ull * (MODE == 2 ? 2 : 1);
-        const bool staged = force_staged || (!force_tma && footprint > (96ull << 20));
         if (staged) {
             const uint64_t cap = static_cast<uint64_t>(sms) * 8;  // resident CTAs: 8 x 256 threads per SM
             const uint64_t passes = (n_chunks + cap - 1) / cap;   // same number of chunks for every CTA
@@ -449,7 +450,8 @@ cudaError_t launch_rain_impl(float* vel, float* pos, uint64_t n, float wx, float
             constexpr int smem = kRainStages * (MODE == 2 ? 2 : 1) * kRainChunkBytes;
             // per device and cheap: set on every launch rather than caching it per process
             cudaFuncSetAttribute(rain_tma_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            static const int ctas_per_sm = getenv("RECS_GPU_RAIN_CTAS") ? atoi(getenv("RECS_GPU_RAIN_CTAS")) : kRainCtasPerSm;
+            static const int forced_ctas = getenv("RECS_GPU_RAIN_CTAS") ? atoi(getenv("RECS_GPU_RAIN_CTAS")) : 0;
+            const int ctas_per_sm = forced_ctas > 0 ? forced_ctas : (footprint > kStreamL2Footprint ? 1 : kRainCtasPerSm);
             const uint64_t cap = static_cast<uint64_t>(sms) * ctas_per_sm;
             const uint32_t grid = static_cast<uint32_t>(n_chunks < cap ? n_chunks : cap);
             rain_tma_kernel<MODE><<<grid, kStreamThreads + 64, smem, s>>>(reinterpret_cast<float4*>(vel),
