@@ -379,7 +379,8 @@ inline uint32_t stream_grid(uint64_t work_items, uint32_t per_block) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint64_t chunks = (work_items + per_block - 1) / per_block;
-    const uint64_t cap = static_cast<uint64_t>(sms) * 8 * 2;  // 8 resident CTAs of 256 threads x 2 waves
+    static const int cap_per_sm = getenv("RECS_GPU_STREAM_CTAS") ? atoi(getenv("RECS_GPU_STREAM_CTAS")) : 16;  // tuning knob
+    const uint64_t cap = static_cast<uint64_t>(sms) * cap_per_sm;  // default: 8 resident CTAs of 256 threads x 2 waves
     if (chunks <= cap) return static_cast<uint32_t>(chunks ? chunks : 1);
     const uint64_t passes = (chunks + cap - 1) / cap;
     return static_cast<uint32_t>((chunks + passes - 1) / passes);
