@@ -199,6 +199,15 @@ typedef struct recs_app recs_app;
 typedef void (*recs_cpu_system_fn)(void* user, uint32_t archetype, uint64_t count, void* const* columns,
                                    uint32_t n_columns);
 
+/* The par-iter form of a CPU system body (`SegmentIterable`, crates/ecs/src/systems/iteration.rs:151-245): called for
+ * rows [row_begin, row_begin + row_count) of one archetype; `columns` are the archetype's column BASE pointers in
+ * parameter order.  Under the Sequential executor it is called once per matched archetype with all rows; under the
+ * WorkerPool executor the concatenation of the matched archetypes is cut into segments of SegmentSize::Auto =
+ * max(16, N / (threads * 4)) entities (systems/mod.rs:394-411, 473-540), one task each, calls may come from any
+ * worker thread concurrently (for disjoint row ranges). */
+typedef void (*recs_cpu_segment_fn)(void* user, uint32_t archetype, uint64_t row_begin, uint64_t row_count,
+                                    void* const* columns, uint32_t n_columns);
+
 int32_t recs_app_create(recs_gpu_ctx* gpu /* may be NULL: CPU systems only */, recs_app** out_app);
 int32_t recs_app_destroy(recs_app* app);
 const char* recs_app_last_error(recs_app* app);
@@ -222,6 +231,12 @@ int32_t recs_fold_swap_removes(uint64_t len_before, const uint32_t* rows, uint32
                                uint32_t* out_src, uint32_t cap, uint32_t* out_n_moves, uint64_t* out_len_after);
 int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
                                 recs_cpu_system_fn fn, void* user, uint32_t* out_index);
+int32_t recs_app_add_cpu_segment_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
+                                        recs_cpu_segment_fn fn, void* user, uint32_t* out_index);
+/* Executor of recs_app_run: 0 = `Sequential` (lib.rs:439-465, the default), n > 0 = `WorkerPool` with n worker
+ * threads (crates/scheduler/src/executor/mod.rs:101-291): the CPU systems of a schedule batch run concurrently, par-iter
+ * systems as segment tasks; GPU systems stay single tasks on the context stream. */
+int32_t recs_app_set_executor(recs_app* app, uint32_t worker_threads);
 /* Application::run for `n_ticks` ticks (lib.rs:314-341): schedule generation on first use
  * (into_tickable, :386-400), then per tick execute_once + playback (structural commands are
  * applied by the caller between calls).  ordered != 0 selects OrderedPrecedenceGraph. */

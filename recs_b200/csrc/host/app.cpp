@@ -14,8 +14,14 @@
 //     downloaded before a CPU system touches a column the device wrote.
 #include <string.h>
 
+#include <condition_variable>
+#include <deque>
+#include <functional>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <set>
+#include <thread>
 
 #include "host.h"
 
@@ -31,7 +37,64 @@ struct AppSystem {
     std::vector<Param> params;
     std::vector<recs_gpu_access> access;
     recs_cpu_system_fn fn = nullptr;
+    recs_cpu_segment_fn segment_fn = nullptr;  // par-iter form: may be cut into segments (SegmentIterable)
     void* user = nullptr;
+};
+
+// `WorkerPool` (crates/scheduler/src/executor/mod.rs:101-188, worker.rs:141-168) reduced to what the executor
+// contract needs: N worker threads draining one shared injector queue of tasks; the dispatching thread blocks
+// until the tasks of the current batch are done (the reference blocks on the systems' finished-channels).
+class WorkerPool {
+  public:
+    explicit WorkerPool(uint32_t n) {
+        for (uint32_t i = 0; i < n; ++i) workers_.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();  // Drop for WorkerPool joins its threads (executor/mod.rs:84-99)
+    }
+    uint32_t size() const { return (uint32_t)workers_.size(); }
+    void submit(std::function<void()> task) {
+        {
+            std::lock_guard<std::mutex> lock(mu_);
+            queue_.push_back(std::move(task));
+            ++pending_;
+        }
+        cv_.notify_one();
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lock(mu_);
+        done_cv_.wait(lock, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void loop() {
+        for (;;) {
+            std::function<void()> task;
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                cv_.wait(lock, [this] { return stop_ || !queue_.empty(); });
+                if (queue_.empty()) return;
+                task = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            task();
+            {
+                std::lock_guard<std::mutex> lock(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::deque<std::function<void()>> queue_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    uint64_t pending_ = 0;
+    bool stop_ = false;
 };
 
 struct Mirror {
@@ -102,6 +165,8 @@ struct recs_app {
         uint64_t version = ~0ull;
     };
     std::map<uint32_t, EntityColumn> entity_columns;
+    std::unique_ptr<WorkerPool> pool;  // null: Sequential executor
+    std::mutex command_mu;             // Commands may be recorded from several worker threads at once
     std::string error;
 
     int32_t fail(int32_t code, const std::string& msg) {
@@ -198,18 +263,31 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
     return RECS_OK;
 }
 
-// `SequentiallyIterable::run` for a CPU system (crates/ecs/src/systems/iteration.rs:26-57).
-int32_t run_cpu_system(recs_app* app, AppSystem& s) {
-    if (!params_controls_iteration(s.params)) {
-        // no iterating parameter: the function runs exactly once (iterate_once, iteration.rs:43)
-        s.fn(s.user, 0, 0, nullptr, 0);
-        return RECS_OK;
+// A CPU system of the current batch, borrowed and cut into tasks.
+struct CpuRun {
+    AppSystem* sys = nullptr;
+    std::vector<uint32_t> archs;
+    std::vector<std::vector<void*>> cols;  // per matched archetype: column base pointers in parameter order
+    std::vector<uint64_t> counts;
+};
+
+void release_borrows(recs_app* app, const AppSystem& s, uint32_t arch, const Param* upto) {
+    for (const Param& q : s.params) {
+        if (&q == upto) break;
+        if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
+            recs_world_release_column(app->world, arch, q.comp, q.op == RECS_PARAM_WRITE);
     }
-    const std::vector<uint32_t> archs = params_archetypes(*app->world, s.params);
-    std::vector<void*> cols;
-    for (uint32_t a : archs) {
-        cols.clear();
-        uint64_t count = app->world->archetypes[a].entities.size();
+}
+
+// Borrow phase of `SequentiallyIterable::run` / `SegmentIterable::segments`
+// (crates/ecs/src/systems/iteration.rs:26-57, 151-245): archetype match, host residency, RwLock try_read /
+// try_write on every column for the duration of the system (archetypes.rs:106-138).
+int32_t prepare_cpu_system(recs_app* app, AppSystem& s, CpuRun* run) {
+    run->sys = &s;
+    if (!params_controls_iteration(s.params)) return RECS_OK;
+    run->archs = params_archetypes(*app->world, s.params);
+    for (uint32_t a : run->archs) {
+        std::vector<void*> cols;
         for (const Param& p : s.params) {
             if (p.op != RECS_PARAM_READ && p.op != RECS_PARAM_WRITE) continue;
             int32_t st = ensure_on_host(app, a, p.comp);
@@ -217,25 +295,79 @@ int32_t run_cpu_system(recs_app* app, AppSystem& s) {
             auto it = app->world->archetypes[a].columns.find(p.comp);
             if (it == app->world->archetypes[a].columns.end())
                 return app->fail(RECS_ERR_MISSING_PARAMETER, "could not execute system due to missing parameter");
-            // RwLock try_read / try_write for the duration of the call (archetypes.rs:106-138)
             st = recs_world_borrow_column(app->world, a, p.comp, p.op == RECS_PARAM_WRITE);
             if (st != RECS_OK) {
-                for (const Param& q : s.params) {  // release what was taken so far
-                    if (&q == &p) break;
-                    if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
-                        recs_world_release_column(app->world, a, q.comp, q.op == RECS_PARAM_WRITE);
-                }
+                release_borrows(app, s, a, &p);  // what was taken so far in this archetype
+                for (size_t k = 0; k + 1 <= run->cols.size(); ++k) release_borrows(app, s, run->archs[k], nullptr);
                 return app->fail(st, recs_world_last_error(app->world));
             }
             cols.push_back(it->second.data.data());
         }
-        s.fn(s.user, a, count, cols.data(), (uint32_t)cols.size());
-        for (const Param& p : s.params) {
-            if (p.op != RECS_PARAM_READ && p.op != RECS_PARAM_WRITE) continue;
-            recs_world_release_column(app->world, a, p.comp, p.op == RECS_PARAM_WRITE);
-            if (p.op == RECS_PARAM_WRITE) app->mirror[ColKey(a, p.comp)].host_dirty = true;
-        }
+        run->cols.push_back(cols);
+        run->counts.push_back(app->world->archetypes[a].entities.size());
     }
+    return RECS_OK;
+}
+
+void finish_cpu_system(recs_app* app, CpuRun& run) {
+    for (size_t k = 0; k < run.cols.size(); ++k) {
+        const uint32_t a = run.archs[k];
+        release_borrows(app, *run.sys, a, nullptr);
+        for (const Param& p : run.sys->params)
+            if (p.op == RECS_PARAM_WRITE) app->mirror[ColKey(a, p.comp)].host_dirty = true;
+    }
+}
+
+// The tasks of one CPU system.  Sequential executor / plain systems: one task.  WorkerPool + par-iter system: one
+// task per segment of SegmentSize::Auto = max(16, N / (threads * 4)) entities (crates/ecs/src/systems/mod.rs:394-411),
+// the concatenation of the matched archetypes' columns cut by split_borrowed_data (:473-540).
+void cpu_system_tasks(recs_app* app, CpuRun& run, std::vector<std::function<void()>>* tasks) {
+    AppSystem& s = *run.sys;
+    if (!params_controls_iteration(s.params)) {
+        // no iterating parameter: the function runs exactly once (iterate_once, iteration.rs:43)
+        if (s.segment_fn)
+            tasks->push_back([&s] { s.segment_fn(s.user, 0, 0, 0, nullptr, 0); });
+        else
+            tasks->push_back([&s] { s.fn(s.user, 0, 0, nullptr, 0); });
+        return;
+    }
+    if (!s.segment_fn) {
+        tasks->push_back([&s, &run] {
+            for (size_t k = 0; k < run.cols.size(); ++k)
+                s.fn(s.user, run.archs[k], run.counts[k], run.cols[k].data(), (uint32_t)run.cols[k].size());
+        });
+        return;
+    }
+    uint64_t total = 0;
+    for (uint64_t c : run.counts) total += c;
+    const uint64_t segment_size = app->pool ? recs_auto_segment_size(total, app->pool->size()) : 0;  // 0 = Single
+    std::vector<recs_segment_slice> slices(run.counts.size() + (segment_size ? total / segment_size + 2 : 1) + 1);
+    uint64_t n_slices = 0, n_segments = 0;
+    recs_split_segments(run.counts.data(), (uint32_t)run.counts.size(), segment_size, slices.data(), slices.size(), &n_slices,
+                        &n_segments);
+    slices.resize(n_slices);
+    for (uint64_t seg = 0; seg < n_segments; ++seg) {
+        std::vector<recs_segment_slice> mine;
+        for (const recs_segment_slice& sl : slices)
+            if (sl.segment == seg && sl.len) mine.push_back(sl);
+        if (mine.empty()) continue;
+        tasks->push_back([&s, &run, mine] {
+            for (const recs_segment_slice& sl : mine)
+                s.segment_fn(s.user, run.archs[sl.column], sl.begin, sl.len, run.cols[sl.column].data(),
+                             (uint32_t)run.cols[sl.column].size());
+        });
+    }
+}
+
+// `SequentiallyIterable::run` for a CPU system on the calling thread.
+int32_t run_cpu_system(recs_app* app, AppSystem& s) {
+    CpuRun run;
+    int32_t st = prepare_cpu_system(app, s, &run);
+    if (st != RECS_OK) return st;
+    std::vector<std::function<void()>> tasks;
+    cpu_system_tasks(app, run, &tasks);
+    for (auto& t : tasks) t();
+    finish_cpu_system(app, run);
     return RECS_OK;
 }
 
@@ -522,6 +654,33 @@ int32_t recs_app_add_cpu_system(recs_app* app, const char* name, const recs_para
     return RECS_OK;
 }
 
+int32_t recs_app_add_cpu_segment_system(recs_app* app, const char* name, const recs_param_token* tokens, uint32_t n_tokens,
+                                        recs_cpu_segment_fn fn, void* user, uint32_t* out_index) {
+    if (!app || !fn) return RECS_ERR_INVALID_ARGUMENT;
+    AppSystem s;
+    s.gpu = false;
+    s.name = name ? name : "system";
+    s.segment_fn = fn;
+    s.user = user;
+    std::string err;
+    if (!parse_params(tokens, n_tokens, &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
+    if (!params_supports_parallelization(s.params))
+        return app->fail(RECS_ERR_UNSUPPORTED, "segment systems need parameters that all support parallelization (a nested Query only with read accesses, systems/mod.rs:1101-1105)");
+    params_accesses(s.params, &s.access);
+    app->systems.push_back(s);
+    if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
+    return RECS_OK;
+}
+
+int32_t recs_app_set_executor(recs_app* app, uint32_t worker_threads) {
+    if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (worker_threads == 0)
+        app->pool.reset();
+    else if (!app->pool || app->pool->size() != worker_threads)
+        app->pool.reset(new WorkerPool(worker_threads));
+    return RECS_OK;
+}
+
 int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
     int32_t st = ensure_schedule(app, ordered ? 1 : 0);
@@ -536,12 +695,40 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
             st = recs_schedule_next_batch(app->schedule, RECS_REACTION_RETURN_ERROR, batch.data(), (uint32_t)batch.size(), &got);
             if (st == RECS_SCHEDULE_NEW_TICK) break;
             if (st != RECS_OK) return app->fail(st, "schedule error");
-            for (uint32_t i = 0; i < got; ++i) {
-                AppSystem& s = app->systems[batch[i]];
-                st = s.gpu ? run_gpu_system(app, s) : run_cpu_system(app, s);
+            if (!app->pool) {
+                for (uint32_t i = 0; i < got; ++i) {
+                    AppSystem& s = app->systems[batch[i]];
+                    st = s.gpu ? run_gpu_system(app, s) : run_cpu_system(app, s);
+                    if (st != RECS_OK) return st;
+                    app->last_order.push_back(batch[i]);
+                    app->last_batch.push_back(batch_no);
+                }
+            } else {
+                // WorkerPool::execute_once (executor/mod.rs:191-236): the systems of a batch do not conflict, so
+                // their tasks share the injector queue; GPU systems are single tasks issued from this thread.
+                std::vector<CpuRun> runs(got);
+                size_t n_runs = 0;
+                for (uint32_t i = 0; i < got && st == RECS_OK; ++i) {
+                    AppSystem& s = app->systems[batch[i]];
+                    if (!s.gpu) st = prepare_cpu_system(app, s, &runs[n_runs++]);
+                }
+                if (st == RECS_OK) {
+                    std::vector<std::function<void()>> tasks;
+                    for (size_t k = 0; k < n_runs; ++k) cpu_system_tasks(app, runs[k], &tasks);
+                    for (auto& t : tasks) app->pool->submit(std::move(t));
+                    for (uint32_t i = 0; i < got && st == RECS_OK; ++i) {
+                        AppSystem& s = app->systems[batch[i]];
+                        if (s.gpu) st = run_gpu_system(app, s);
+                    }
+                    app->pool->wait_idle();
+                }
+                for (size_t k = 0; k < n_runs; ++k)
+                    if (runs[k].sys) finish_cpu_system(app, runs[k]);
                 if (st != RECS_OK) return st;
-                app->last_order.push_back(batch[i]);
-                app->last_batch.push_back(batch_no);
+                for (uint32_t i = 0; i < got; ++i) {
+                    app->last_order.push_back(batch[i]);
+                    app->last_batch.push_back(batch_no);
+                }
             }
             // completion == dropping the SystemExecutionGuard (lib.rs:525-557)
             for (uint32_t i = 0; i < got; ++i) recs_schedule_complete(app->schedule, batch[i]);
@@ -564,12 +751,14 @@ int32_t recs_app_command_create(recs_app* app, const uint64_t* ids, const void* 
         if (it->second.elem && values && values[i]) memcpy(bytes.data(), values[i], it->second.elem);
         cmd.values.push_back(bytes);
     }
+    std::lock_guard<std::mutex> lock(app->command_mu);
     app->creates.push_back(cmd);
     return RECS_OK;
 }
 
 int32_t recs_app_command_remove(recs_app* app, recs_entity entity) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(app->command_mu);
     app->removes.push_back(entity);
     return RECS_OK;
 }

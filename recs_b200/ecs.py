@@ -42,6 +42,7 @@ class SystemInfo(C.Structure):
 
 
 CPU_SYSTEM_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint64, C.POINTER(C.c_void_p), C.c_uint32)
+CPU_SEGMENT_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p), C.c_uint32)
 
 _w, _s, _a = C.c_void_p, C.c_void_p, C.c_void_p
 _u32p, _u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
@@ -94,6 +95,8 @@ ECS_SYMBOLS = {
         [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32, _u32p],
     ),
     "recs_app_set_system_uniform": (C.c_int32, [_a, C.c_uint32, C.c_void_p, C.c_uint32]),
+    "recs_app_add_cpu_segment_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SEGMENT_FN, C.c_void_p, _u32p]),
+    "recs_app_set_executor": (C.c_int32, [_a, C.c_uint32]),
     "recs_fold_swap_removes": (C.c_int32, [C.c_uint64, _u32p, C.c_uint32, _u32p, _u32p, C.c_uint32, _u32p, C.POINTER(C.c_uint64)]),
     "recs_app_add_cpu_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SYSTEM_FN, C.c_void_p, _u32p]),
     "recs_app_run": (C.c_int32, [_a, C.c_uint32, C.c_int32]),
@@ -509,6 +512,26 @@ class Application:
         self._check(lib.recs_app_add_cpu_system(self._h, name.encode(), arr, n, cb, None, C.byref(idx)), "recs_app_add_cpu_system")
         self.system_names.append(name)
         return int(idx.value)
+
+    def add_cpu_segment_system(self, name: str, params, fn) -> int:
+        """Par-iter CPU system: fn(archetype, row_begin, row_count, columns) with columns = raw host BASE pointers
+        of the archetype's columns in parameter order; may be called from worker threads."""
+
+        def trampoline(_user, archetype, row_begin, row_count, cols, n_cols):
+            fn(int(archetype), int(row_begin), int(row_count), [cols[i] for i in range(n_cols)])
+
+        cb = CPU_SEGMENT_FN(trampoline)
+        self._callbacks.append(cb)
+        arr, n = tokens(params)
+        idx = C.c_uint32()
+        self._check(lib.recs_app_add_cpu_segment_system(self._h, name.encode(), arr, n, cb, None, C.byref(idx)),
+                    "recs_app_add_cpu_segment_system")
+        self.system_names.append(name)
+        return int(idx.value)
+
+    def set_executor(self, worker_threads: int) -> None:
+        """0 = Sequential executor, n > 0 = WorkerPool with n worker threads."""
+        self._check(lib.recs_app_set_executor(self._h, worker_threads), "recs_app_set_executor")
 
     def command_create(self, components: dict) -> None:
         """`commands.create(...)` from inside a CPU system."""

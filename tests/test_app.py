@@ -135,3 +135,112 @@ def test_cpu_system_sees_device_results(gpu_ctx):
     app.run(3)
     # observer reads Position, add writes it: readers first within a tick -> sees 0, 2, 4
     assert [float(s[0]) for s in seen] == [0.0, 2.0, 4.0]
+
+
+# ---- WorkerPool executor (crates/scheduler/src/executor/mod.rs:101-291) -------------------------------------------------
+def _segment_app(threads):
+    app = ecs.Application(gpu=None)
+    w = app.world
+    DATA, TAG = 7, 8
+    w.register_component(DATA, np.dtype(np.float32), "Data")
+    w.register_component(TAG, np.dtype(np.float32), "Tag")
+    counts = {1: 1000, 2: 37}  # archetype 1: {Data}, archetype 2: {Data, Tag}
+    w.create_entities(counts[1], {DATA: np.arange(counts[1], dtype=np.float32)})
+    w.create_entities(counts[2], {DATA: np.arange(counts[2], dtype=np.float32) + 5000, TAG: np.zeros(counts[2], np.float32)})
+    app.set_executor(threads)
+    return app, w, DATA, TAG, counts
+
+
+@pytest.mark.parametrize("threads", [0, 1, 4])
+def test_segment_system_visits_every_entity_exactly_once(threads):
+    """The par-iter contract (crates/ecs/src/systems/iteration.rs:271-324: segmented == sequential visitation): under
+    the WorkerPool executor the matched archetypes are cut into SegmentSize::Auto segments (systems/mod.rs:394-411),
+    segments may span archetypes, and the union of all calls covers every row once."""
+    import threading
+
+    app, w, DATA, TAG, counts = _segment_app(threads)
+    calls, lock, thread_ids = [], threading.Lock(), set()
+
+    def doubling(arch, row_begin, row_count, cols):
+        d = _f32(cols[0], counts[arch])
+        d[row_begin : row_begin + row_count] *= np.float32(2.0)
+        with lock:
+            calls.append((arch, row_begin, row_count))
+            thread_ids.add(threading.get_ident())
+
+    app.add_cpu_segment_system("doubling", [("write", DATA)], doubling)
+    app.run(1)
+    assert np.array_equal(w.column(1, DATA).reshape(-1), np.arange(1000, dtype=np.float32) * 2)
+    assert np.array_equal(w.column(2, DATA).reshape(-1), (np.arange(37, dtype=np.float32) + 5000) * 2)
+    covered = {1: np.zeros(1000, int), 2: np.zeros(37, int)}
+    for arch, b, c in calls:
+        covered[arch][b : b + c] += 1
+    assert all((v == 1).all() for v in covered.values())
+    total = 1037
+    if threads == 0:
+        assert sorted(calls) == [(1, 0, 1000), (2, 0, 37)]  # Sequential executor: whole columns
+    else:
+        size = ecs.auto_segment_size(total, threads)  # max(16, N / (threads * 4))
+        want = ecs.split_segments([1000, 37], size)
+        want_calls = sorted((1 + col, begin, ln) for seg in want for (col, begin, ln) in seg if ln)
+        assert sorted(calls) == want_calls
+        assert len(want) == ecs.segment_count(total, size)
+    if threads == 4:
+        assert threading.get_ident() not in thread_ids  # bodies ran on worker threads, not on the caller
+
+
+def test_pool_runs_non_conflicting_systems_of_a_batch_and_orders_conflicting_ones():
+    app, w, DATA, TAG, counts = _segment_app(3)
+    log = []
+
+    def read_data(arch, row_begin, row_count, cols):
+        log.append("read_data")
+
+    def write_tag(arch, row_begin, row_count, cols):  # does not conflict with read_data: same batch
+        _f32(cols[0], counts[arch])[row_begin : row_begin + row_count] += np.float32(1.0)
+        log.append("write_tag")
+
+    def write_data(arch, count, cols):  # plain system: one task, after its reader
+        log.append("write_data")
+        _f32(cols[0], count)[:] += np.float32(0.5)
+
+    app.add_cpu_segment_system("read_data", [("read", DATA)], read_data)
+    app.add_cpu_segment_system("write_tag", [("write", TAG)], write_tag)
+    app.add_cpu_system("write_data", [("write", DATA)], write_data)
+    app.run(3)
+    order, batches = app.last_tick_order()
+    names = [app.system_names[i] for i in order]
+    assert batches[names.index("read_data")] < batches[names.index("write_data")]
+    last_reader = max(i for i, x in enumerate(log) if x == "read_data")
+    per_tick = len(log) // 3
+    for t in range(3):  # within every tick all read_data segments precede write_data
+        chunk = log[t * per_tick : (t + 1) * per_tick]
+        assert max(i for i, x in enumerate(chunk) if x == "read_data") < min(i for i, x in enumerate(chunk) if x == "write_data")
+    assert last_reader >= 0
+    assert np.array_equal(w.column(2, TAG).reshape(-1), np.full(37, 3.0, np.float32))
+    assert np.array_equal(w.column(1, DATA).reshape(-1), np.arange(1000, dtype=np.float32) + 1.5)
+
+
+def test_commands_recorded_from_worker_threads_are_played_back():
+    app, w, DATA, TAG, counts = _segment_app(4)
+
+    def spawn(arch, row_begin, row_count, cols):  # every segment records one create
+        app.command_create({DATA: np.float32(-1.0)})
+
+    app.add_cpu_segment_system("spawn", [("read", DATA), ("commands",)], spawn)
+    app.run(1)
+    size = ecs.auto_segment_size(1037, 4)
+    n_calls = sum(1 for seg in ecs.split_segments([1000, 37], size) for (_, _, ln) in seg if ln)
+    assert app.last_playback() == (n_calls, 0)
+    assert len(w.archetype_entities(1)) == 1000 + n_calls
+
+
+def test_segment_systems_need_parallelizable_parameters():
+    """`try_as_segment_iterable` is None unless every parameter supports parallelization; a nested Query does only
+    if all of its accesses are reads (crates/ecs/src/systems/mod.rs:210-212, 1101-1105)."""
+    app = ecs.Application(gpu=None)
+    app.world.register_component(7, np.dtype(np.float32), "Data")
+    app.add_cpu_segment_system("ok", [("read", 7), ("query", [("read", 7)])], lambda *a: None)
+    with pytest.raises(ecs.EcsError) as e:
+        app.add_cpu_segment_system("bad", [("read", 7), ("query", [("write", 7)])], lambda *a: None)
+    assert e.value.code == 11  # RECS_ERR_UNSUPPORTED

@@ -129,10 +129,14 @@ def test_nbody_demo_with_collision_through_application(gpu_ctx, nbody_oracle):
 # the complete rain tick: clouds spawn drops (CPU, Commands::create), drops fall (GPU), drops that
 # reach the ground are removed (GPU decides, host plays back)
 # ---------------------------------------------------------------------------------------------------
-def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle):
+@pytest.mark.parametrize("worker_threads", [0, 3])
+def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle, worker_threads):
+    """worker_threads = 0: Sequential executor; 3: WorkerPool -- the CPU systems of a batch run on worker threads
+    while the GPU systems of the same batch are enqueued from the scheduling thread."""
     VEL, POS, MASS, CLOUD = 20, 21, 22, 23
     n_clouds, ticks = 9, 60
     app = ecs.Application(gpu=gpu_ctx)
+    app.set_executor(worker_threads)
     w = app.world
     for c, dt, name in ((VEL, F3, "Velocity"), (POS, F3, "Position"), (MASS, np.float32, "Mass"), (CLOUD, F3, "Cloud")):
         w.register_component(c, dt, name)
