@@ -257,3 +257,35 @@ def test_application_runs_generic_systems_with_filters(gpu_ctx):
     assert n == 53 - 1
     assert np.all(col[:n].reshape(-1) % np.float32(8.0) == 0)
     app.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("floats,expect_chunk", [(16, 256), (1024, 0)])
+def test_wide_components_pipelined_and_direct(gpu_ctx, floats, expect_chunk):
+    """A Matrix4-sized component (64 B: 256-entity chunks) and a 4 KiB one (direct form), two archetypes, ragged
+    counts; body = an in-place transform that reads the whole element (heavy_compute's access pattern,
+    crates/ecs_bench_suite/src/recs/heavy_compute.rs:47-52, without cgmath's invert)."""
+    ctx = gpu_ctx
+    src = (f"struct W {{ float m[{floats}]; }};\nstruct P {{ float x, y, z; }};\n"
+           "void f(W& w, P& p) {\n"
+           f"    float s = 0.0f; for (int i = 0; i < {floats}; ++i) s += w.m[i];\n"
+           f"    for (int i = 0; i < {floats}; ++i) w.m[i] = w.m[i] * 2.0f + (float)i;\n"
+           "    p.x = s; p.y += 1.0f;\n}\n")
+    st, log, _, chunk = compile_kernel_system(src, "f", [(1, floats * 4, "write", "W"), (2, 12, "write", "P")])
+    assert st == 0 and chunk == expect_chunk, log
+    rng = np.random.default_rng(floats)
+    data = {}
+    for arch, count in ((1, 700), (2, 3)):
+        w = rng.integers(-8, 8, size=(count, floats)).astype(np.float32)  # small integers: sums are exact in any order
+        p = np.zeros((count, 3), np.float32)
+        data[arch] = (w, p, w.copy())
+        _bind(ctx, arch, 1, w)
+        _bind(ctx, arch, 2, p)
+    sid = ctx.create_kernel_system("f", src, "f", [(1, floats * 4, "write", "W"), (2, 12, "write", "P")])
+    ctx.set_archetypes(sid, [1, 2])
+    ctx.run_system(sid)
+    for arch, (w, p, w0) in data.items():
+        ctx.download(arch, 1)
+        ctx.download(arch, 2)
+        assert np.array_equal(w, w0 * np.float32(2.0) + np.arange(floats, dtype=np.float32))
+        assert np.array_equal(p[:, 0], w0.sum(axis=1)) and np.all(p[:, 1] == 1.0) and np.all(p[:, 2] == 0.0)
