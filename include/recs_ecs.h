@@ -216,9 +216,11 @@ recs_world* recs_app_world(recs_app* app);
 int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const uint64_t* component_ids,
                                 uint32_t n_component_ids, uint32_t* out_index);
 /* A generic GPU system (recs_gpu_system_create_kernel) behind the same registration path: `tokens` is the
- * parameter list of the function -- Read / Write / Entity become the arguments of `body` in order, With / Not /
- * And / Or / Xor only filter the archetype match (crates/ecs/src/filter.rs) -- and type_names[i] is the C++
- * type of the i-th argument in `source`.  Element sizes come from the component registry. */
+ * parameter list of the function -- Read / Write / Entity become the arguments of `body` in order, a Commands
+ * parameter becomes `const recs_commands&` (remove() of the body's own entity; the rows feed the tick's command
+ * playback like those of the built-in removal-deciding kinds), With / Not / And / Or / Xor only filter the archetype
+ * match (crates/ecs/src/filter.rs) -- and type_names[i] is the C++ type of the i-th Read / Write / Entity argument in
+ * `source`.  Element sizes come from the component registry. */
 int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
                                        const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
                                        const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index);

@@ -223,7 +223,8 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
  * 151-245; segments may span archetypes, crates/ecs/src/systems/mod.rs:473-540, 645-710).
  *
  * The body is CUDA C++ source defining the component types and one function
- *     void body(Write params as T&, Read/Entity params as const T&, ... [, const Uniform& u]);
+ *     void body(Write params as T&, Read/Entity params as const T&, Commands as const recs_commands&, ...
+ *               [, const Uniform& u]);
  * in parameter order.  It is compiled for sm_100a with NVRTC when the system is registered
  * (--fmad=false: rustc never contracts a*b+c), wrapped in a kernel that finds each entity's
  * archetype through a prefix table and, when the rows fit, stages every column chunk through
@@ -233,6 +234,9 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
 #define RECS_KPARAM_READ 0u
 #define RECS_KPARAM_WRITE 1u
 #define RECS_KPARAM_ENTITY 2u
+#define RECS_KPARAM_COMMANDS 3u /* `Commands` restricted to remove(): the body receives `const recs_commands&` and may call
+                                 * .remove() for its own entity (crates/ecs/src/systems/command_buffers.rs:53-112); the rows
+                                 * are fetched with recs_gpu_system_removals like for the built-in removal-deciding kinds */
 /* Component id under which the host binds an archetype's entity column for `Entity` parameters:
  * one uint64 per row, generation << 32 | id, the value `Entity::hash` feeds
  * (crates/ecs/src/lib.rs:918-927). */
@@ -240,7 +244,7 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
 typedef struct recs_gpu_kernel_param {
     uint64_t component_id; /* ignored for RECS_KPARAM_ENTITY (RECS_GPU_ENTITY_COMPONENT is used)  */
     uint32_t elem_size;    /* sizeof(T) on the host == sizeof(type_name) in `source`              */
-    uint32_t kind;         /* RECS_KPARAM_READ / RECS_KPARAM_WRITE / RECS_KPARAM_ENTITY              */
+    uint32_t kind;         /* RECS_KPARAM_READ / _WRITE / _ENTITY / _COMMANDS (type_name, elem_size unused)  */
     const char* type_name; /* C++ type of this parameter in `source`                              */
 } recs_gpu_kernel_param;
 /* Registers a generic system.  `uniform_type` (may be NULL) names a POD struct of at most 256 bytes

@@ -46,6 +46,7 @@ SYS_KERNEL = 11
 KPARAM_READ = 0
 KPARAM_WRITE = 1
 KPARAM_ENTITY = 2
+KPARAM_COMMANDS = 3
 ENTITY_COMPONENT = 0xFFFFFFFFFFFFFFFE
 
 GPU_ASYNC = 0

@@ -44,6 +44,7 @@ struct KernelSys {
     cudaKernel_t kernel = nullptr;
     std::vector<unsigned char> uniform;    // bytes passed by value to every launch
     bool has_uniform = false;
+    bool has_commands = false;             // one RECS_KPARAM_COMMANDS parameter: the system decides removals
     // archetype table on the device, rebuilt when bindings / membership change
     unsigned long long* table = nullptr;
     size_t table_cap = 0;
@@ -52,6 +53,7 @@ struct KernelSys {
     uint64_t n_items = 0;
     uint32_t n_arch = 0;
     uint64_t footprint_bytes = 0;          // bytes of all columns one launch touches
+    std::vector<uint32_t> table_archs;     // archetypes with rows, in table order
     ~KernelSys() {
         if (table) cudaFree(table);
         if (lib) cudaLibraryUnload(lib);
@@ -609,10 +611,16 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         for (uint32_t a : sys.archs) {
             std::vector<Column*> row(n_params, nullptr);
             int32_t st;
-            for (size_t p = 0; p < n_params; ++p)
+            Column* first = nullptr;
+            for (size_t p = 0; p < n_params; ++p) {
+                if (k.params[p].kind == RECS_KPARAM_COMMANDS) continue;
                 if ((st = need_column(c, a, k.comp[p], k.params[p].elem_size, &row[p])) != RECS_OK) return st;
-            for (size_t p = 1; p < n_params; ++p)
-                if ((st = same_count(c, row[0], row[p])) != RECS_OK) return st;
+                if (!first) first = row[p];
+                if ((st = same_count(c, first, row[p])) != RECS_OK) return st;
+            }
+            if (!first) return fail(c, RECS_ERR_UNSUPPORTED, "a generic system needs at least one Read / Write / Entity parameter");
+            for (size_t p = 0; p < n_params; ++p)
+                if (!row[p]) row[p] = first;  // Commands: counted like the first column
             // sharded contexts: every rank runs the body over its own contiguous slice of each archetype
             uint64_t rb = 0, re = row[0]->count, slice;
             if (c->cfg.world_size > 1) shard_rows(c->cfg, row[0]->count, &slice, &rb, &re);
@@ -630,14 +638,35 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
             t[i] = items;
             items += k.plan.staged ? (count + k.plan.chunk - 1) / k.plan.chunk : count;
             t[n_arch + 1 + i] = count;
-            for (size_t p = 0; p < n_params; ++p)
+            for (size_t p = 0; p < n_params; ++p) {
+                if (k.params[p].kind == RECS_KPARAM_COMMANDS) {
+                    // removal flags of this archetype (grown here, with the table, never during a captured tick)
+                    System::Removals& r = sys.removals[archs[i]];
+                    const uint32_t n = (uint32_t)cols[i][p]->count;
+                    if (r.cap_rows < std::max<uint32_t>(n, 1)) {
+                        if (r.flags) RECS_CUDA(c, cudaFree(r.flags));
+                        if (r.rows) RECS_CUDA(c, cudaFree(r.rows));
+                        if (!r.counter) RECS_CUDA(c, cudaMalloc((void**)&r.counter, sizeof(uint32_t)));
+                        size_t cap = 256;
+                        while (cap < n) cap <<= 1;
+                        RECS_CUDA(c, cudaMalloc((void**)&r.flags, cap * sizeof(uint32_t)));
+                        RECS_CUDA(c, cudaMalloc((void**)&r.rows, cap * sizeof(uint32_t)));
+                        r.cap_rows = cap;
+                    }
+                    r.n_rows = n;
+                    t[2 * n_arch + 1 + p * n_arch + i] = (unsigned long long)(uintptr_t)(r.flags + ranges[i].first);
+                    continue;
+                }
                 t[2 * n_arch + 1 + p * n_arch + i] =
                     (unsigned long long)(uintptr_t)((unsigned char*)cols[i][p]->dev + ranges[i].first * k.params[p].elem_size);
+            }
         }
         t[n_arch] = items;
         k.footprint_bytes = 0;
         for (size_t i = 0; i < n_arch; ++i)
-            for (size_t p = 0; p < n_params; ++p) k.footprint_bytes += (ranges[i].second - ranges[i].first) * k.params[p].elem_size;
+            for (size_t p = 0; p < n_params; ++p)
+                if (k.params[p].kind != RECS_KPARAM_COMMANDS)
+                    k.footprint_bytes += (ranges[i].second - ranges[i].first) * k.params[p].elem_size;
         int32_t st = ensure(c, &k.table, &k.table_cap, std::max<size_t>(t.size() * sizeof(unsigned long long), 64));
         if (st != RECS_OK) return st;
         RECS_CUDA(c, cudaMemcpyAsync(k.table, t.data(), t.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
@@ -645,7 +674,24 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // t is pageable host memory
         k.n_items = items;
         k.n_arch = (uint32_t)n_arch;
+        k.table_archs = archs;
         k.table_epoch = c->epoch;
+    }
+    if (k.has_commands) {
+        for (auto& kv : sys.removals) kv.second.valid = false;
+        for (uint32_t a : sys.archs) {  // archetypes without rows still answer recs_gpu_system_removals (with nothing)
+            System::Removals& r = sys.removals[a];
+            if (!r.counter) {
+                if (c->capturing) return fail(c, RECS_ERR_CUDA, "workspace growth during graph capture");
+                RECS_CUDA(c, cudaMalloc((void**)&r.counter, sizeof(uint32_t)));
+            }
+            RECS_CUDA(c, cudaMemsetAsync(r.counter, 0, sizeof(uint32_t), c->stream));
+            r.valid = true;
+        }
+        for (uint32_t a : k.table_archs) {
+            System::Removals& r = sys.removals[a];
+            RECS_CUDA(c, cudaMemsetAsync(r.flags, 0, (size_t)r.n_rows * sizeof(uint32_t), c->stream));
+        }
     }
     if (k.n_items == 0) return RECS_OK;
     // grid: persistent CTAs for the pipelined form (three per SM while shared memory allows), one resident wave of
@@ -676,6 +722,12 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
                                       c->stream));
     }
     c->kernel_launches++;
+    if (k.has_commands)
+        for (uint32_t a : k.table_archs) {
+            System::Removals& r = sys.removals[a];
+            RECS_CUDA(c, launch_compact_flags(r.flags, r.n_rows, r.rows, r.counter, (uint32_t)r.cap_rows, c->stream));
+            c->kernel_launches++;
+        }
     for (uint32_t a : sys.archs)
         for (size_t p = 0; p < n_params; ++p)
             if (k.params[p].kind == RECS_KPARAM_WRITE) {
@@ -1240,7 +1292,16 @@ int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* c, const char* name, const c
     s.n_comp = 0;
     for (uint32_t i = 0; i < n_params; ++i) {
         const recs_gpu_kernel_param& p = params[i];
-        if (!p.type_name || !p.type_name[0] || p.elem_size == 0 || p.kind > RECS_KPARAM_ENTITY)
+        if (p.kind > RECS_KPARAM_COMMANDS) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: bad parameter kind");
+        if (p.kind == RECS_KPARAM_COMMANDS) {  // no column: one removal flag per row, owned by the context
+            if (ks->has_commands) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: more than one Commands parameter");
+            if (c->cfg.world_size > 1) return fail(c, RECS_ERR_UNSUPPORTED, "removal-deciding systems are single-GPU");
+            ks->has_commands = true;
+            ks->params.push_back({"recs_commands", 4u, p.kind});
+            ks->comp.push_back(0);
+            continue;
+        }
+        if (!p.type_name || !p.type_name[0] || p.elem_size == 0)
             return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: bad parameter description");
         if (p.kind == RECS_KPARAM_ENTITY && p.elem_size != 8)
             return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: Entity parameters are 8 bytes (generation << 32 | id)");

@@ -38,6 +38,7 @@ struct AppSystem {
     std::vector<recs_gpu_access> access;
     recs_cpu_system_fn fn = nullptr;
     recs_cpu_segment_fn segment_fn = nullptr;  // par-iter form: may be cut into segments (SegmentIterable)
+    bool decides_removals = false;             // generic GPU system with a Commands parameter
     void* user = nullptr;
 };
 
@@ -255,7 +256,7 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
         if ((st = recs_gpu_system_set_query_archetypes(app->gpu, s.gpu_id, qarchs.data(), (uint32_t)qarchs.size())) != RECS_OK)
             return gpu_fail(app, st);
     if ((st = recs_gpu_run_system(app->gpu, s.gpu_id, RECS_GPU_ASYNC)) != RECS_OK) return gpu_fail(app, st);
-    if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION)
+    if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION || s.decides_removals)
         app->gpu_removal_sources.push_back(std::make_pair((uint32_t)(&s - app->systems.data()), archs));
     for (const Param& p : s.params)
         if (p.op == RECS_PARAM_WRITE)
@@ -582,10 +583,12 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
     if (!parse_params(tokens, n_tokens, &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
     // Read / Write / Entity become kernel arguments in order; filters only shape the archetype match
     std::vector<recs_gpu_kernel_param> kp;
+    size_t n_typed = 0;  // Read / Write / Entity parameters seen so far (index into type_names)
     for (const Param& p : s.params) {
         recs_gpu_kernel_param k;
         k.component_id = p.comp;
-        k.type_name = type_names[kp.size()];
+        k.type_name = nullptr;
+        if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE || p.op == RECS_PARAM_ENTITY) k.type_name = type_names[n_typed];
         if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE) {
             auto it = app->world->registry.find(p.comp);
             if (it == app->world->registry.end()) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: component is not registered");
@@ -594,13 +597,22 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
         } else if (p.op == RECS_PARAM_ENTITY) {
             k.elem_size = 8;
             k.kind = RECS_KPARAM_ENTITY;
-        } else if (p.op == RECS_PARAM_QUERY_BEGIN || p.op == RECS_PARAM_COMMANDS) {
-            return app->fail(RECS_ERR_UNSUPPORTED, "kernel system: Query<...> and Commands parameters are not available in generic GPU systems");
+        } else if (p.op == RECS_PARAM_COMMANDS) {  // remove() only; no type name consumed
+            k.component_id = 0;
+            k.elem_size = 0;
+            k.kind = RECS_KPARAM_COMMANDS;
+            k.type_name = nullptr;
+            kp.push_back(k);
+            s.decides_removals = true;
+            continue;
+        } else if (p.op == RECS_PARAM_QUERY_BEGIN) {
+            return app->fail(RECS_ERR_UNSUPPORTED, "kernel system: nested Query<...> parameters are not available in generic GPU systems");
         } else {
             continue;  // With / Not / And / Or / Xor
         }
         if (!k.type_name) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: missing type name");
         kp.push_back(k);
+        ++n_typed;
     }
     int32_t st = recs_gpu_system_create_kernel(app->gpu, name, source, body, kp.data(), (uint32_t)kp.size(), uniform_type,
                                                uniform_bytes, &s.gpu_id);

@@ -255,7 +255,8 @@ class GpuContext:
         return arr
 
 
-_KPARAM_KINDS = {"read": _lib.KPARAM_READ, "write": _lib.KPARAM_WRITE, "entity": _lib.KPARAM_ENTITY}
+_KPARAM_KINDS = {"read": _lib.KPARAM_READ, "write": _lib.KPARAM_WRITE, "entity": _lib.KPARAM_ENTITY,
+                 "commands": _lib.KPARAM_COMMANDS}
 
 
 def kernel_params(params):
@@ -265,7 +266,7 @@ def kernel_params(params):
         arr[i].component_id = comp
         arr[i].elem_size = elem
         arr[i].kind = _KPARAM_KINDS[kind]
-        arr[i].type_name = type_name.encode()
+        arr[i].type_name = type_name.encode() if type_name else None
     arr._n = len(params)
     return arr
 

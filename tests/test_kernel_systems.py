@@ -289,3 +289,83 @@ def test_wide_components_pipelined_and_direct(gpu_ctx, floats, expect_chunk):
         ctx.download(arch, 2)
         assert np.array_equal(w, w0 * np.float32(2.0) + np.arange(floats, dtype=np.float32))
         assert np.array_equal(p[:, 0], w0.sum(axis=1)) and np.all(p[:, 1] == 1.0) and np.all(p[:, 2] == 0.0)
+
+
+GROUND = ("struct Position { float x, y, z; };\n"
+          # crates/rain-simulation/src/lib.rs:152-156
+          "void ground_collision(const unsigned long long& entity, const Position& p, const recs_commands& commands) {\n"
+          "    if (p.y <= 0.0f) commands.remove();\n}\n")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("direct", [False, True])
+def test_commands_remove_in_a_generic_system(monkeypatch, direct):
+    """`ground_collision(Entity, Read<Position>, Commands)` written as a generic system: the rows it removes must be the
+    rows the built-in RECS_SYS_RAIN_GROUND_COLLISION kind flags, over several archetypes incl. an empty one."""
+    from recs_b200 import GpuContext, _lib
+
+    if direct:
+        monkeypatch.setenv("RECS_GPU_KERNEL_DIRECT", "1")
+    rng = np.random.default_rng(9)
+    with GpuContext(device=0) as ctx:
+        cols = {}
+        for arch, count in ((1, 3000), (2, 0), (3, 77), (4, 1025)):
+            pos = (rng.standard_normal((count, 3)) * 2).astype(np.float32)
+            pos[::5, 1] = 0.0  # exactly on the ground: removed (`<=`)
+            cols[arch] = pos
+            _bind(ctx, arch, POS, pos)
+            _bind(ctx, arch, _lib.ENTITY_COMPONENT, np.arange(count, dtype=np.uint64))
+        gen = ctx.create_kernel_system(
+            "ground_collision", GROUND, "ground_collision",
+            [(0, 8, "entity", "unsigned long long"), (POS, 12, "read", "Position"), (0, 0, "commands", None)])
+        assert ctx.describe_system(gen) == ("ground_collision", [(POS, False)])
+        builtin = ctx.create_system(_lib.SYS_RAIN_GROUND_COLLISION, [POS])
+        for s in (gen, builtin):
+            ctx.set_archetypes(s, [1, 2, 3, 4])
+        for _ in range(2):  # flags are cleared per run
+            ctx.run_system(gen)
+        ctx.run_system(builtin)
+        for arch, pos in cols.items():
+            want = np.flatnonzero(pos[:, 1] <= 0.0).astype(np.uint32)
+            assert np.array_equal(ctx.system_removals(gen, arch), want), arch
+            assert np.array_equal(ctx.system_removals(builtin, arch), want), arch
+
+
+@pytest.mark.gpu
+def test_generic_removal_system_feeds_command_playback(gpu_ctx):
+    """Through the Application: a generic system with a Commands parameter removes entities at the end of the tick
+    (playback on the host World, resident columns follow by row moves) while another generic system keeps writing
+    the same archetype."""
+    from recs_b200.ecs import Application
+
+    app = Application(gpu_ctx)
+    w = app.world
+    F3 = np.dtype((np.float32, 3))
+    w.register_component(POS, F3, "Position")
+    n = 500
+    pos = np.zeros((n, 3), np.float32)
+    pos[:, 1] = np.arange(n, dtype=np.float32) * 0.01 + 0.005  # heights 0.005 .. 4.995
+    w.create_entities(n, {POS: pos})
+    fall = "struct Position { float x, y, z; };\nvoid fall(Position& p) { p.y -= 1.0f; }\n"
+    app.add_gpu_kernel_system("fall", fall, "fall", [("write", POS)], ["Position"])
+    app.add_gpu_kernel_system("ground_collision", GROUND, "ground_collision",
+                              [("entity",), ("read", POS), ("commands",)], ["unsigned long long", "Position"])
+    alive = n
+    for tick in range(1, 5):
+        app.run(1)
+        order, _ = app.last_tick_order()
+        names = [app.system_names[i] for i in order]
+        # the reader of Position precedes its writer (precedence.rs:39-66): collisions are decided on last tick's heights
+        assert names == ["ground_collision", "fall"]
+        heights_before = pos[:, 1] - np.float32(tick - 1)
+        expected_alive = int(np.count_nonzero(heights_before > 0))
+        created, removed = app.last_playback()
+        assert created == 0 and alive - removed == expected_alive, tick
+        alive = expected_alive
+    app.sync_to_host()
+    left = w.column(1, POS)[:alive]
+    assert alive == len(w.archetype_entities(1)) and alive > 0
+    assert np.all(left[:, 1] + np.float32(1.0) > 0)  # every survivor was above ground when last checked
+    h2d, d2h = gpu_ctx.transfer_bytes()
+    assert d2h == n * 12 * 0 + alive * 12  # only the final sync came back
+    app.close()
