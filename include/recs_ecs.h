@@ -224,6 +224,12 @@ int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const 
 int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
                                        const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
                                        const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index);
+/* The nested-query form (recs_gpu_system_create_pair_kernel): `tokens` holds one Query<...> group; type_names lists the
+ * C++ types of the outer Read / Write / Entity parameters and of the query's parameters in token order. */
+int32_t recs_app_add_gpu_pair_kernel_system(recs_app* app, const char* name, const char* source, const char* acc_type,
+                                            const char* pair_fn, const char* finish_fn, const recs_param_token* tokens,
+                                            uint32_t n_tokens, const char* const* type_names, const char* uniform_type,
+                                            uint32_t uniform_bytes, uint32_t* out_index);
 int32_t recs_app_set_system_uniform(recs_app* app, uint32_t system_index, const void* data, uint32_t bytes);
 /* The fold behind resident command playback, as a pure function: `rows[i]` is the row index passed to the i-th
  * `swap_remove` (crates/ecs/src/archetypes.rs:233-243) of a column that had len_before rows.  The result is the

@@ -244,7 +244,8 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
 typedef struct recs_gpu_kernel_param {
     uint64_t component_id; /* ignored for RECS_KPARAM_ENTITY (RECS_GPU_ENTITY_COMPONENT is used)  */
     uint32_t elem_size;    /* sizeof(T) on the host == sizeof(type_name) in `source`              */
-    uint32_t kind;         /* RECS_KPARAM_READ / _WRITE / _ENTITY / _COMMANDS (type_name, elem_size unused)  */
+    uint32_t kind;         /* RECS_KPARAM_READ / _WRITE / _ENTITY / _COMMANDS (type_name, elem_size unused) /
+                            * _QUERY_READ / _QUERY_ENTITY (pair kernels only)                                 */
     const char* type_name; /* C++ type of this parameter in `source`                              */
 } recs_gpu_kernel_param;
 /* Registers a generic system.  `uniform_type` (may be NULL) names a POD struct of at most 256 bytes
@@ -257,6 +258,29 @@ int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* ctx, const char* name, const
                                       uint32_t uniform_bytes, uint32_t* out_system_id);
 int32_t recs_gpu_system_set_uniform(recs_gpu_ctx* ctx, uint32_t system_id, const void* data,
                                     uint32_t bytes);
+/* Generic systems with a nested `Query<(...)>` parameter (crates/ecs/src/systems/mod.rs:915-934, 1028-1140) -- the
+ * shape of the reference's `gravity` (crates/n-body/src/lib.rs:104-135) and `collision`
+ * (crates/n-body/examples/n_body_demo.rs:54-71).  Parameters of kind RECS_KPARAM_QUERY_READ / _QUERY_ENTITY describe the
+ * nested query (read-only, as `supports_parallelization` demands, systems/mod.rs:1101-1105); its archetypes are set
+ * with recs_gpu_system_set_query_archetypes.  `source` defines an accumulator type and two functions:
+ *     void pair(ACC& acc, <outer Read / Entity params as const T&>, <query params as const T&> [, const U& u]);
+ *     void finish(<all outer params: Write as T&, Read / Entity as const T&, Commands as const recs_commands&>,
+ *                 const ACC& acc [, const U& u]);
+ * For every outer entity: ACC acc{}; pair(...) for every query entity IN QUERY ORDER (archetype order, then
+ * row order); finish(...).  One thread per outer entity, query entities staged through shared memory in tiles, so a
+ * body that accumulates in call order reproduces the reference's sequential fold bit for bit (--fmad=false, IEEE
+ * division and square root).  Single-GPU contexts only. */
+#define RECS_KPARAM_QUERY_READ 4u
+#define RECS_KPARAM_QUERY_ENTITY 5u
+int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* ctx, const char* name, const char* source,
+                                           const char* acc_type, const char* pair_fn, const char* finish_fn,
+                                           const recs_gpu_kernel_param* params, uint32_t n_params,
+                                           const char* uniform_type, uint32_t uniform_bytes,
+                                           uint32_t* out_system_id);
+int32_t recs_gpu_pair_kernel_system_compile(const char* source, const char* acc_type, const char* pair_fn,
+                                            const char* finish_fn, const recs_gpu_kernel_param* params,
+                                            uint32_t n_params, const char* uniform_type, char* log,
+                                            uint32_t log_cap, uint64_t* out_cubin_bytes);
 /* Generation + compilation only: needs neither a context nor a GPU (NVRTC cross-compiles), so a
  * host can validate its systems at build time.  `force_direct` != 0 selects the unstaged kernel
  * form.  Writes the NVRTC log (NUL terminated, truncated to log_cap), the cubin size and the

@@ -47,6 +47,8 @@ KPARAM_READ = 0
 KPARAM_WRITE = 1
 KPARAM_ENTITY = 2
 KPARAM_COMMANDS = 3
+KPARAM_QUERY_READ = 4
+KPARAM_QUERY_ENTITY = 5
 ENTITY_COMPONENT = 0xFFFFFFFFFFFFFFFE
 
 GPU_ASYNC = 0
@@ -129,6 +131,16 @@ GPU_SYMBOLS = {
     "recs_gpu_system_create_kernel": (
         C.c_int32,
         [_ctx, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KernelParam), C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32)],
+    ),
+    "recs_gpu_system_create_pair_kernel": (
+        C.c_int32,
+        [_ctx, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KernelParam), C.c_uint32, C.c_char_p,
+         C.c_uint32, C.POINTER(C.c_uint32)],
+    ),
+    "recs_gpu_pair_kernel_system_compile": (
+        C.c_int32,
+        [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(KernelParam), C.c_uint32, C.c_char_p, C.c_char_p, C.c_uint32,
+         C.POINTER(C.c_uint64)],
     ),
     "recs_gpu_system_set_uniform": (C.c_int32, [_ctx, C.c_uint32, C.c_void_p, C.c_uint32]),
     "recs_gpu_kernel_system_compile": (

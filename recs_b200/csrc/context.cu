@@ -45,6 +45,14 @@ struct KernelSys {
     std::vector<unsigned char> uniform;    // bytes passed by value to every launch
     bool has_uniform = false;
     bool has_commands = false;             // one RECS_KPARAM_COMMANDS parameter: the system decides removals
+    // nested Query<(...)> form (recs_gpu_system_create_pair_kernel)
+    bool is_pair = false;
+    std::vector<KernelParamSpec> qparams;
+    std::vector<uint64_t> qcomp;
+    unsigned long long* qtable = nullptr;
+    size_t qtable_cap = 0;
+    std::vector<unsigned long long> qtable_host;
+    uint32_t n_qarch = 0;
     // archetype table on the device, rebuilt when bindings / membership change
     unsigned long long* table = nullptr;
     size_t table_cap = 0;
@@ -56,6 +64,7 @@ struct KernelSys {
     std::vector<uint32_t> table_archs;     // archetypes with rows, in table order
     ~KernelSys() {
         if (table) cudaFree(table);
+        if (qtable) cudaFree(qtable);
         if (lib) cudaLibraryUnload(lib);
     }
 };
@@ -675,6 +684,34 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         k.n_items = items;
         k.n_arch = (uint32_t)n_arch;
         k.table_archs = archs;
+        if (k.is_pair) {
+            // the nested query: its own archetype list, every row of every matched archetype, in order
+            const size_t nq = k.qparams.size();
+            std::vector<std::vector<Column*>> qcols;
+            for (uint32_t a : sys.qarchs) {
+                std::vector<Column*> row(nq, nullptr);
+                for (size_t p = 0; p < nq; ++p) {
+                    if ((st = need_column(c, a, k.qcomp[p], k.qparams[p].elem_size, &row[p])) != RECS_OK) return st;
+                    if ((st = same_count(c, row[0], row[p])) != RECS_OK) return st;
+                }
+                if (row[0]->count) qcols.push_back(row);
+            }
+            const size_t nqa = qcols.size();
+            std::vector<unsigned long long>& q = k.qtable_host;
+            q.assign(2 * nqa + 1 + nq * nqa, 0ull);
+            unsigned long long rows = 0;
+            for (size_t i = 0; i < nqa; ++i) {
+                q[i] = rows;
+                rows += qcols[i][0]->count;
+                q[nqa + 1 + i] = qcols[i][0]->count;
+                for (size_t p = 0; p < nq; ++p) q[2 * nqa + 1 + p * nqa + i] = (unsigned long long)(uintptr_t)qcols[i][p]->dev;
+            }
+            q[nqa] = rows;
+            if ((st = ensure(c, &k.qtable, &k.qtable_cap, std::max<size_t>(q.size() * sizeof(unsigned long long), 64))) != RECS_OK) return st;
+            RECS_CUDA(c, cudaMemcpyAsync(k.qtable, q.data(), q.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+            RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+            k.n_qarch = (uint32_t)nqa;
+        }
         k.table_epoch = c->epoch;
     }
     if (k.has_commands) {
@@ -715,7 +752,15 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
     const unsigned long long* table = k.table;
     unsigned n_arch = k.n_arch;
     unsigned long long n_items = k.n_items;
-    void* args[4] = {(void*)&table, (void*)&n_arch, (void*)&n_items, k.has_uniform ? (void*)k.uniform.data() : nullptr};
+    const unsigned long long* qtable = k.qtable;
+    unsigned n_qarch = k.n_qarch;
+    void* args[6] = {(void*)&table, (void*)&n_arch, (void*)&n_items, nullptr, nullptr, nullptr};
+    int n_args = 3;
+    if (k.is_pair) {
+        args[n_args++] = (void*)&qtable;
+        args[n_args++] = (void*)&n_qarch;
+    }
+    if (k.has_uniform) args[n_args++] = (void*)k.uniform.data();
     {
         Timed t(c, T_OTHER);
         RECS_CUDA(c, cudaLaunchKernel((const void*)k.kernel, dim3(grid), dim3(k.plan.threads), args, k.plan.smem_bytes,
@@ -1326,6 +1371,78 @@ int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* c, const char* name, const c
     if (ks->plan.smem_bytes > 32u * 1024u)  // dynamic + the static barrier words must stay under the 48 KiB default
         RECS_CUDA(c, cudaFuncSetAttribute((const void*)ks->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)ks->plan.smem_bytes));
+    ks->has_uniform = uniform_bytes != 0;
+    ks->uniform.assign(std::max<uint32_t>(uniform_bytes, 1), 0);
+    s.ks = ks;
+    c->systems.push_back(s);
+    *out_id = (uint32_t)c->systems.size() - 1;
+    c->epoch++;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* c, const char* name, const char* source, const char* acc_type,
+                                           const char* pair_fn, const char* finish_fn, const recs_gpu_kernel_param* params,
+                                           uint32_t n_params, const char* uniform_type, uint32_t uniform_bytes,
+                                           uint32_t* out_id) {
+    RECS_ENTER(c);
+    if (!name || !source || !acc_type || !pair_fn || !finish_fn || !out_id || !params || n_params == 0 ||
+        n_params > 2 * RECS_GPU_MAX_ACCESSES)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: bad argument");
+    if ((uniform_type != nullptr && uniform_type[0]) != (uniform_bytes != 0) || uniform_bytes > 256)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: uniform type / size (<= 256 bytes) mismatch");
+    if (c->cfg.world_size > 1)
+        return fail(c, RECS_ERR_UNSUPPORTED, "generic nested-query systems are single-GPU (the built-in gravity kind is the sharded one)");
+    auto ks = std::make_shared<KernelSys>();
+    ks->is_pair = true;
+    System s;
+    s.kind = RECS_SYS_KERNEL;
+    s.name = name;
+    s.n_comp = 0;
+    std::vector<recs_gpu_access> query_access;
+    for (uint32_t i = 0; i < n_params; ++i) {
+        const recs_gpu_kernel_param& p = params[i];
+        if (p.kind > RECS_KPARAM_QUERY_ENTITY) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: bad parameter kind");
+        if (p.kind == RECS_KPARAM_COMMANDS) {
+            if (ks->has_commands) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: more than one Commands parameter");
+            ks->has_commands = true;
+            ks->params.push_back({"recs_commands", 4u, p.kind});
+            ks->comp.push_back(0);
+            continue;
+        }
+        if (!p.type_name || !p.type_name[0] || p.elem_size == 0)
+            return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: bad parameter description");
+        const bool entity = p.kind == RECS_KPARAM_ENTITY || p.kind == RECS_KPARAM_QUERY_ENTITY;
+        if (entity && p.elem_size != 8)
+            return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: Entity parameters are 8 bytes (generation << 32 | id)");
+        const uint64_t comp = entity ? RECS_GPU_ENTITY_COMPONENT : p.component_id;
+        const bool nested = p.kind == RECS_KPARAM_QUERY_READ || p.kind == RECS_KPARAM_QUERY_ENTITY;
+        if (nested) {
+            ks->qparams.push_back({p.type_name, p.elem_size, p.kind});
+            ks->qcomp.push_back(comp);
+        } else {
+            ks->params.push_back({p.type_name, p.elem_size, p.kind});
+            ks->comp.push_back(comp);
+        }
+        if (!entity) {  // accesses in parameter order, the nested query's after the outer ones (systems/mod.rs:973-978)
+            recs_gpu_access a;
+            a.component_id = comp;
+            a.is_write = p.kind == RECS_KPARAM_WRITE ? 1 : 0;
+            (nested ? query_access : s.access).push_back(a);
+        }
+    }
+    if (ks->qparams.empty()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: no nested query parameter");
+    bool outer_column = false;
+    for (const auto& p : ks->params) outer_column = outer_column || p.kind != RECS_KPARAM_COMMANDS;
+    if (!outer_column) return fail(c, RECS_ERR_UNSUPPORTED, "a generic system needs at least one outer Read / Write / Entity parameter");
+    s.access.insert(s.access.end(), query_access.begin(), query_access.end());
+    if (s.access.size() > RECS_GPU_MAX_ACCESSES) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: too many component accesses");
+    ks->plan = plan_pair_kernel_system(source, acc_type, pair_fn, finish_fn, ks->params, ks->qparams, uniform_type ? uniform_type : "");
+    std::vector<char> cubin;
+    std::string log;
+    if (!compile_kernel_system(ks->plan.source, &cubin, &log))
+        return fail(c, RECS_ERR_COMPILE, std::string("system '") + name + "' did not compile:\n" + log);
+    RECS_CUDA(c, cudaLibraryLoadData(&ks->lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0));
+    RECS_CUDA(c, cudaLibraryGetKernel(&ks->kernel, ks->lib, "recs_generic_system"));
     ks->has_uniform = uniform_bytes != 0;
     ks->uniform.assign(std::max<uint32_t>(uniform_bytes, 1), 0);
     s.ks = ks;

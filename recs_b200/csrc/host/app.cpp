@@ -245,14 +245,20 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
             for (uint32_t a : archs)
                 if ((st = ensure_entities_on_device(app, a)) != RECS_OK) return st;
         if (p.op == RECS_PARAM_QUERY_BEGIN)
-            for (const Param& q : p.children)
+            for (const Param& q : p.children) {
                 if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE)
                     for (uint32_t a : qarchs)
                         if ((st = ensure_on_device(app, a, q.comp)) != RECS_OK) return st;
+                if (q.op == RECS_PARAM_ENTITY && s.kind == RECS_SYS_KERNEL)
+                    for (uint32_t a : qarchs)
+                        if ((st = ensure_entities_on_device(app, a)) != RECS_OK) return st;
+            }
     }
     if ((st = recs_gpu_system_set_archetypes(app->gpu, s.gpu_id, archs.data(), (uint32_t)archs.size())) != RECS_OK)
         return gpu_fail(app, st);
-    if (!qarchs.empty() || s.kind == RECS_SYS_NBODY_GRAVITY)
+    bool has_query = false;
+    for (const Param& p : s.params) has_query = has_query || p.op == RECS_PARAM_QUERY_BEGIN;
+    if (!qarchs.empty() || s.kind == RECS_SYS_NBODY_GRAVITY || has_query)
         if ((st = recs_gpu_system_set_query_archetypes(app->gpu, s.gpu_id, qarchs.data(), (uint32_t)qarchs.size())) != RECS_OK)
             return gpu_fail(app, st);
     if ((st = recs_gpu_run_system(app->gpu, s.gpu_id, RECS_GPU_ASYNC)) != RECS_OK) return gpu_fail(app, st);
@@ -641,6 +647,72 @@ int32_t recs_fold_swap_removes(uint64_t len_before, const uint32_t* rows, uint32
         if (out_dst) out_dst[i] = dst[i];
         if (out_src) out_src[i] = src[i];
     }
+    return RECS_OK;
+}
+
+int32_t recs_app_add_gpu_pair_kernel_system(recs_app* app, const char* name, const char* source, const char* acc_type,
+                                            const char* pair_fn, const char* finish_fn, const recs_param_token* tokens,
+                                            uint32_t n_tokens, const char* const* type_names, const char* uniform_type,
+                                            uint32_t uniform_bytes, uint32_t* out_index) {
+    if (!app || !name || !source || !acc_type || !pair_fn || !finish_fn || (n_tokens && !tokens) || !type_names)
+        return RECS_ERR_INVALID_ARGUMENT;
+    if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "no GPU context: GPU systems cannot be registered (there is no CPU fallback)");
+    AppSystem s;
+    s.gpu = true;
+    s.kind = RECS_SYS_KERNEL;
+    s.name = name;
+    std::string err;
+    if (!parse_params(tokens, n_tokens, &s.params, &err)) return app->fail(RECS_ERR_INVALID_ARGUMENT, err);
+    std::vector<recs_gpu_kernel_param> kp;
+    size_t n_typed = 0;
+    bool have_query = false;
+    auto typed = [&](const Param& p, bool nested) -> int32_t {
+        recs_gpu_kernel_param k;
+        k.component_id = p.comp;
+        k.type_name = type_names[n_typed];
+        if (!k.type_name) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: missing type name");
+        if (p.op == RECS_PARAM_ENTITY) {
+            k.elem_size = 8;
+            k.kind = nested ? RECS_KPARAM_QUERY_ENTITY : RECS_KPARAM_ENTITY;
+        } else {
+            auto it = app->world->registry.find(p.comp);
+            if (it == app->world->registry.end()) return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: component is not registered");
+            k.elem_size = it->second.elem;
+            if (nested && p.op == RECS_PARAM_WRITE)
+                return app->fail(RECS_ERR_UNSUPPORTED, "kernel system: a nested Query may only read (systems/mod.rs:1101-1105)");
+            k.kind = nested ? RECS_KPARAM_QUERY_READ : (p.op == RECS_PARAM_WRITE ? RECS_KPARAM_WRITE : RECS_KPARAM_READ);
+        }
+        kp.push_back(k);
+        ++n_typed;
+        return RECS_OK;
+    };
+    for (const Param& p : s.params) {
+        int32_t st = RECS_OK;
+        if (p.op == RECS_PARAM_READ || p.op == RECS_PARAM_WRITE || p.op == RECS_PARAM_ENTITY) {
+            st = typed(p, false);
+        } else if (p.op == RECS_PARAM_COMMANDS) {
+            recs_gpu_kernel_param k;
+            k.component_id = 0;
+            k.elem_size = 0;
+            k.kind = RECS_KPARAM_COMMANDS;
+            k.type_name = nullptr;
+            kp.push_back(k);
+            s.decides_removals = true;
+        } else if (p.op == RECS_PARAM_QUERY_BEGIN) {
+            if (have_query) return app->fail(RECS_ERR_UNSUPPORTED, "kernel system: one nested Query per system");
+            have_query = true;
+            for (const Param& q : p.children)
+                if (q.op == RECS_PARAM_READ || q.op == RECS_PARAM_WRITE || q.op == RECS_PARAM_ENTITY)
+                    if ((st = typed(q, true)) != RECS_OK) break;
+        }
+        if (st != RECS_OK) return st;
+    }
+    int32_t st = recs_gpu_system_create_pair_kernel(app->gpu, name, source, acc_type, pair_fn, finish_fn, kp.data(),
+                                                    (uint32_t)kp.size(), uniform_type, uniform_bytes, &s.gpu_id);
+    if (st != RECS_OK) return gpu_fail(app, st);
+    params_accesses(s.params, &s.access);
+    app->systems.push_back(s);
+    if (out_index) *out_index = (uint32_t)app->systems.size() - 1;
     return RECS_OK;
 }
 

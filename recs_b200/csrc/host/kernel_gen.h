@@ -33,6 +33,16 @@ KernelPlan plan_kernel_system(const std::string& user_source, const std::string&
                               const std::vector<KernelParamSpec>& params, const std::string& uniform_type,
                               int force_direct);
 
+// Systems with a nested `Query<(...)>` parameter (crates/ecs/src/systems/mod.rs:915-934, 1028-1140; the reference's
+// `gravity` and `collision`): for every entity of the outer parameters the nested query is iterated IN QUERY ORDER and
+// folded into an accumulator --
+//     ACC acc = ACC();  for each query entity: pair(acc, outer reads..., query params...);  finish(outer params..., acc);
+// Query entities are staged through shared memory in tiles of 256; one thread per outer entity, so a body that adds
+// in the order it is called reproduces the reference's sequential `.sum()` bit for bit.
+KernelPlan plan_pair_kernel_system(const std::string& user_source, const std::string& acc_type, const std::string& pair_fn,
+                                   const std::string& finish_fn, const std::vector<KernelParamSpec>& outer,
+                                   const std::vector<KernelParamSpec>& query, const std::string& uniform_type);
+
 // NVRTC (dlopen'ed: libnvrtc.so.12) -> cubin for sm_100a.  Needs no GPU.  Returns false and fills `log`.
 bool compile_kernel_system(const std::string& source, std::vector<char>* cubin, std::string* log);
 

@@ -95,6 +95,11 @@ ECS_SYMBOLS = {
         [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32, _u32p],
     ),
     "recs_app_set_system_uniform": (C.c_int32, [_a, C.c_uint32, C.c_void_p, C.c_uint32]),
+    "recs_app_add_gpu_pair_kernel_system": (
+        C.c_int32,
+        [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p),
+         C.c_char_p, C.c_uint32, _u32p],
+    ),
     "recs_app_add_cpu_segment_system": (C.c_int32, [_a, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, CPU_SEGMENT_FN, C.c_void_p, _u32p]),
     "recs_app_set_executor": (C.c_int32, [_a, C.c_uint32]),
     "recs_fold_swap_removes": (C.c_int32, [C.c_uint64, _u32p, C.c_uint32, _u32p, _u32p, C.c_uint32, _u32p, C.POINTER(C.c_uint64)]),
@@ -491,6 +496,21 @@ class Application:
                 self._h, name.encode(), source.encode(), body.encode(), arr, n, names,
                 uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(idx)),
             "recs_app_add_gpu_kernel_system",
+        )
+        self.system_names.append(name)
+        return int(idx.value)
+
+    def add_gpu_pair_kernel_system(self, name: str, source: str, acc_type: str, pair_fn: str, finish_fn: str, params,
+                                   type_names: Sequence[str], uniform_type: str | None = None, uniform_bytes: int = 0) -> int:
+        """A generic GPU system with a nested Query; type_names: outer parameters first, then the query's, in token order."""
+        arr, n = tokens(params)
+        names = (C.c_char_p * max(len(type_names), 1))(*[t.encode() for t in type_names])
+        idx = C.c_uint32()
+        self._check(
+            lib.recs_app_add_gpu_pair_kernel_system(
+                self._h, name.encode(), source.encode(), acc_type.encode(), pair_fn.encode(), finish_fn.encode(), arr, n,
+                names, uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(idx)),
+            "recs_app_add_gpu_pair_kernel_system",
         )
         self.system_names.append(name)
         return int(idx.value)

@@ -142,6 +142,20 @@ class GpuContext:
         )
         return int(out.value)
 
+    def create_pair_kernel_system(self, name: str, source: str, acc_type: str, pair_fn: str, finish_fn: str, params,
+                                  uniform_type: str | None = None, uniform_bytes: int = 0) -> int:
+        """A generic system with a nested Query (recs_gpu_system_create_pair_kernel); nested-query parameters use
+        the kinds "query_read" / "query_entity"."""
+        arr = kernel_params(params)
+        out = C.c_uint32()
+        self._check(
+            lib.recs_gpu_system_create_pair_kernel(
+                self._ctx, name.encode(), source.encode(), acc_type.encode(), pair_fn.encode(), finish_fn.encode(), arr,
+                len(arr), uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(out)),
+            "recs_gpu_system_create_pair_kernel",
+        )
+        return int(out.value)
+
     def set_system_uniform(self, system: int, data: bytes) -> None:
         buf = C.create_string_buffer(bytes(data), len(data))
         self._check(lib.recs_gpu_system_set_uniform(self._ctx, system, buf, len(data)), "recs_gpu_system_set_uniform")
@@ -256,7 +270,8 @@ class GpuContext:
 
 
 _KPARAM_KINDS = {"read": _lib.KPARAM_READ, "write": _lib.KPARAM_WRITE, "entity": _lib.KPARAM_ENTITY,
-                 "commands": _lib.KPARAM_COMMANDS}
+                 "commands": _lib.KPARAM_COMMANDS, "query_read": _lib.KPARAM_QUERY_READ,
+                 "query_entity": _lib.KPARAM_QUERY_ENTITY}
 
 
 def kernel_params(params):
@@ -282,3 +297,14 @@ def compile_kernel_system(source: str, body: str, params, uniform_type: str | No
         source.encode(), body.encode(), arr, len(params), uniform_type.encode() if uniform_type else None,
         1 if force_direct else 0, log, len(log), C.byref(size), C.byref(chunk))
     return int(st), log.value.decode(errors="replace"), int(size.value), int(chunk.value)
+
+
+def compile_pair_kernel_system(source: str, acc_type: str, pair_fn: str, finish_fn: str, params, uniform_type: str | None = None):
+    """recs_gpu_pair_kernel_system_compile: (status, log, cubin_bytes); needs no GPU."""
+    arr = kernel_params(params)
+    log = C.create_string_buffer(16384)
+    size = C.c_uint64()
+    st = lib.recs_gpu_pair_kernel_system_compile(
+        source.encode(), acc_type.encode(), pair_fn.encode(), finish_fn.encode(), arr, len(params),
+        uniform_type.encode() if uniform_type else None, log, len(log), C.byref(size))
+    return int(st), log.value.decode(errors="replace"), int(size.value)

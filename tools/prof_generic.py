@@ -47,4 +47,27 @@ with GpuContext(device=0, use_cuda_graph=False) as ctx:
     for _ in range(100):
         ctx.run_system(frag, sync=False)
     out["frag_iter_26x20_us_per_run"] = ctx.timer_stop() * 10.0
+    # gravity written as a generic nested-query system (reference order, IEEE div + sqrt) against the hand-written kernel
+    sys.path.insert(0, "tests")
+    from test_pair_kernel_systems import GRAVITY, GRAVITY_PARAMS  # noqa: E402
+    from recs_b200 import scenes  # noqa: E402
+
+    for n in (16384, 65536):
+        pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 1)
+        arch = 100 + n
+        for comp, arr in ((1, pos), (2, mass), (4, acc)):
+            ctx.bind_column(arch, comp, arr)
+            ctx.upload(arch, comp)
+        gsys = ctx.create_pair_kernel_system("gravity", GRAVITY, "Total", "pair", "finish", GRAVITY_PARAMS)
+        hsys = ctx.create_system(_lib.SYS_NBODY_GRAVITY, [1, 4, 2])
+        for sid in (gsys, hsys):
+            ctx.set_archetypes(sid, [arch])
+            ctx.set_query_archetypes(sid, [arch])
+        for name, sid in (("generic_reference_order", gsys), ("hand_written", hsys)):
+            ctx.run_system(sid)
+            ctx.timer_start()
+            for _ in range(3):
+                ctx.run_system(sid, sync=False)
+            ms = ctx.timer_stop() / 3
+            out[f"gravity_{n}_{name}"] = {"ms": ms, "G_interactions_per_s": n * n / ms / 1e6}
 print(json.dumps(out))
