@@ -72,3 +72,19 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "liboracle" not in text and "nbody_oracle" not in text, f
+
+
+def test_only_tests_bench_and_smoke_touch_the_oracle():
+    """The oracle is test infrastructure: besides tests/ only bench.py (cpu_baseline / --impl reference) and
+    __graft_entry__.smoke() may import it; the package and the developer tools must not."""
+    allowed = {os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")}
+    for top in ("recs_b200", "tools", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, top)):
+            for f in files:
+                if f.endswith((".py", ".sh", ".cu", ".cuh", ".cpp", ".h")):
+                    text = open(os.path.join(dirpath, f)).read()
+                    assert "import oracle" not in text and "from oracle" not in text and "liboracle" not in text, os.path.join(dirpath, f)
+    for f in os.listdir(ROOT):
+        path = os.path.join(ROOT, f)
+        if f.endswith(".py") and path not in allowed:
+            assert "import oracle" not in open(path).read(), f

@@ -30,7 +30,7 @@ def test_sharded_ticks_match_oracle(bodies, ticks, mode):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), "tools/multi_gpu_check.py", str(bodies), str(ticks), mode]
+           "--master-port", str(port), "tests/tools/multi_gpu_check.py", str(bodies), str(ticks), mode]
     proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
 
@@ -46,6 +46,6 @@ def test_sharded_streaming_systems_need_no_exchange():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), "tools/multi_gpu_stream_check.py", "100003"]
+           "--master-port", str(port), "tests/tools/multi_gpu_stream_check.py", "100003"]
     proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0 and "MULTI_GPU_STREAM_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]

@@ -1,7 +1,7 @@
 """Multi-rank parity check of the index-sharded n-body path (run under torchrun, one rank per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port P \
-        tools/multi_gpu_check.py [bodies] [ticks]
+        tests/tools/multi_gpu_check.py [bodies] [ticks]
 """
 import os
 import sys

@@ -3,7 +3,7 @@ system over two archetypes.  Every rank must have updated exactly its own slice 
 against the oracle / numpy, and left the other rows alone (run under torchrun, one rank per GPU).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port P \
-        tools/multi_gpu_stream_check.py [entities]
+        tests/tools/multi_gpu_stream_check.py [entities]
 """
 import os
 import sys
