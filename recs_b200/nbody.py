@@ -62,3 +62,55 @@ class NBodyGpuApp:
 
     def tick(self, n: int = 1) -> None:
         self.ctx.tick(n)
+
+
+# `gravity` as a GENERIC nested-query system (recs_gpu_system_create_pair_kernel): crates/n-body/src/lib.rs:104-135 one
+# expression per line.  Folded in query order with IEEE division / square root and no FMA contraction, it reproduces
+# the reference's sequential f32 sum bit for bit -- the exactness cross-check of the hand-written kernel (about 7x
+# slower than it).
+REFERENCE_ORDER_GRAVITY_SOURCE = """
+struct Position { float x, y, z; };
+struct Mass { float m; };
+struct Acceleration { float x, y, z; };
+struct Total { float x, y, z; };                                   // Vector3::sum() starts from zero
+void pair(Total& total, const Position& position, const Position& body_position, const Mass& body_mass) {
+    const float tx = body_position.x - position.x;                 // let to_body = body_position.point - position.point;
+    const float ty = body_position.y - position.y;
+    const float tz = body_position.z - position.z;
+    const float distance_squared = (tx * tx + ty * ty) + tz * tz;  // to_body.magnitude2()
+    float cx = 0.0f, cy = 0.0f, cz = 0.0f;                         // if distance_squared <= f32::EPSILON { return zero }
+    if (!(distance_squared <= 1.1920929e-7f)) {
+        const float acceleration = (6.67e-11f * body_mass.m) / distance_squared;
+        const float scale = acceleration / sqrtf(distance_squared);  // normalize_to(m) = self * (m / self.magnitude())
+        cx = tx * scale; cy = ty * scale; cz = tz * scale;
+    }
+    total.x += cx; total.y += cy; total.z += cz;
+}
+void finish(const Position& position, Acceleration& acceleration, const Total& total) {
+    acceleration.x = total.x; acceleration.y = total.y; acceleration.z = total.z;   // *acceleration = total_acceleration
+}
+"""
+REFERENCE_ORDER_GRAVITY_PARAMS = [
+    (POSITION, 12, "read", "Position"),
+    (ACCELERATION, 12, "write", "Acceleration"),
+    (POSITION, 12, "query_read", "Position"),
+    (MASS, 4, "query_read", "Mass"),
+]
+
+
+def reference_order_gravity(ctx: GpuContext, outer_pos: np.ndarray, qpos: np.ndarray, qmass: np.ndarray,
+                            outer_archetype: int = 1001, query_archetype: int = 1002) -> np.ndarray:
+    """Accelerations of `outer_pos` rows against the bodies (qpos, qmass), computed on the device by the generic
+    reference-order system above.  Single-GPU contexts."""
+    acc = np.zeros_like(outer_pos)
+    for arch, comp, arr in ((outer_archetype, POSITION, outer_pos), (outer_archetype, ACCELERATION, acc),
+                            (query_archetype, POSITION, qpos), (query_archetype, MASS, qmass)):
+        ctx.bind_column(arch, comp, arr)
+        ctx.upload(arch, comp)
+    sid = ctx.create_pair_kernel_system("gravity_reference_order", REFERENCE_ORDER_GRAVITY_SOURCE, "Total", "pair", "finish",
+                                        REFERENCE_ORDER_GRAVITY_PARAMS)
+    ctx.set_archetypes(sid, [outer_archetype])
+    ctx.set_query_archetypes(sid, [query_archetype])
+    ctx.run_system(sid)
+    ctx.download(outer_archetype, ACCELERATION)
+    return acc

@@ -13,31 +13,9 @@ from recs_b200.gpu import compile_pair_kernel_system
 
 POS, MASS, VEL, ACC = 1, 2, 3, 4
 
-# crates/n-body/src/lib.rs:104-135, one expression per line of the Rust body
-GRAVITY = """
-struct Position { float x, y, z; };
-struct Mass { float m; };
-struct Acceleration { float x, y, z; };
-struct Total { float x, y, z; };                                   // Vector3::sum() starts from zero
-void pair(Total& total, const Position& position, const Position& body_position, const Mass& body_mass) {
-    const float tx = body_position.x - position.x;                 // let to_body = body_position.point - position.point;
-    const float ty = body_position.y - position.y;
-    const float tz = body_position.z - position.z;
-    const float distance_squared = (tx * tx + ty * ty) + tz * tz;  // to_body.magnitude2()
-    float cx = 0.0f, cy = 0.0f, cz = 0.0f;                         // if distance_squared <= f32::EPSILON { return zero }
-    if (!(distance_squared <= 1.1920929e-7f)) {
-        const float acceleration = (6.67e-11f * body_mass.m) / distance_squared;
-        const float scale = acceleration / sqrtf(distance_squared);  // normalize_to(m) = self * (m / self.magnitude())
-        cx = tx * scale; cy = ty * scale; cz = tz * scale;
-    }
-    total.x += cx; total.y += cy; total.z += cz;
-}
-void finish(const Position& position, Acceleration& acceleration, const Total& total) {
-    acceleration.x = total.x; acceleration.y = total.y; acceleration.z = total.z;   // *acceleration = total_acceleration
-}
-"""
-GRAVITY_PARAMS = [(POS, 12, "read", "Position"), (ACC, 12, "write", "Acceleration"), (POS, 12, "query_read", "Position"),
-                  (MASS, 4, "query_read", "Mass")]
+# crates/n-body/src/lib.rs:104-135, one expression per line of the Rust body (shipped as an example in recs_b200/nbody.py)
+from recs_b200.nbody import REFERENCE_ORDER_GRAVITY_PARAMS as GRAVITY_PARAMS  # noqa: E402
+from recs_b200.nbody import REFERENCE_ORDER_GRAVITY_SOURCE as GRAVITY  # noqa: E402
 
 # crates/n-body/examples/n_body_demo.rs:54-71
 COLLISION = """
