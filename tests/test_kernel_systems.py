@@ -369,3 +369,51 @@ def test_generic_removal_system_feeds_command_playback(gpu_ctx):
     h2d, d2h = gpu_ctx.transfer_bytes()
     assert d2h == n * 12 * 0 + alive * 12  # only the final sync came back
     app.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(10))
+def test_random_layouts_against_numpy(gpu_ctx, seed):
+    """Fuzz of the generated kernels: random element sizes (1 ... 40 bytes, odd ones included), 1-4 parameters, 1-5
+    archetypes with random row counts around the chunk boundaries (0, 1, 1023, 1024, 1025, ...).  Body: every Write
+    parameter gets its first and last byte bumped by a value that depends on the first byte of every Read parameter."""
+    rng = np.random.default_rng(1000 + seed)
+    n_params = int(rng.integers(1, 5))
+    sizes = [int(rng.choice([1, 2, 3, 4, 6, 8, 12, 16, 20, 36, 40])) for _ in range(n_params)]
+    kinds = ["write"] + [str(rng.choice(["read", "write"])) for _ in range(n_params - 1)]
+    counts = [int(rng.choice([0, 1, 31, 255, 1023, 1024, 1025, 2048, 3000])) for _ in range(int(rng.integers(1, 6)))]
+    src = "".join(f"struct T{i} {{ unsigned char b[{s}]; }};\n" for i, s in enumerate(sizes))
+    args = ", ".join(f"{'const ' if k == 'read' else ''}T{i}& p{i}" for i, k in enumerate(kinds))
+    reads = " + ".join([f"p{i}.b[0]" for i, k in enumerate(kinds) if k == "read"] or ["0"])
+    body = "".join(f"    p{i}.b[0] += (unsigned char)(1 + k); p{i}.b[{s - 1}] += (unsigned char)(2 + k);\n"
+                   for i, (s, k) in enumerate(zip(sizes, kinds)) if k == "write")
+    src += f"void f({args}) {{\n    const unsigned k = {reads};\n{body}}}\n"
+    ctx = gpu_ctx
+    data = {}
+    for a, c in enumerate(counts, start=1):
+        cols = []
+        for i, s in enumerate(sizes):
+            col = rng.integers(0, 256, size=(c, s), dtype=np.uint8)
+            cols.append(col)
+            ctx.bind_column(a, 50 + i, col, elem_size=s)
+            ctx.upload(a, 50 + i)
+        data[a] = (cols, [c_.copy() for c_ in cols])
+    params = [(50 + i, s, k, f"T{i}") for i, (s, k) in enumerate(zip(sizes, kinds))]
+    sid = ctx.create_kernel_system("fuzz", src, "f", params)
+    ctx.set_archetypes(sid, list(data))
+    ctx.run_system(sid)
+    for a, (cols, before) in data.items():
+        k = np.zeros(len(before[0]), np.uint32)
+        for i, kind in enumerate(kinds):
+            if kind == "read":
+                k += before[i][:, 0]
+        for i, (s, kind) in enumerate(zip(sizes, kinds)):
+            ctx.download(a, 50 + i)
+            want = before[i].copy()
+            if kind == "write":
+                if s == 1:
+                    want[:, 0] = (want[:, 0].astype(np.uint32) + 1 + k + 2 + k).astype(np.uint8)
+                else:
+                    want[:, 0] = (want[:, 0].astype(np.uint32) + 1 + k).astype(np.uint8)
+                    want[:, s - 1] = (want[:, s - 1].astype(np.uint32) + 2 + k).astype(np.uint8)
+            assert np.array_equal(cols[i], want), (seed, a, i, sizes, kinds, counts)
