@@ -10,7 +10,7 @@ HOSTCPP   := $(wildcard $(CSRC)/host/*.cpp)
 OBJ       := $(CU:.cu=.o) $(HOSTCPP:.cpp=.o)
 HDR       := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.h $(CSRC)/host/*.h) include/recs_gpu.h include/recs_ecs.h
 
-all: $(LIB) oracle
+all: $(LIB) oracle examples
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDR)
 	$(NVCC) $(NVCCFLAGS) -c $< -o $@
@@ -24,8 +24,13 @@ $(LIB): $(OBJ)
 oracle:
 	$(MAKE) -C oracle
 
+# plain-C host on the C ABI alone (no Python): proves the headers are C and the library links standalone
+examples: examples/nbody_bench
+examples/nbody_bench: examples/nbody_bench.c $(LIB) include/recs_gpu.h include/recs_ecs.h
+	$(CC) -O2 -Wall -Iinclude $< -o $@ -Lrecs_b200 -lrecs_gpu -Wl,-rpath,'$$ORIGIN/../recs_b200' -lm
+
 clean:
-	rm -f $(OBJ) $(LIB)
+	rm -f $(OBJ) $(LIB) examples/nbody_bench
 	$(MAKE) -C oracle clean
 
-.PHONY: all oracle clean
+.PHONY: all oracle examples clean
