@@ -5,6 +5,7 @@
 // columns and the workspace of the gravity system (pair-interleaved posm mirror, fragments).
 #include <cuda_runtime.h>
 #include <math.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -782,9 +783,17 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
     return RECS_OK;
 }
 
+// NVTX range per system run: the counterpart of the reference's `#[instrument]` tracing spans on its systems
+// (crates/n-body/src/lib.rs:87,95,104); free when no profiler is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 int32_t run_system_locked(recs_gpu_ctx* c, uint32_t id) {
     if (id >= c->systems.size()) return fail(c, RECS_ERR_INVALID_ARGUMENT, "unknown system id");
     System& s = c->systems[id];
+    NvtxRange range(s.name.c_str());
     switch (s.kind) {
         case RECS_SYS_NBODY_GRAVITY:
             return run_gravity(c, s);
@@ -865,6 +874,7 @@ bool try_fused_nbody(recs_gpu_ctx* c, size_t i, int32_t* st) {
 }
 
 int32_t run_tick_once(recs_gpu_ctx* c) {
+    NvtxRange range("tick");  // tracy_client::frame_mark() per tick in the reference (schedule/mod.rs:226-227)
     for (size_t i = 0; i < c->order.size(); ++i) {
         int32_t st = RECS_OK;
         if (try_fused_nbody(c, i, &st)) {
