@@ -167,6 +167,10 @@ struct recs_app {
     };
     std::map<uint32_t, EntityColumn> entity_columns;
     std::unique_ptr<WorkerPool> pool;  // null: Sequential executor
+    // GPU systems of the current tick that are prepared but not yet launched: consecutive GPU systems go to the
+    // context as ONE chain (recs_gpu_set_tick_order + recs_gpu_tick), so its fusions apply through the Application too
+    // (gravity -> movement -> acceleration in the reduce tail, wind -> gravity -> movement in one pass).
+    std::vector<uint32_t> gpu_chain;
     std::mutex command_mu;             // Commands may be recorded from several worker threads at once
     std::string error;
 
@@ -229,7 +233,17 @@ int32_t ensure_entities_on_device(recs_app* app, uint32_t arch) {
     return RECS_OK;
 }
 
-// Query membership of the system + residency of every column it touches, then the launch.
+// Launches the pending chain of GPU systems in order.  Called before anything on the host may look at or change a
+// column (CPU systems with component parameters, playback, sync_to_host) and at the end of every tick.
+int32_t flush_gpu_chain(recs_app* app) {
+    if (app->gpu_chain.empty()) return RECS_OK;
+    int32_t st = recs_gpu_set_tick_order(app->gpu, app->gpu_chain.data(), (uint32_t)app->gpu_chain.size());
+    if (st == RECS_OK) st = recs_gpu_tick(app->gpu, 1);
+    app->gpu_chain.clear();
+    return st == RECS_OK ? RECS_OK : gpu_fail(app, st);
+}
+
+// Query membership of the system + residency of every column it touches; the launch itself is deferred (gpu_chain).
 int32_t run_gpu_system(recs_app* app, AppSystem& s) {
     if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "GPU system registered on an application without a GPU context");
     std::vector<uint32_t> archs = params_archetypes(*app->world, s.params);
@@ -261,7 +275,7 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
     if (!qarchs.empty() || s.kind == RECS_SYS_NBODY_GRAVITY || has_query)
         if ((st = recs_gpu_system_set_query_archetypes(app->gpu, s.gpu_id, qarchs.data(), (uint32_t)qarchs.size())) != RECS_OK)
             return gpu_fail(app, st);
-    if ((st = recs_gpu_run_system(app->gpu, s.gpu_id, RECS_GPU_ASYNC)) != RECS_OK) return gpu_fail(app, st);
+    app->gpu_chain.push_back(s.gpu_id);  // launched by flush_gpu_chain
     if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION || s.decides_removals)
         app->gpu_removal_sources.push_back(std::make_pair((uint32_t)(&s - app->systems.data()), archs));
     for (const Param& p : s.params)
@@ -292,6 +306,10 @@ void release_borrows(recs_app* app, const AppSystem& s, uint32_t arch, const Par
 int32_t prepare_cpu_system(recs_app* app, AppSystem& s, CpuRun* run) {
     run->sys = &s;
     if (!params_controls_iteration(s.params)) return RECS_OK;
+    // the host is about to read or write columns: everything the device still owes must have been enqueued, or a
+    // later upload could overtake a pending kernel that has to see the old contents
+    int32_t flushed = flush_gpu_chain(app);
+    if (flushed != RECS_OK) return flushed;
     run->archs = params_archetypes(*app->world, s.params);
     for (uint32_t a : run->archs) {
         std::vector<void*> cols;
@@ -771,6 +789,7 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
     if (st != RECS_OK) return st;
     std::vector<uint32_t> batch(app->systems.size() + 1);
     for (uint32_t tick = 0; tick < n_ticks; ++tick) {
+        app->gpu_chain.clear();  // nothing survives a tick (or an error return)
         app->last_order.clear();
         app->last_batch.clear();
         uint32_t batch_no = 0;
@@ -818,6 +837,7 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
             for (uint32_t i = 0; i < got; ++i) recs_schedule_complete(app->schedule, batch[i]);
             ++batch_no;
         }
+        if ((st = flush_gpu_chain(app)) != RECS_OK) return st;
         // loop { runner.tick(); runner.playback_commands(); } (lib.rs:321-323)
         if ((st = playback_commands(app)) != RECS_OK) return st;
     }
@@ -866,6 +886,10 @@ int32_t recs_app_last_tick_order(recs_app* app, uint32_t* out_order, uint32_t* o
 
 int32_t recs_app_sync_to_host(recs_app* app) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (app->gpu) {
+        int32_t flushed = flush_gpu_chain(app);
+        if (flushed != RECS_OK) return flushed;
+    }
     for (auto& kv : app->mirror) {
         if (!kv.second.device_dirty) continue;
         int32_t st = recs_gpu_download(app->gpu, kv.first.first, kv.first.second);

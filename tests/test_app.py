@@ -244,3 +244,48 @@ def test_segment_systems_need_parallelizable_parameters():
     with pytest.raises(ecs.EcsError) as e:
         app.add_cpu_segment_system("bad", [("read", 7), ("query", [("write", 7)])], lambda *a: None)
     assert e.value.code == 11  # RECS_ERR_UNSUPPORTED
+
+
+@pytest.mark.gpu
+def test_application_hands_gpu_chains_to_the_context_as_one(gpu_ctx, nbody_oracle):
+    """Consecutive GPU systems of a tick reach the context as one chain, so its fusions apply behind the Application
+    too: the n-body tick is two launches (interaction kernel, reduce with the movement / acceleration tail) even with
+    a parameterless CPU system (`benchmark_system`, crates/ecs_bench_suite/src/recs/n_body.rs:59) in the schedule --
+    and a CPU system that touches a column splits the chain without changing the results."""
+    n, ticks = 2000, 6
+    for with_cpu_reader in (False, True):
+        gpu_ctx.reset_timing()
+        app = ecs.Application(gpu=gpu_ctx)
+        w = app.world
+        for c, dt, name in ((POS, F3, "Position"), (MASS, np.float32, "Mass"), (VEL, F3, "Velocity"), (ACC, F3, "Acceleration")):
+            w.register_component(c, dt, name)
+        pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 3)
+        ref = [a.copy() for a in (pos, mass, vel, acc)]
+        app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+        app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+        app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+        seen = []
+        app.add_cpu_system("benchmark_system", [], lambda a, c, cols: seen.append(1))
+        if with_cpu_reader:  # reads Acceleration on the host every tick: forces a flush + download mid-tick
+            app.add_cpu_system("probe", [("read", ACC)], lambda a, c, cols: seen.append(float(_f32(cols[0], c, 3)[0])))
+        w.create_entities(n, {POS: pos, MASS: mass, VEL: vel, ACC: acc})
+        app.run(1)
+        before = gpu_ctx.timing()["kernel_launches"]
+        app.run(ticks - 1)
+        per_tick = (gpu_ctx.timing()["kernel_launches"] - before) / (ticks - 1)
+        if not with_cpu_reader:
+            assert per_tick == 2
+        app.sync_to_host()
+        # the extra reader of Acceleration changes the DAG: follow whatever order the schedule produced
+        from oracle.nbody import SYS_ACCELERATION, SYS_GRAVITY, SYS_MOVEMENT
+
+        code = {"gravity": SYS_GRAVITY, "movement": SYS_MOVEMENT, "acceleration": SYS_ACCELERATION}
+        order, _ = app.last_tick_order()
+        names = [app.system_names[i] for i in order if app.system_names[i] in code]
+        if not with_cpu_reader:
+            assert names == ["gravity", "movement", "acceleration"]
+        nbody_oracle.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks, order=tuple(code[x] for x in names))
+        assert rel_err_rows(w.column(1, POS)[:n], ref[0], floor=1.0).max() <= 1e-4, names
+        assert rel_err_rows(w.column(1, VEL)[:n], ref[2], floor=1.0).max() <= 1e-4, names
+        assert rel_err_rows(w.column(1, ACC)[:n], ref[3]).max() <= 1e-3, names
+        app.close()
