@@ -413,7 +413,9 @@ def run_gpu_arm(args) -> None:
 
     # ---- secondary configs (streaming systems), reported as extras ---------------------------------
     extras = {}
-    if not args.no_extras and rank == 0:
+    if world > 1:
+        extras = {"skipped": "the streaming configs are reported by the N=1 run (a sharded context streams only its own slice)"}
+    elif not args.no_extras and rank == 0:
         try:
             extras = streaming_extras(ctx)
         except Exception as exc:  # extras never invalidate the headline line
@@ -421,7 +423,7 @@ def run_gpu_arm(args) -> None:
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------------
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the contract: rank 0 at N=1 only
         threads = host_threads()
         rate, rows, sec, _ = cpu_sample_rate(n, 12.0, threads)
         cpu = {
