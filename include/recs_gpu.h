@@ -312,18 +312,44 @@ int32_t recs_gpu_set_wind_direction(recs_gpu_ctx* ctx, const float xyz[3]);
 int32_t recs_gpu_get_wind_direction(recs_gpu_ctx* ctx, float xyz[3]);
 
 /* ------------------------------------------------------------------------------------------
- * Index-sharded multi-GPU n-body (one process per GPU).  Rank r owns rows
- * [r*N/R, (r+1)*N/R) of the body archetype; positions are exchanged every step with an NCCL
- * all-gather on a second stream, overlapped with the local j-tiles of gravity.
+ * Index-sharded multi-GPU n-body (one process per GPU).  Rank r owns one contiguous slice of the
+ * rows of the body archetype (recs_gpu_shard_plan) and needs every body's position and mass for
+ * its nested query (crates/n-body/src/lib.rs:104-135).  Two exchanges of the 16-byte
+ * {position, G*m} mirror entries:
+ *
+ *  (a) peer push (default once recs_gpu_exchange_import succeeded): every rank's mirror lives in
+ *      one device allocation that all ranks map through CUDA IPC.  The integration tail of the
+ *      tick (or the pack kernel after a host upload) stores a rank's refreshed rows straight into
+ *      EVERY rank's next mirror buffer over NVLink and then raises a generation flag there
+ *      (release, system scope); the next tick's interaction kernel -- ONE persistent launch per
+ *      tick -- starts on its own tiles at once and acquires a peer's flag only before the first
+ *      tile of that peer's slice.  No collective kernel competes for SMs, nothing is exposed.
+ *  (b) NCCL: ncclAllGather of the mirror on a second stream between an own-tile launch and a
+ *      launch over the other ranks' tiles (needs only recs_gpu_comm_init).
+ *
+ * The result of a row does not depend on the exchange, the rank count or the grid: tile sums are
+ * added in a fixed tree (chunks of consecutive tiles, then chunks in ascending order).
  * ---------------------------------------------------------------------------------------- */
 #define RECS_GPU_NCCL_ID_BYTES 128
 int32_t recs_gpu_comm_get_unique_id(recs_gpu_ctx* ctx, uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]);
 int32_t recs_gpu_comm_init(recs_gpu_ctx* ctx, const uint8_t id_bytes[RECS_GPU_NCCL_ID_BYTES]);
+/* Peer push, step 1 (every rank): allocates the exchange buffers for up to `max_bodies` bodies
+ * and returns the CUDA IPC handle of the allocation.  The host distributes the handles (any
+ * channel: the one that carried the NCCL id will do). */
+#define RECS_GPU_IPC_HANDLE_BYTES 64
+int32_t recs_gpu_exchange_export(recs_gpu_ctx* ctx, uint64_t max_bodies,
+                                 uint8_t handle_bytes[RECS_GPU_IPC_HANDLE_BYTES]);
+/* Peer push, step 2 (every rank): `handles` = world_size handles in rank order (the own one is
+ * ignored).  Maps every peer's buffers (cudaIpcOpenMemHandle, peer access over NVLink). */
+int32_t recs_gpu_exchange_import(recs_gpu_ctx* ctx, const uint8_t* handles, uint32_t n_handles);
+/* 0 = single GPU, 1 = NCCL all-gather, 2 = peer push. */
+int32_t recs_gpu_exchange_mode(recs_gpu_ctx* ctx);
 /* Rows [row_begin, row_end) of gravity / movement / acceleration that this rank computes. */
 int32_t recs_gpu_shard_rows(recs_gpu_ctx* ctx, uint64_t n_rows, uint64_t* row_begin,
                             uint64_t* row_end);
 /* The same partition as a pure function (no device needed): every rank owns one slice of
- * `*slice_rows` rows of the tile-padded body range; the all-gather moves 16 bytes per slice row. */
+ * `*slice_rows` rows of the padded body range (whole chunks of tiles); the exchange moves 16 bytes
+ * per slice row and peer. */
 int32_t recs_gpu_shard_plan(uint64_t n_rows, int32_t rank, int32_t world_size, uint64_t* row_begin,
                             uint64_t* row_end, uint64_t* slice_rows);
 

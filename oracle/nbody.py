@@ -36,6 +36,8 @@ class NBodyOracle:
         lib.oracle_gravity_rows_f64.restype = None
         lib.oracle_gravity_sample.argtypes = [_f32p, _u64p, z, _f32p, _f32p, z, C.c_void_p, C.c_void_p]
         lib.oracle_gravity_sample.restype = None
+        lib.oracle_gravity_sample_mt.argtypes = [_f32p, _u64p, z, _f32p, _f32p, z, C.c_void_p, C.c_void_p, C.c_int]
+        lib.oracle_gravity_sample_mt.restype = None
         lib.oracle_axpy_rows.argtypes = [_f32p, _f32p, C.c_float, z, z]
         lib.oracle_axpy_rows.restype = None
         lib.oracle_add_rows.argtypes = [_f32p, _f32p, z, z]
@@ -74,12 +76,16 @@ class NBodyOracle:
         self.lib.oracle_gravity_rows_f64(pos, acc, b, e, pos, mass, pos.shape[0])
         return acc
 
-    def gravity_sample(self, pos, mass, rows, f64=True):
+    def gravity_sample(self, pos, mass, rows, f64=True, threads=None):
+        """Reference-order f32 (and f64) accelerations of the sampled `rows` against all bodies; the rows are
+        spread over `threads` host threads (default: all), which does not change a row's result."""
         rows = np.ascontiguousarray(rows, dtype=np.uint64)
         out32 = np.zeros((rows.size, 3), dtype=np.float32)
         out64 = np.zeros((rows.size, 3), dtype=np.float64) if f64 else None
-        self.lib.oracle_gravity_sample(
-            pos, rows, rows.size, pos, mass, pos.shape[0], out32.ctypes.data, out64.ctypes.data if f64 else None
+        if threads is None:
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.lib.oracle_gravity_sample_mt(
+            pos, rows, rows.size, pos, mass, pos.shape[0], out32.ctypes.data, out64.ctypes.data if f64 else None, int(threads)
         )
         return out32, out64
 

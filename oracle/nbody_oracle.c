@@ -118,6 +118,39 @@ ORACLE_API void oracle_gravity_sample(const float* pos, const uint64_t* rows, si
     }
 }
 
+/* The same sampled rows spread over `n_threads` host threads (per-row results do not depend on it). */
+typedef struct {
+    const float* pos;
+    const uint64_t* rows;
+    size_t begin, end;
+    const float *qpos, *qmass;
+    size_t nq;
+    float* out_f32;
+    double* out_f64;
+} sample_job_t;
+static void* sample_worker(void* arg) {
+    const sample_job_t* j = (const sample_job_t*)arg;
+    oracle_gravity_sample(j->pos, j->rows + j->begin, j->end - j->begin, j->qpos, j->qmass, j->nq,
+                          j->out_f32 ? j->out_f32 + 3 * j->begin : NULL, j->out_f64 ? j->out_f64 + 3 * j->begin : NULL);
+    return NULL;
+}
+ORACLE_API void oracle_gravity_sample_mt(const float* pos, const uint64_t* rows, size_t n_rows, const float* qpos,
+                                         const float* qmass, size_t nq, float* out_f32, double* out_f64, int n_threads) {
+    if (n_threads < 1) n_threads = 1;
+    if ((size_t)n_threads > n_rows) n_threads = n_rows ? (int)n_rows : 1;
+    pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+    sample_job_t* jobs = (sample_job_t*)malloc(sizeof(sample_job_t) * (size_t)n_threads);
+    for (int t = 0; t < n_threads; ++t) {
+        sample_job_t j = {pos, rows, n_rows * (size_t)t / (size_t)n_threads, n_rows * (size_t)(t + 1) / (size_t)n_threads,
+                          qpos, qmass, nq, out_f32, out_f64};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, sample_worker, &jobs[t]);
+    }
+    for (int t = 0; t < n_threads; ++t) pthread_join(th[t], NULL);
+    free(jobs);
+    free(th);
+}
+
 /* ---- movement / acceleration: crates/n-body/src/lib.rs:87-102 ---------------------------- */
 /* position.point += velocity * FIXED_TIME_STEP  (mul, then add; componentwise) */
 ORACLE_API void oracle_axpy_rows(float* y, const float* x, float a, size_t row_begin, size_t row_end) {

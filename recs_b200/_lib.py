@@ -54,6 +54,7 @@ ENTITY_COMPONENT = 0xFFFFFFFFFFFFFFFE
 GPU_ASYNC = 0
 GPU_SYNC = 1
 NCCL_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 MAX_ACCESSES = 8
 
 
@@ -159,6 +160,9 @@ GPU_SYMBOLS = {
     "recs_gpu_get_wind_direction": (C.c_int32, [_ctx, C.POINTER(C.c_float)]),
     "recs_gpu_comm_get_unique_id": (C.c_int32, [_ctx, C.POINTER(C.c_uint8)]),
     "recs_gpu_comm_init": (C.c_int32, [_ctx, C.POINTER(C.c_uint8)]),
+    "recs_gpu_exchange_export": (C.c_int32, [_ctx, C.c_uint64, C.POINTER(C.c_uint8)]),
+    "recs_gpu_exchange_import": (C.c_int32, [_ctx, C.POINTER(C.c_uint8), C.c_uint32]),
+    "recs_gpu_exchange_mode": (C.c_int32, [_ctx]),
     "recs_gpu_shard_rows": (C.c_int32, [_ctx, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_shard_plan": (C.c_int32, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_enable_timing": (C.c_int32, [_ctx, C.c_int32]),

@@ -131,6 +131,25 @@ struct recs_gpu_ctx {
     std::vector<std::pair<ColKey, uint64_t>> posm_sources;  // (column, version) the mirror was packed from
     float4* frags = nullptr;
     size_t frags_cap = 0;
+    int grav_grid_forced = 0;           // RECS_GPU_GRAVITY_GRID: test knob (results must not depend on it)
+    int emulate_ranks = 0, emulate_rank = 0;  // RECS_GPU_GRAVITY_EMULATE_RANK="R,r": rank r's phase split on one GPU (test knob)
+
+    // sharded runs, peer-pushed mirror: one allocation [mirror buffer 0 | mirror buffer 1 | flags | done counter],
+    // mapped into every rank through CUDA IPC (recs_gpu_exchange_export / _import)
+    struct Exchange {
+        unsigned char* base = nullptr;
+        uint64_t cap_bodies = 0;        // bodies per mirror buffer
+        bool imported = false;
+        unsigned char* peer[kGravMaxPeers] = {nullptr};  // every rank's base in this process (own rank: base)
+        uint32_t gen = 0;               // newest generation pushed by this rank
+        float* buffer(int rank_slot, uint32_t g) const { return reinterpret_cast<float*>(peer[rank_slot] + (size_t)(g & 1u) * cap_bodies * 16); }
+        uint32_t* flags(int rank_slot) const { return reinterpret_cast<uint32_t*>(peer[rank_slot] + 2 * (size_t)cap_bodies * 16); }
+        uint32_t* done_counter() const { return reinterpret_cast<uint32_t*>(base + 2 * (size_t)cap_bodies * 16 + 256); }
+        size_t bytes() const { return 2 * (size_t)cap_bodies * 16 + 512; }
+    } xchg;
+    uint32_t* dev_error_host = nullptr;  // mapped pinned word the kernels raise when a peer wait timed out
+    uint32_t* dev_error = nullptr;
+    bool exchange_nccl_forced = false;   // RECS_GPU_EXCHANGE=nccl
 
     // rain
     float wind[3] = {1.f, 0.f, 0.f};
@@ -139,6 +158,7 @@ struct recs_gpu_ctx {
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_epoch = ~0ull;
     bool capturing = false;
+    bool graph_elided_pack = false;  // the captured tick found the mirror current and holds no pack kernel
 
     // timing
     bool timing = false;
@@ -268,25 +288,34 @@ int32_t ensure(recs_gpu_ctx* c, T** p, size_t* cap, size_t bytes) {
     return RECS_OK;
 }
 
-// Equal slices of the tile-padded body range, one per rank.
-void shard_rows(const recs_gpu_config& cfg, uint64_t n, uint64_t* slice, uint64_t* rb, uint64_t* re) {
-    const uint64_t R = cfg.world_size > 0 ? (uint64_t)cfg.world_size : 1;
-    const uint64_t quantum = (uint64_t)kGravTile * R;
-    const uint64_t padded = (n + quantum - 1) / quantum * quantum;
-    const uint64_t s = padded / R;
+// Equal slices of the padded body range, one per rank: whole chunks of the summation tree (kernels.cuh), so a rank's
+// own tiles and the other ranks' tiles are two runs of whole chunks and the result does not depend on the rank count.
+void shard_rows_for(int rank, int world_size, uint64_t n, uint64_t* slice, uint64_t* rb, uint64_t* re) {
+    const uint64_t R = world_size > 0 ? (uint64_t)world_size : 1;
+    const uint64_t K = gravity_chunk_tiles(n);
+    const uint64_t tiles = (n + kGravTile - 1) / kGravTile;
+    uint64_t slice_tiles = ((tiles + R - 1) / R + K - 1) / K * K;
+    if (slice_tiles == 0) slice_tiles = K;
+    const uint64_t s = slice_tiles * kGravTile;
     *slice = s;
-    uint64_t b = s * (uint64_t)cfg.rank, e = b + s;
+    uint64_t b = s * (uint64_t)rank, e = b + s;
     if (b > n) b = n;
     if (e > n) e = n;
     *rb = b;
     *re = e;
 }
+void shard_rows(const recs_gpu_config& cfg, uint64_t n, uint64_t* slice, uint64_t* rb, uint64_t* re) {
+    shard_rows_for(cfg.rank, cfg.world_size, n, slice, rb, re);
+}
+
+bool posm_is_current(recs_gpu_ctx* c);
 
 // ---- systems -----------------------------------------------------------------------------------
 // `movement` / `acceleration`: the systems fused into the tail of the reduce kernel, or null.
 int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, System* acceleration = nullptr) {
     const uint64_t POS = sys.comp[0], ACC = sys.comp[1], MASS = sys.comp[2];
     const bool sharded = c->cfg.world_size > 1;
+    const bool p2p = sharded && c->xchg.imported && !c->exchange_nccl_forced;
     // 1. the nested Query<(Read<Position>, Read<Mass>)>: concatenation of its archetypes
     std::vector<std::pair<Column*, Column*>> q;
     uint64_t total_j = 0;
@@ -305,15 +334,26 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     if (sharded && (sys.qarchs.size() != 1 || sys.archs.size() != 1 || sys.qarchs[0] != sys.archs[0]))
         return fail(c, RECS_ERR_UNSUPPORTED, "sharded gravity needs exactly one body archetype");
     if (total_j >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 bodies");
+    if (sharded && c->cfg.world_size > kGravMaxPeers) return fail(c, RECS_ERR_UNSUPPORTED, "more than 16 ranks");
 
+    // the mirror's tile layout: whole chunks of the summation tree, equal slices per rank
+    const int lay_R = sharded ? c->cfg.world_size : (c->emulate_ranks > 1 ? c->emulate_ranks : 1);
+    const int lay_r = sharded ? c->cfg.rank : (c->emulate_ranks > 1 ? c->emulate_rank : 0);
     uint64_t slice = 0, rb = 0, re = 0;
-    shard_rows(c->cfg, total_j, &slice, &rb, &re);
-    const uint64_t n_jpad = sharded ? slice * (uint64_t)c->cfg.world_size
-                                    : (total_j + kGravTile - 1) / kGravTile * kGravTile;
+    shard_rows_for(lay_r, lay_R, total_j, &slice, &rb, &re);
+    if (!sharded) rb = 0, re = total_j;  // (an emulated rank still computes every row)
+    const uint32_t K = gravity_chunk_tiles(total_j);
+    const uint64_t n_jpad = slice * (uint64_t)lay_R;
     const uint32_t n_tiles = (uint32_t)(n_jpad / kGravTile);
+    const uint32_t slice_tiles = (uint32_t)(slice / kGravTile);
 
-    int32_t st = ensure(c, &c->posm, &c->posm_cap, std::max<size_t>(n_jpad, kGravTile) * 16);
-    if (st != RECS_OK) return st;
+    int32_t st = RECS_OK;
+    if (p2p) {
+        if (n_jpad > c->xchg.cap_bodies)
+            return fail(c, RECS_ERR_SIZE_MISMATCH, "the exported exchange buffer is smaller than the body count: export / import again");
+    } else if ((st = ensure(c, &c->posm, &c->posm_cap, std::max<size_t>(n_jpad, kGravTile) * 16)) != RECS_OK) {
+        return st;
+    }
 
     // kernel shape by outer-row count (profiles/r01_gravity_small_n_sweep.txt, r01_gravity_variant_sweep5.txt):
     // small i-blocks give the stream-K split more units, and below 16 384 rows the redo of the tile that holds a
@@ -331,37 +371,57 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     const bool scaled = gravity_variant(variant).scaled;
     const float pscale = scaled ? kGravPosScale : 1.f;
 
+    auto peer_push = [&](uint32_t gen) {
+        PeerPush pp = no_peer_push();
+        pp.n = (uint32_t)c->cfg.world_size;
+        pp.gen = gen;
+        for (int r = 0; r < c->cfg.world_size; ++r) {
+            pp.posm[r] = c->xchg.buffer(r, gen);
+            pp.flag[r] = c->xchg.flags(r) + c->cfg.rank;
+        }
+        pp.local_flags = c->xchg.flags(c->cfg.rank);
+        pp.done_counter = c->xchg.done_counter();
+        pp.error = c->dev_error;
+        return pp;
+    };
+
     // 2. refresh the posm mirror if any source column changed since it was packed
     const bool dirty = sources != c->posm_sources || c->posm_bodies != n_jpad || c->posm_scaled != scaled;
     if (dirty) {
         Timed t(c, T_PACK);
         if (!sharded) {
             uint64_t off = 0;
-            for (auto& pm : q) {
-                RECS_CUDA(c, launch_pack_posm((const float*)pm.first->dev, (const float*)pm.second->dev,
-                                              c->cfg.nbody_g, c->posm, 0, pm.first->count, off, pscale, c->stream));
+            for (size_t qi = 0; qi < q.size(); ++qi) {
+                auto& pm = q[qi];
+                const uint64_t pad = qi + 1 == q.size() ? n_jpad - total_j : 0;
+                RECS_CUDA(c, launch_pack_posm((const float*)pm.first->dev, (const float*)pm.second->dev, c->cfg.nbody_g,
+                                              c->posm, 0, pm.first->count, pad, off, pscale, no_peer_push(), c->stream));
                 off += pm.first->count;
-                c->kernel_launches += pm.first->count ? 1 : 0;
+                c->kernel_launches += pm.first->count + pad ? 1 : 0;
             }
-            RECS_CUDA(c, launch_pad_posm(c->posm, total_j, n_jpad, c->stream));
-            c->kernel_launches += n_jpad > total_j ? 1 : 0;
         } else {
-            // own rows only; the other slices arrive through the all-gather below
-            RECS_CUDA(c, launch_pack_posm((const float*)q[0].first->dev, (const float*)q[0].second->dev,
-                                          c->cfg.nbody_g, c->posm, rb, re - rb, rb, pscale, c->stream));
+            // own rows (and the null bodies that fill the slice) only: the other slices arrive from their owners
             const uint64_t own_end = slice * ((uint64_t)c->cfg.rank + 1);
-            RECS_CUDA(c, launch_pad_posm(c->posm, re, own_end, c->stream));
-            c->kernel_launches += (re > rb ? 1 : 0) + (own_end > re ? 1 : 0);
+            const uint64_t own_begin = slice * (uint64_t)c->cfg.rank;
+            const PeerPush pp = p2p ? peer_push(++c->xchg.gen) : no_peer_push();
+            RECS_CUDA(c, launch_pack_posm((const float*)q[0].first->dev, (const float*)q[0].second->dev, c->cfg.nbody_g,
+                                          c->posm, rb, re - rb, own_end - std::max(re, own_begin), std::max(rb, own_begin),
+                                          pscale, pp, c->stream));
+            c->kernel_launches++;
         }
         c->posm_sources = sources;
         c->posm_bodies = n_jpad;
         c->posm_scaled = scaled;
+    } else if (c->capturing) {
+        c->graph_elided_pack = true;
     }
-    if (sharded && !c->comm) return fail(c, RECS_ERR_NCCL, "world_size > 1 but recs_gpu_comm_init was not called");
-    // The all-gather is enqueued further down, AFTER launch A: an NCCL kernel that is resident
+    if (sharded && !p2p && !c->comm)
+        return fail(c, RECS_ERR_NCCL, "world_size > 1 but neither recs_gpu_exchange_import nor recs_gpu_comm_init was called");
+    const float* posm_now = p2p ? c->xchg.buffer(c->cfg.rank, c->xchg.gen) : c->posm;
+    // NCCL exchange: the all-gather is enqueued AFTER the own-tile launch: an NCCL kernel that is resident
     // while it waits for a late peer would keep persistent gravity CTAs off its SMs.
     auto enqueue_gather = [&]() -> int32_t {
-        RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));  // after launch A (and the pack before it)
+        RECS_CUDA(c, cudaEventRecord(c->ev_pack, c->stream));  // after the own-tile launch (and the pack before it)
         RECS_CUDA(c, cudaStreamWaitEvent(c->comm_stream, c->ev_pack, 0));
         float* send = c->posm + (size_t)slice * (uint64_t)c->cfg.rank * 4;
         TimedSpan span;
@@ -382,77 +442,120 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         return RECS_OK;
     };
 
-    // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes
+    // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes.  Every archetype's
+    //    interaction launch comes before any reduce: the fused tail of one archetype moves bodies that the nested
+    //    query of the next one still has to see where they were (gravity reads Position, movement writes it).
     const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm[variant]);
     const uint32_t kGravRows = (uint32_t)gravity_variant(variant).rows();
-    for (uint32_t a : sys.archs) {
+    struct Outer {
+        uint32_t arch;
         Column *p, *acc;
-        if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
-        if ((st = need_column(c, a, ACC, 12, &acc)) != RECS_OK) return st;
-        if ((st = same_count(c, p, acc)) != RECS_OK) return st;
-        uint64_t row_begin = 0, row_count = p->count;
-        if (sharded) {
-            row_begin = rb;
-            row_count = re - rb;
-        }
-        if (row_count == 0) continue;
-        if (row_count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
-        const uint32_t n_iblocks = (uint32_t)((row_count + kGravRows - 1) / kGravRows);
-        if ((uint64_t)n_iblocks * n_tiles >= (1ull << 32))
+        uint64_t row_begin, row_count;
+        GravityWork work;
+        size_t frag_slot_base;
+        uint32_t self_offset;
+    };
+    std::vector<Outer> outers;
+    size_t frag_slots = 0;
+    for (uint32_t a : sys.archs) {
+        Outer o;
+        o.arch = a;
+        if ((st = need_column(c, a, POS, 12, &o.p)) != RECS_OK) return st;
+        if ((st = need_column(c, a, ACC, 12, &o.acc)) != RECS_OK) return st;
+        if ((st = same_count(c, o.p, o.acc)) != RECS_OK) return st;
+        o.row_begin = sharded ? rb : 0;
+        o.row_count = sharded ? re - rb : o.p->count;
+        if (o.row_count == 0 && !sharded) continue;
+        if (o.row_count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
+        GravityWork& w = o.work;
+        memset(&w, 0, sizeof w);
+        w.n_iblocks = (uint32_t)((o.row_count + kGravRows - 1) / kGravRows);
+        w.n_tiles_total = n_tiles;
+        w.chunk_tiles = K;
+        if ((uint64_t)w.n_iblocks * n_tiles >= (1ull << 32))
             return fail(c, RECS_ERR_UNSUPPORTED, "work-unit count overflows 32 bits");
-
-        GravityReduceArgs ra;
-        memset(&ra, 0, sizeof ra);
-        ra.acc = (float*)acc->dev;
-        ra.row_begin = (uint32_t)row_begin;
-        ra.row_count = (uint32_t)row_count;
-        ra.iblock_rows = kGravRows;
-        // launch A: local tiles (all tiles when not sharded); launch B: the other ranks' tiles
-        const uint32_t own_tiles = sharded ? (uint32_t)(slice / kGravTile) : n_tiles;
-        const uint32_t own_off = sharded ? own_tiles * (uint32_t)c->cfg.rank : 0;
-        uint32_t frag_base = 0;
-        for (int l = 0; l < (sharded ? 2 : 1); ++l) {
-            GravityLaunch L;
-            L.n_iblocks = n_iblocks;
-            L.n_vtiles = l == 0 ? own_tiles : n_tiles - own_tiles;
-            L.tile_offset = l == 0 ? own_off : (own_off + own_tiles) % n_tiles;
-            const uint64_t units = (uint64_t)L.n_iblocks * L.n_vtiles;
-            L.grid = (uint32_t)std::min<uint64_t>(slots, std::max<uint64_t>(units, 1));
-            L.frag_base = frag_base;
-            frag_base += gravity_frag_slots(L);
-            ra.launch[l] = L;
+        if (lay_R > 1) {
+            // phase 0: the rank's own slice; phase 1: the other ranks' slices, starting behind the own one
+            w.n_phases = 2;
+            w.phase[0].n_vtiles = slice_tiles;
+            w.phase[0].tile_offset = slice_tiles * (uint32_t)lay_r;
+            w.phase[1].n_vtiles = n_tiles - slice_tiles;
+            w.phase[1].tile_offset = (w.phase[0].tile_offset + slice_tiles) % n_tiles;
+        } else {
+            w.n_phases = 1;
+            w.phase[0].n_vtiles = n_tiles;
+            w.phase[0].tile_offset = 0;
         }
-        ra.n_launches = sharded ? 2 : 1;
-        st = ensure(c, &c->frags, &c->frags_cap, (size_t)frag_base * kGravRows * sizeof(float4));
-        if (st != RECS_OK) return st;
-        ra.frags = c->frags;
+        uint64_t max_units = 1;
+        for (uint32_t ph = 0; ph < w.n_phases; ++ph) max_units = std::max<uint64_t>(max_units, (uint64_t)w.n_iblocks * w.phase[ph].n_vtiles);
+        w.grid = (uint32_t)std::min<uint64_t>(slots, max_units);
+        if (c->grav_grid_forced > 0) w.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->grav_grid_forced, max_units);
+        o.frag_slot_base = frag_slots;
+        frag_slots += gravity_assign_frag_slots(w);
+        // mirror index of outer row 0 when this archetype is part of the nested query
+        o.self_offset = 0xffffffffu;
+        uint64_t off = 0;
+        for (size_t qi = 0; qi < sys.qarchs.size(); ++qi) {
+            if (sys.qarchs[qi] == a) {
+                o.self_offset = (uint32_t)off;
+                break;
+            }
+            off += q[qi].first->count;
+        }
+        outers.push_back(o);
+    }
+    if ((st = ensure(c, &c->frags, &c->frags_cap, std::max<size_t>(frag_slots, 1) * kGravRows * sizeof(float4))) != RECS_OK) return st;
 
-        for (uint32_t l = 0; l < ra.n_launches; ++l) {
-            if (l == 1) {
+    for (Outer& o : outers) {
+        GravityArgs ga;
+        memset(&ga, 0, sizeof ga);
+        ga.posm = reinterpret_cast<const float4*>(posm_now);
+        ga.ipos = (const float*)o.p->dev;
+        ga.frags = c->frags + o.frag_slot_base * kGravRows;
+        ga.row_begin = (uint32_t)o.row_begin;
+        ga.row_count = (uint32_t)o.row_count;
+        ga.eps = c->cfg.nbody_epsilon;
+        ga.self_offset = o.self_offset;
+        ga.work = o.work;
+        ga.variant = variant;
+        ga.tiles_per_rank = slice_tiles;
+        ga.own_rank = (uint32_t)lay_r;
+        ga.error = c->dev_error;
+        if (p2p) {
+            ga.flags = c->xchg.flags(c->cfg.rank);
+            ga.wait_gen = c->xchg.gen;
+        }
+        // one launch for all phases, except with the NCCL exchange: own tiles, all-gather, the other tiles
+        const bool split = sharded && !p2p;
+        for (uint32_t l = 0; l < (split ? 2u : 1u); ++l) {
+            ga.phase_begin = split ? l : 0;
+            ga.phase_end = split ? l + 1 : o.work.n_phases;
+            if (split && l == 1) {
                 if ((st = enqueue_gather()) != RECS_OK) return st;
                 RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
             }
-            GravityArgs ga;
-            ga.posm = reinterpret_cast<const float4*>(c->posm);
-            ga.ipos = (const float*)p->dev;
-            ga.frags = c->frags;
-            ga.row_begin = (uint32_t)row_begin;
-            ga.row_count = (uint32_t)row_count;
-            ga.n_tiles_total = n_tiles;
-            ga.eps = c->cfg.nbody_epsilon;
-            ga.launch = ra.launch[l];
-            ga.variant = variant;
-            if (ga.launch.n_vtiles == 0) continue;
+            if (o.row_count == 0) continue;
             Timed t(c, T_GRAVITY);
             RECS_CUDA(c, launch_gravity(ga, c->stream));
             c->kernel_launches++;
             c->gravity_launches++;
         }
+    }
+    // the tail may be fused when it cannot disturb a later read of this tick: every interaction launch is enqueued
+    for (Outer& o : outers) {
+        GravityReduceArgs ra;
+        memset(&ra, 0, sizeof ra);
+        ra.frags = c->frags + o.frag_slot_base * kGravRows;
+        ra.acc = (float*)o.acc->dev;
+        ra.row_begin = (uint32_t)o.row_begin;
+        ra.row_count = (uint32_t)o.row_count;
+        ra.iblock_rows = kGravRows;
+        ra.work = o.work;
         Column *tail_pos = nullptr, *tail_vel = nullptr;
         if (movement) {
             Column* mass_col = nullptr;
-            if ((st = need_column(c, a, movement->comp[0], 12, &tail_pos)) != RECS_OK) return st;
-            if ((st = need_column(c, a, movement->comp[1], 12, &tail_vel)) != RECS_OK) return st;
+            if ((st = need_column(c, o.arch, movement->comp[0], 12, &tail_pos)) != RECS_OK) return st;
+            if ((st = need_column(c, o.arch, movement->comp[1], 12, &tail_vel)) != RECS_OK) return st;
             if ((st = same_count(c, tail_pos, tail_vel)) != RECS_OK) return st;
             ra.tail.pos = (float*)tail_pos->dev;
             ra.tail.vel = (float*)tail_vel->dev;
@@ -460,16 +563,17 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             ra.tail.g = c->cfg.nbody_g;
             ra.tail.pscale = pscale;
             // refresh the mirror in place when this archetype is part of the nested query
-            uint64_t off = 0;
-            for (size_t qi = 0; qi < sys.qarchs.size(); ++qi) {
-                if (sys.qarchs[qi] == a && movement->comp[0] == POS) {
-                    if ((st = need_column(c, a, MASS, 4, &mass_col)) != RECS_OK) return st;
-                    ra.tail.mass = (const float*)mass_col->dev;
+            if (o.self_offset != 0xffffffffu && movement->comp[0] == POS) {
+                if ((st = need_column(c, o.arch, MASS, 4, &mass_col)) != RECS_OK) return st;
+                ra.tail.mass = (const float*)mass_col->dev;
+                ra.tail.posm_offset = o.self_offset;
+                if (p2p) {
+                    // the refreshed rows go to every rank's buffer of the next generation
+                    ra.push = peer_push(++c->xchg.gen);
+                    ra.tail.posm = ra.push.posm[c->cfg.rank];
+                } else {
                     ra.tail.posm = c->posm;
-                    ra.tail.posm_offset = (uint32_t)off;
-                    break;
                 }
-                off += q[qi].first->count;
             }
         }
         {
@@ -477,7 +581,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             RECS_CUDA(c, launch_gravity_reduce(ra, c->stream));
             c->kernel_launches++;
         }
-        acc->version++;
+        o.acc->version++;
         if (movement) {
             tail_pos->version++;
             tail_vel->version++;
@@ -487,7 +591,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         // every source of the mirror was just refreshed by the tail: record it as current
         for (auto& src : c->posm_sources) src.second = find_column(c, src.first.first, src.first.second)->version;
     }
-    if (sharded && (sys.archs.empty() || re == rb)) {  // nothing launched here: still take part in the collective
+    if (sharded && !p2p && outers.empty()) {  // nothing launched here: still take part in the collective
         if ((st = enqueue_gather()) != RECS_OK) return st;
         RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
     }
@@ -904,6 +1008,24 @@ void drop_graph(recs_gpu_ctx* c) {
     if (c->graph) cudaGraphExecDestroy(c->graph);
     c->graph = nullptr;
     c->graph_epoch = ~0ull;
+    c->graph_elided_pack = false;
+}
+
+// True while no source column of the gravity mirror was written since it was packed / refreshed.
+bool posm_is_current(recs_gpu_ctx* c) {
+    for (const auto& src : c->posm_sources) {
+        const Column* col = find_column(c, src.first.first, src.first.second);
+        if (!col || col->version != src.second) return false;
+    }
+    return true;
+}
+
+int32_t check_device_error(recs_gpu_ctx* c) {
+    if (c->dev_error_host && *reinterpret_cast<volatile uint32_t*>(c->dev_error_host)) {
+        *c->dev_error_host = 0;
+        return fail(c, RECS_ERR_NCCL, "peer exchange timed out: a rank did not push its slice of the position mirror (ranks must run the same ticks)");
+    }
+    return RECS_OK;
 }
 
 void fill_system(System& s, recs_gpu_system_kind kind, const uint64_t* ids) {
@@ -1054,6 +1176,17 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
             c->grav_ctas_per_sm[k] = gravity_max_ctas_per_sm(k);
             ok = c->grav_ctas_per_sm[k] > 0;
         }
+        // test knobs: neither may change a bit of the result (tests/test_gpu_nbody.py)
+        if (const char* g = getenv("RECS_GPU_GRAVITY_GRID")) c->grav_grid_forced = atoi(g);
+        if (const char* e = getenv("RECS_GPU_GRAVITY_EMULATE_RANK")) {
+            int R = 0, r = 0;
+            if (sscanf(e, "%d,%d", &R, &r) == 2 && R > 1 && R <= kGravMaxPeers && r >= 0 && r < R) c->emulate_ranks = R, c->emulate_rank = r;
+        }
+        const char* x = getenv("RECS_GPU_EXCHANGE");  // "nccl": keep the all-gather exchange even when peers are mapped
+        c->exchange_nccl_forced = x && strcmp(x, "nccl") == 0;
+        ok = ok && cudaHostAlloc((void**)&c->dev_error_host, 64, cudaHostAllocMapped) == cudaSuccess &&
+             cudaHostGetDevicePointer((void**)&c->dev_error, c->dev_error_host, 0) == cudaSuccess;
+        if (ok) *c->dev_error_host = 0;
     }
     if (!ok) {
         fprintf(stderr, "recs_gpu: context creation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -1083,6 +1216,10 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
             }
         if (c->posm) cudaFree(c->posm);
         if (c->frags) cudaFree(c->frags);
+        for (int r = 0; r < kGravMaxPeers; ++r)
+            if (c->xchg.peer[r] && c->xchg.peer[r] != c->xchg.base) cudaIpcCloseMemHandle(c->xchg.peer[r]);
+        if (c->xchg.base) cudaFree(c->xchg.base);
+        if (c->dev_error_host) cudaFreeHost(c->dev_error_host);
         if (c->l2_flush) cudaFree(c->l2_flush);
         if (c->move_idx) cudaFree(c->move_idx);
         if (c->move_tmp) cudaFree(c->move_tmp);
@@ -1121,7 +1258,7 @@ int32_t recs_gpu_synchronize(recs_gpu_ctx* c) {
     RECS_ENTER(c);
     RECS_CUDA(c, cudaStreamSynchronize(c->stream));
     RECS_CUDA(c, cudaStreamSynchronize(c->comm_stream));
-    return RECS_OK;
+    return check_device_error(c);
 }
 
 int32_t recs_gpu_bind_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void* host_ptr, uint32_t elem,
@@ -1130,6 +1267,7 @@ int32_t recs_gpu_bind_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void
     if (elem == 0 || (count > 0 && !host_ptr)) return fail(c, RECS_ERR_INVALID_ARGUMENT, "bind_column: null host pointer or zero element size");
     Column& col = c->columns[ColKey(arch, comp)];
     const size_t bytes = std::max<size_t>((size_t)elem * count, 16);
+    const bool layout_changed = col.cap < bytes || !col.dev || col.elem != elem || col.count != count || col.stale;
     if (col.cap < bytes || !col.dev) {
         // wait for in-flight work before releasing the old buffer
         RECS_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1148,7 +1286,7 @@ int32_t recs_gpu_bind_column(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, void
     col.count = count;
     col.stale = false;
     col.version++;
-    c->epoch++;
+    if (layout_changed) c->epoch++;  // the layout epoch: device pointers, row counts, archetype lists (tables, graph)
     return RECS_OK;
 }
 
@@ -1161,8 +1299,7 @@ int32_t recs_gpu_upload(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
         RECS_CUDA(c, cudaMemcpyAsync(col->dev, col->host, (size_t)col->elem * col->count, cudaMemcpyHostToDevice,
                                      c->stream));
     c->h2d_bytes += (uint64_t)col->elem * col->count;
-    col->version++;
-    c->epoch++;  // a captured tick may have elided the posm re-pack: capture again after new host data
+    col->version++;  // (a captured tick that elided the mirror re-pack is dropped by the version check in recs_gpu_tick)
     return RECS_OK;
 }
 
@@ -1179,7 +1316,6 @@ int32_t recs_gpu_upload_rows(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, uint
                                      cudaMemcpyHostToDevice, c->stream));
     c->h2d_bytes += bytes;
     col->version++;
-    c->epoch++;
     return RECS_OK;
 }
 
@@ -1195,7 +1331,7 @@ int32_t recs_gpu_download_rows(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, ui
                                      cudaMemcpyDeviceToHost, c->stream));
     c->d2h_bytes += bytes;
     RECS_CUDA(c, cudaStreamSynchronize(c->stream));
-    return RECS_OK;
+    return check_device_error(c);
 }
 
 int32_t recs_gpu_download(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
@@ -1208,7 +1344,7 @@ int32_t recs_gpu_download(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
                                      c->stream));
     c->d2h_bytes += (uint64_t)col->elem * col->count;
     RECS_CUDA(c, cudaStreamSynchronize(c->stream));
-    return RECS_OK;
+    return check_device_error(c);
 }
 
 // ---- structural changes without a round trip ------------------------------------------------------------------------
@@ -1545,7 +1681,7 @@ int32_t recs_gpu_set_tick_order(recs_gpu_ctx* c, const uint32_t* ids, uint32_t n
     std::vector<uint32_t> next(ids, ids + n);
     if (next != c->order) {
         c->order.swap(next);
-        c->epoch++;
+        drop_graph(c);  // the captured chain is another one; archetype tables of generic systems stay valid
     }
     return RECS_OK;
 }
@@ -1562,6 +1698,9 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
     const bool want_graph = c->cfg.use_cuda_graph && c->cfg.world_size == 1 && !c->timing && order_is_capturable(c);
     uint32_t done = 0;
     if (want_graph && n_ticks > 1) {
+        // a captured tick that found the gravity mirror current holds no pack kernel: it is only valid while nothing
+        // outside the chain (recs_gpu_run_system, an upload) has written the mirror's source columns since
+        if (c->graph && c->graph_elided_pack && !posm_is_current(c)) drop_graph(c);
         if (!c->graph || c->graph_epoch != c->epoch) {
             drop_graph(c);
             // one eager tick sizes every workspace, then the same chain is captured
@@ -1636,6 +1775,63 @@ int32_t recs_gpu_comm_init(recs_gpu_ctx* c, const uint8_t id_bytes[RECS_GPU_NCCL
     int r = c->nccl.CommInitRank(&c->comm, c->cfg.world_size, id, c->cfg.rank);
     if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclCommInitRank: ") + c->nccl.GetErrorString(r));
     return RECS_OK;
+}
+
+// ---- peer-pushed position exchange (sharded runs) -------------------------------------------------------------------
+int32_t recs_gpu_exchange_export(recs_gpu_ctx* c, uint64_t max_bodies, uint8_t handle_bytes[RECS_GPU_IPC_HANDLE_BYTES]) {
+    RECS_ENTER(c);
+    if (!handle_bytes || max_bodies == 0) return fail(c, RECS_ERR_INVALID_ARGUMENT, "exchange_export: bad argument");
+    if (c->cfg.world_size > kGravMaxPeers) return fail(c, RECS_ERR_UNSUPPORTED, "exchange_export: more than 16 ranks");
+    static_assert(sizeof(cudaIpcMemHandle_t) == RECS_GPU_IPC_HANDLE_BYTES, "IPC handle size");
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < kGravMaxPeers; ++r) {
+        if (c->xchg.peer[r] && c->xchg.peer[r] != c->xchg.base) RECS_CUDA(c, cudaIpcCloseMemHandle(c->xchg.peer[r]));
+        c->xchg.peer[r] = nullptr;
+    }
+    if (c->xchg.base) RECS_CUDA(c, cudaFree(c->xchg.base));
+    c->xchg = recs_gpu_ctx::Exchange();
+    uint64_t slice, rb, re;
+    shard_rows(c->cfg, max_bodies, &slice, &rb, &re);
+    c->xchg.cap_bodies = slice * (uint64_t)c->cfg.world_size;
+    RECS_CUDA(c, cudaMalloc((void**)&c->xchg.base, c->xchg.bytes()));
+    // all zero: null bodies everywhere, generation 0 on every flag
+    RECS_CUDA(c, cudaMemset(c->xchg.base, 0, c->xchg.bytes()));
+    cudaIpcMemHandle_t h;
+    RECS_CUDA(c, cudaIpcGetMemHandle(&h, c->xchg.base));
+    memcpy(handle_bytes, &h, sizeof h);
+    c->posm_sources.clear();  // the mirror moves into the exchange buffer: pack again
+    c->posm_bodies = 0;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_exchange_import(recs_gpu_ctx* c, const uint8_t* handles, uint32_t n_handles) {
+    RECS_ENTER(c);
+    if (!handles || n_handles != (uint32_t)c->cfg.world_size) return fail(c, RECS_ERR_INVALID_ARGUMENT, "exchange_import: one handle per rank, in rank order");
+    if (!c->xchg.base) return fail(c, RECS_ERR_INVALID_ARGUMENT, "exchange_import: call recs_gpu_exchange_export first");
+    for (int r = 0; r < c->cfg.world_size; ++r) {
+        if (r == c->cfg.rank) {
+            c->xchg.peer[r] = c->xchg.base;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)r * RECS_GPU_IPC_HANDLE_BYTES, sizeof h);
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, RECS_ERR_CUDA, std::string("cudaIpcOpenMemHandle (rank ") + std::to_string(r) + "): " + cudaGetErrorString(e));
+        }
+        c->xchg.peer[r] = (unsigned char*)p;
+    }
+    c->xchg.imported = true;
+    return RECS_OK;
+}
+
+int32_t recs_gpu_exchange_mode(recs_gpu_ctx* c) {
+    if (!c) return RECS_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(c->mu);
+    if (c->cfg.world_size <= 1) return 0;
+    return c->xchg.imported && !c->exchange_nccl_forced ? 2 : 1;
 }
 
 int32_t recs_gpu_shard_rows(recs_gpu_ctx* c, uint64_t n_rows, uint64_t* row_begin, uint64_t* row_end) {
@@ -1720,7 +1916,7 @@ int32_t recs_gpu_timer_stop(recs_gpu_ctx* c, float* out_ms) {
     RECS_CUDA(c, cudaEventSynchronize(c->timer_b));
     RECS_CUDA(c, cudaStreamSynchronize(c->comm_stream));
     RECS_CUDA(c, cudaEventElapsedTime(out_ms, c->timer_a, c->timer_b));
-    return RECS_OK;
+    return check_device_error(c);
 }
 
 int32_t recs_gpu_measure_fp32_peak(recs_gpu_ctx* c, int32_t packed, float* out_tflops, float* out_sm_mhz) {

@@ -23,6 +23,8 @@
 //     per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies load all 148 SMs as evenly as 1 M
 //     bodies do.  A CTA writes one partial ("fragment") per i-block it touched; a second kernel adds the
 //     fragments of each i-block in ascending j order -- deterministic, no float atomics -- and integrates.
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -74,8 +76,15 @@ __device__ __forceinline__ void pair_interaction(const f32x2 xj, const f32x2 yj,
     const f32x2 dy = ptx::add2(yj, ptx::pack(-ny, -ny));
     const f32x2 dz = ptx::add2(zj, ptx::pack(-nz, -nz));
     f32x2 d2 = ptx::mul2(dx, dx);
-    d2 = ptx::fma2(dy, dy, d2);
-    d2 = ptx::fma2(dz, dz, d2);
+    if (MASKED) {
+        // the mask decision must be the reference's: cgmath's magnitude2 = (dx*dx + dy*dy) + dz*dz with every
+        // product and sum rounded on its own (rustc never contracts), crates/n-body/src/lib.rs:116-120
+        d2 = ptx::add2_unfused(d2, ptx::mul2(dy, dy));
+        d2 = ptx::add2_unfused(d2, ptx::mul2(dz, dz));
+    } else {
+        d2 = ptx::fma2(dy, dy, d2);
+        d2 = ptx::fma2(dz, dz, d2);
+    }
     float d2a, d2b;
     ptx::unpack(d2, d2a, d2b);
     float ra = ptx::rsqrt_approx(d2a);
@@ -127,8 +136,13 @@ __device__ __forceinline__ void ipair_interaction(const float xj, const float yj
     const f32x2 dy = ptx::add2(ny, ptx::pack(yj, yj));
     const f32x2 dz = ptx::add2(nz, ptx::pack(zj, zj));
     f32x2 d2 = ptx::mul2(dx, dx);
-    d2 = ptx::fma2(dy, dy, d2);
-    d2 = ptx::fma2(dz, dz, d2);
+    if (MASKED) {  // unfused: the reference's own d2, so `d2 <= epsilon` decides exactly as it does (see pair_interaction)
+        d2 = ptx::add2_unfused(d2, ptx::mul2(dy, dy));
+        d2 = ptx::add2_unfused(d2, ptx::mul2(dz, dz));
+    } else {
+        d2 = ptx::fma2(dy, dy, d2);
+        d2 = ptx::fma2(dz, dz, d2);
+    }
     float d2a, d2b;
     ptx::unpack(d2, d2a, d2b);
     float ra, rb;
@@ -194,17 +208,13 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
     constexpr int kGravRows = kGravConsumerThreads * RI;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4* tiles = reinterpret_cast<float4*>(smem_raw);
-    // running sums of the current i-block, one private float4 slot per (row, thread): the second
-    // level of the summation (level 1 = one tile of 128 pairs in registers)
+    // running prefix of the current chunk, one private float4 slot per (row, thread): the second
+    // level of the summation (level 1 = one tile of 256 bodies in registers)
     float4* run = reinterpret_cast<float4*>(smem_raw + kGravSmemBytes);
     __shared__ __align__(8) uint64_t full_bar[kGravStages];
     __shared__ __align__(8) uint64_t empty_bar[kGravStages];
 
-    const uint32_t n_vtiles = a.launch.n_vtiles;
-    const uint32_t units = a.launch.n_iblocks * n_vtiles;
-    const Span span = span_of(blockIdx.x, gridDim.x, units);
-    if (span.count == 0) return;
-
+    const GravityWork& w = a.work;
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
 
@@ -221,31 +231,45 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
     if (warp == kGravConsumerWarps) {
         // ---- TMA producer: one thread streams this CTA's tiles through the ring --------------
         if (lane == 0) {
-            uint32_t v = span.begin % n_vtiles;
-            for (uint32_t k = 0; k < span.count; ++k) {
-                const uint32_t stage = k % kGravStages;
-                const uint32_t phase = (k / kGravStages) & 1u;
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-                uint32_t tile = v + a.launch.tile_offset;
-                if (tile >= a.n_tiles_total) tile -= a.n_tiles_total;
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], kGravTileBytes);
-                ptx::bulk_g2s(tiles + stage * kGravTile, a.posm + static_cast<size_t>(tile) * kGravTile,
-                              kGravTileBytes, &full_bar[stage]);
-                if (++v == n_vtiles) v = 0;
+            uint32_t kk = 0;                         // position in the ring, running across the phases
+            uint32_t ready = 1u << (a.own_rank & 31);  // ranks whose slice of the mirror has been seen complete
+            for (uint32_t ph = a.phase_begin; ph < a.phase_end; ++ph) {
+                const GravityPhase& P = w.phase[ph];
+                const Span span = span_of(blockIdx.x, w.grid, w.n_iblocks * P.n_vtiles);
+                if (span.count == 0) continue;
+                uint32_t v = span.begin % P.n_vtiles;
+                for (uint32_t k = 0; k < span.count; ++k, ++kk) {
+                    const uint32_t stage = kk % kGravStages;
+                    const uint32_t phase = (kk / kGravStages) & 1u;
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint32_t tile = v + P.tile_offset;
+                    if (tile >= w.n_tiles_total) tile -= w.n_tiles_total;
+                    if (a.flags) {
+                        // the slice of another rank: its tail / pack kernel pushed it into this GPU's memory and then
+                        // raised flags[rank] to the generation (release.sys); acquire it before the first bulk load
+                        const uint32_t r = tile / a.tiles_per_rank;
+                        if (!(ready >> r & 1u)) {
+                            ptx::wait_generation(a.flags + r, a.wait_gen, a.error);
+                            ptx::fence_proxy_async_global();
+                            ready |= 1u << r;
+                        }
+                    }
+                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kGravTileBytes);
+                    ptx::bulk_g2s(tiles + stage * kGravTile, a.posm + static_cast<size_t>(tile) * kGravTile,
+                                  kGravTileBytes, &full_bar[stage]);
+                    if (++v == P.n_vtiles) v = 0;
+                }
             }
         }
         return;
     }
 
     // ---- consumers ---------------------------------------------------------------------------
-    const uint32_t tid = threadIdx.x;  // 0..255
-    uint32_t b = span.begin / n_vtiles;
-    uint32_t v = span.begin % n_vtiles;
-
+    const uint32_t tid = threadIdx.x;  // 0..kGravConsumerThreads-1
     float nxi[kGravRowsPerThread], nyi[kGravRowsPerThread], nzi[kGravRowsPerThread];
 
     // row of the i-block that register slot r of this thread holds.  i-packed shapes give a warp RI*32 consecutive
-    // rows, so the warp's own bodies sit in ONE j tile (one exact-path redo per i-block instead of RI).
+    // rows, so the warp's own bodies sit in ONE j tile (one exact-path tile per i-block instead of RI).
     auto row_in_block = [&](int r) -> uint32_t {
         return IPACK ? (warp * (32u * RI) + r * 32u + lane) : (r * kGravConsumerThreads + tid);
     };
@@ -264,221 +288,315 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             nxi[r] = x;  // kept positive; negated at the use (see pair_interaction)
             nyi[r] = y;
             nzi[r] = z;
-            run[r * kGravConsumerThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
-    // the (CTA, i-block) fragment is written exactly once, when the CTA leaves the i-block
-    auto flush = [&](uint32_t iblock) {
-        float4* dst = a.frags + static_cast<size_t>(a.launch.frag_base + blockIdx.x + iblock) * kGravRows;
-#pragma unroll
-        for (int r = 0; r < kGravRowsPerThread; ++r)
-            dst[row_in_block(r)] = run[r * kGravConsumerThreads + tid];
-    };
-
-    load_rows(b);
     const float eps = a.eps;
+    const uint32_t K = w.chunk_tiles;
 
-    for (uint32_t k = 0; k < span.count; ++k) {
-        const uint32_t stage = k % kGravStages;
-        const uint32_t phase = (k / kGravStages) & 1u;
-        ptx::mbar_wait(&full_bar[stage], phase);
-        const float4* t = tiles + stage * kGravTile;
+    uint32_t kk = 0;
+    for (uint32_t ph = a.phase_begin; ph < a.phase_end; ++ph) {
+        const GravityPhase& P = w.phase[ph];
+        const Span span = span_of(blockIdx.x, w.grid, w.n_iblocks * P.n_vtiles);
+        if (span.count == 0) continue;
+        const uint32_t chunks_per_iblock = P.n_vtiles / K;
+        uint32_t b = span.begin / P.n_vtiles;
+        uint32_t v = span.begin % P.n_vtiles;
+        uint32_t cv = v / K;        // chunk of the phase the tile belongs to
+        uint32_t pic = v - cv * K;  // position of the tile in its chunk
+        // A span that begins inside a chunk stores that chunk's remaining tile sums one by one: the CTA holding the
+        // chunk's first tile owns the running prefix, and the reduce kernel continues it in tile order.
+        bool prefix = false;
+        // v of the tile that holds this warp's own bodies (i-packed shapes: 32 * RI consecutive rows), if the outer
+        // archetype is part of the nested query and the tile belongs to this phase: it goes straight to the exact path
+        auto own_tile_of = [&](uint32_t iblock) -> uint32_t {
+            if (a.self_offset == 0xffffffffu) return 0xffffffffu;
+            const uint32_t tile = (a.self_offset + a.row_begin + iblock * kGravRows + warp * (32u * RI)) / kGravTile;
+            const uint32_t ov = tile >= P.tile_offset ? tile - P.tile_offset : tile + w.n_tiles_total - P.tile_offset;
+            return ov < P.n_vtiles ? ov : 0xffffffffu;
+        };
+        uint32_t own_v = own_tile_of(b);
+        load_rows(b);
 
-        float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
-        if constexpr (IPACK) {
-            // lanes = rows (2q, 2q+1) of this thread
-            constexpr int RP = RI / 2;
-            f32x2 nx[RP], ny[RP], nz[RP], ax[RP], ay[RP], az[RP];
+        for (uint32_t k = 0; k < span.count; ++k, ++kk) {
+            const uint32_t stage = kk % kGravStages;
+            const uint32_t phase = (kk / kGravStages) & 1u;
+            if (pic == 0) {
+                prefix = true;
 #pragma unroll
-            for (int q = 0; q < RP; ++q) {
-                nx[q] = ptx::pack(-nxi[2 * q], -nxi[2 * q + 1]);
-                ny[q] = ptx::pack(-nyi[2 * q], -nyi[2 * q + 1]);
-                nz[q] = ptx::pack(-nzi[2 * q], -nzi[2 * q + 1]);
-                ax[q] = ay[q] = az[q] = 0ull;
+                for (int r = 0; r < kGravRowsPerThread; ++r) run[r * kGravConsumerThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if constexpr ((ABL & kAblOverflow) != 0) {
-                // Range-shifted fast path: tile and row positions are stored times 2^-32 (an exact scaling; G*m is
-                // stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
-                // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the tile sums, which come out times 2^64.
-                // No per-pair detector instruction at all: one finiteness test per tile, then the exact masked
-                // path on true-scale values.  A tile in which G*m/d^3 of some pair reaches 2^32 s^-2 (a density
-                // above 1e19 kg/m^3) or whose sums reach 2^64 m/s^2 takes the exact path as well.
-                itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-                float chk = 0.f;
+            ptx::mbar_wait(&full_bar[stage], phase);
+            const float4* t = tiles + stage * kGravTile;
+
+            float sx[kGravRowsPerThread], sy[kGravRowsPerThread], sz[kGravRowsPerThread];  // this tile's sums per row
+            float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
+            if constexpr (IPACK) {
+                // lanes = rows (2q, 2q+1) of this thread
+                constexpr int RP = RI / 2;
+                f32x2 nx[RP], ny[RP], nz[RP], ax[RP], ay[RP], az[RP];
 #pragma unroll
                 for (int q = 0; q < RP; ++q) {
-                    const f32x2 sc = ptx::pack(kGravOutScale, kGravOutScale);
-                    ax[q] = ptx::mul2(ax[q], sc);
-                    ay[q] = ptx::mul2(ay[q], sc);
-                    az[q] = ptx::mul2(az[q], sc);
-                    float u0, u1, v0, v1, w0, w1;
-                    ptx::unpack(ax[q], u0, u1);
-                    ptx::unpack(ay[q], v0, v1);
-                    ptx::unpack(az[q], w0, w1);
-                    chk += fabsf(u0) + fabsf(u1) + fabsf(v0) + fabsf(v1) + fabsf(w0) + fabsf(w1);
+                    nx[q] = ptx::pack(-nxi[2 * q], -nxi[2 * q + 1]);
+                    ny[q] = ptx::pack(-nyi[2 * q], -nyi[2 * q + 1]);
+                    nz[q] = ptx::pack(-nzi[2 * q], -nzi[2 * q + 1]);
+                    ax[q] = ay[q] = az[q] = 0ull;
                 }
-                if (!(chk < 3.0e38f)) {  // inf or NaN somewhere
-                    f32x2 ux[RP], uy[RP], uz[RP];
-                    const f32x2 un = ptx::pack(kGravPosUnscale, kGravPosUnscale);
+                if constexpr ((ABL & kAblOverflow) != 0) {
+                    // Range-shifted fast path: tile and row positions are stored times 2^-32 (an exact scaling; G*m is
+                    // stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
+                    // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the tile sums, which come out times 2^64.
+                    // No per-pair detector instruction at all: one finiteness test per tile, then the exact masked
+                    // path on true-scale values.  A tile in which G*m/d^3 of some pair reaches 2^32 s^-2 (a density
+                    // above 1e19 kg/m^3) or whose sums reach 2^64 m/s^2 takes the exact path as well.
+                    // The tile that holds the warp's own bodies is known in advance and skips the doomed fast pass.
+                    const bool own_tile = v == own_v;
+                    auto exact_tile = [&]() {
+                        f32x2 ux[RP], uy[RP], uz[RP];
+                        const f32x2 un = ptx::pack(kGravPosUnscale, kGravPosUnscale);
 #pragma unroll
-                    for (int q = 0; q < RP; ++q) {
-                        ux[q] = ptx::mul2(nx[q], un);
-                        uy[q] = ptx::mul2(ny[q], un);
-                        uz[q] = ptx::mul2(nz[q], un);
-                        ax[q] = ay[q] = az[q] = 0ull;
+                        for (int q = 0; q < RP; ++q) {
+                            ux[q] = ptx::mul2(nx[q], un);
+                            uy[q] = ptx::mul2(ny[q], un);
+                            uz[q] = ptx::mul2(nz[q], un);
+                            ax[q] = ay[q] = az[q] = 0ull;
+                        }
+                        itile_loop<RP, 2, true, 0, true>(t, ux, uy, uz, eps, ax, ay, az, dmin_a, dmin_b);
+                    };
+                    if (own_tile) {
+                        exact_tile();
+                    } else {
+                        itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                        float chk = 0.f;
+#pragma unroll
+                        for (int q = 0; q < RP; ++q) {
+                            const f32x2 sc = ptx::pack(kGravOutScale, kGravOutScale);
+                            ax[q] = ptx::mul2(ax[q], sc);
+                            ay[q] = ptx::mul2(ay[q], sc);
+                            az[q] = ptx::mul2(az[q], sc);
+                            float u0, u1, v0, v1, w0, w1;
+                            ptx::unpack(ax[q], u0, u1);
+                            ptx::unpack(ay[q], v0, v1);
+                            ptx::unpack(az[q], w0, w1);
+                            chk += fabsf(u0) + fabsf(u1) + fabsf(v0) + fabsf(v1) + fabsf(w0) + fabsf(w1);
+                        }
+                        if (!(chk < 3.0e38f)) exact_tile();  // inf or NaN somewhere
                     }
-                    itile_loop<RP, 1, true, 0, true>(t, ux, uy, uz, eps, ax, ay, az, dmin_a, dmin_b);
-                }
-            } else if (DETECT) {
-                itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-                if (fminf(dmin_a, dmin_b) <= eps) {
+                } else if (DETECT) {
+                    itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                    // the detector sees the FUSED d2, the mask the reference's unfused one: they differ by an ulp or two,
+                    // so everything within a factor 1 + 2^-20 of epsilon is sent to the exact path as well
+                    if (fminf(dmin_a, dmin_b) <= eps * 1.000001f) {
 #pragma unroll
-                    for (int q = 0; q < RP; ++q) ax[q] = ay[q] = az[q] = 0ull;
-                    itile_loop<RP, 1, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                        for (int q = 0; q < RP; ++q) ax[q] = ay[q] = az[q] = 0ull;
+                        itile_loop<RP, 1, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                    }
+                } else {
+                    itile_loop<RP, UNROLL, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
+                }
+#pragma unroll
+                for (int q = 0; q < RP; ++q) {
+                    ptx::unpack(ax[q], sx[2 * q], sx[2 * q + 1]);
+                    ptx::unpack(ay[q], sy[2 * q], sy[2 * q + 1]);
+                    ptx::unpack(az[q], sz[2 * q], sz[2 * q + 1]);
                 }
             } else {
-                itile_loop<RP, UNROLL, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-            }
-#pragma unroll
-            for (int q = 0; q < RP; ++q) {
-                float x0, x1, y0, y1, z0, z1;
-                ptx::unpack(ax[q], x0, x1);
-                ptx::unpack(ay[q], y0, y1);
-                ptx::unpack(az[q], z0, z1);
-                float4 acc0 = run[(2 * q) * kGravConsumerThreads + tid];
-                float4 acc1 = run[(2 * q + 1) * kGravConsumerThreads + tid];
-                acc0.x += x0;
-                acc0.y += y0;
-                acc0.z += z0;
-                acc1.x += x1;
-                acc1.y += y1;
-                acc1.z += z1;
-                run[(2 * q) * kGravConsumerThreads + tid] = acc0;
-                run[(2 * q + 1) * kGravConsumerThreads + tid] = acc1;
-            }
-        } else {
-        f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
-#pragma unroll
-        for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
-        if (DETECT) {
-            tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
-            if (fminf(dmin_a, dmin_b) <= eps) {
-                // some pair of this thread in this tile is at or below epsilon (its own body, or a
-                // coincident one): the unmasked sums are garbage (inf/NaN) -- redo the tile exactly.
+                f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
 #pragma unroll
                 for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
-                tile_loop<RI, 1, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
-            }
-        } else {
-            tile_loop<RI, UNROLL, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
-        }
-        // level-2 accumulation in shared memory (private slots, no synchronisation needed)
+                if (DETECT) {
+                    tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+                    if (fminf(dmin_a, dmin_b) <= eps * 1.000001f) {
+                        // some pair of this thread in this tile is at or below epsilon (its own body, or a
+                        // coincident one): the unmasked sums are garbage (inf/NaN) -- redo the tile exactly.
 #pragma unroll
-        for (int r = 0; r < kGravRowsPerThread; ++r) {
-            float x0, x1, y0, y1, z0, z1;
-            ptx::unpack(ax[r], x0, x1);
-            ptx::unpack(ay[r], y0, y1);
-            ptx::unpack(az[r], z0, z1);
-            float4 acc = run[r * kGravConsumerThreads + tid];
-            acc.x += x0 + x1;
-            acc.y += y0 + y1;
-            acc.z += z0 + z1;
-            run[r * kGravConsumerThreads + tid] = acc;
-        }
-        }
+                        for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
+                        tile_loop<RI, 1, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+                    }
+                } else {
+                    tile_loop<RI, UNROLL, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+                }
+#pragma unroll
+                for (int r = 0; r < kGravRowsPerThread; ++r) {
+                    float x0, x1, y0, y1, z0, z1;
+                    ptx::unpack(ax[r], x0, x1);
+                    ptx::unpack(ay[r], y0, y1);
+                    ptx::unpack(az[r], z0, z1);
+                    sx[r] = x0 + x1;  // even + odd bodies of the tile
+                    sy[r] = y0 + y1;
+                    sz[r] = z0 + z1;
+                }
+            }
 
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+            // the tile is consumed: hand the stage back before the bookkeeping below
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
 
-        if (++v == n_vtiles) {
-            v = 0;
-            flush(b);
-            ++b;
-            if (k + 1 < span.count) load_rows(b);
+            if (prefix) {
+                // level 2: running prefix of the chunk (private shared-memory slots, no synchronisation needed)
+                if (pic + 1 == K || k + 1 == span.count) {
+                    float4* dst = a.frags + static_cast<size_t>(P.frag_base + b * chunks_per_iblock + cv) * kGravRows;
+#pragma unroll
+                    for (int r = 0; r < kGravRowsPerThread; ++r) {
+                        float4 acc = run[r * kGravConsumerThreads + tid];
+                        acc.x += sx[r];
+                        acc.y += sy[r];
+                        acc.z += sz[r];
+                        __stcs(dst + row_in_block(r), acc);
+                    }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kGravRowsPerThread; ++r) {
+                        float4 acc = run[r * kGravConsumerThreads + tid];
+                        acc.x += sx[r];
+                        acc.y += sy[r];
+                        acc.z += sz[r];
+                        run[r * kGravConsumerThreads + tid] = acc;
+                    }
+                }
+            } else {
+                float4* dst = a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(blockIdx.x) * (K - 1) + k) * kGravRows;
+#pragma unroll
+                for (int r = 0; r < kGravRowsPerThread; ++r) __stcs(dst + row_in_block(r), make_float4(sx[r], sy[r], sz[r], 0.f));
+            }
+
+            if (++pic == K) pic = 0, ++cv;
+            if (++v == P.n_vtiles) {
+                v = 0;
+                cv = 0;
+                ++b;
+                if (k + 1 < span.count) {
+                    own_v = own_tile_of(b);
+                    load_rows(b);
+                }
+            }
         }
     }
-    if (v != 0) flush(b);
+}
+
+// Waits until every rank's previous generation has arrived here (nobody still reads the buffer this push overwrites
+// on a peer: a rank that has pushed generation g-1 has finished every kernel that read generation g-2), CTA-wide.
+__device__ __forceinline__ void push_begin(const PeerPush& p) {
+    if (p.n == 0) return;
+    if (threadIdx.x < p.n) ptx::wait_generation(p.local_flags + threadIdx.x, p.gen - 1u, p.error);
+    __syncthreads();
+}
+// After the CTA's stores: the last CTA of the grid raises this rank's flag on every peer.
+__device__ __forceinline__ void push_end(const PeerPush& p) {
+    if (p.n == 0) return;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ uint32_t is_last;
+    if (threadIdx.x == 0) is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (is_last) {
+        if (threadIdx.x == 0) *p.done_counter = 0;  // the next pushing kernel follows in stream order
+        __threadfence_system();
+        if (threadIdx.x < p.n) ptx::st_release_sys(p.flag[threadIdx.x], p.gen);
+    }
+}
+// One refreshed mirror entry: local mirror, or the same slot of every rank's buffer.
+__device__ __forceinline__ void store_posm(const PeerPush& p, float* local, uint64_t J, float x, float y, float z, float gm) {
+    const size_t o = (J >> 1) * 8 + (J & 1);
+    if (p.n == 0) {
+        float* d = local + o;
+        d[0] = x, d[2] = y, d[4] = z, d[6] = gm;
+    } else {
+        for (uint32_t q = 0; q < p.n; ++q) {
+            float* d = p.posm[q] + o;
+            d[0] = x, d[2] = y, d[4] = z, d[6] = gm;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.row_count) return;
-    const uint32_t kGravRows = a.iblock_rows;
-    const uint32_t b = i / kGravRows;
-    const uint32_t idx = i % kGravRows;
-    // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
-    float sx = 0.f, sy = 0.f, sz = 0.f;
-    for (uint32_t l = 0; l < a.n_launches; ++l) {
-        const GravityLaunch& L = a.launch[l];
-        if (L.n_vtiles == 0) continue;
-        const uint32_t units = L.n_iblocks * L.n_vtiles;
-        const uint32_t u_lo = b * L.n_vtiles;
-        const uint32_t u_hi = u_lo + L.n_vtiles - 1;
-        const uint32_t c_lo = cta_of(u_lo, L.grid, units);
-        const uint32_t c_hi = cta_of(u_hi, L.grid, units);
-        for (uint32_t c = c_lo; c <= c_hi; ++c) {
-            const float4 f = a.frags[static_cast<size_t>(L.frag_base + c + b) * kGravRows + idx];
-            sx += f.x;
-            sy += f.y;
-            sz += f.z;
+    const bool valid = i < a.row_count;
+    if (a.tail.posm) push_begin(a.push);
+    if (valid) {
+        const GravityWork& w = a.work;
+        const uint32_t rows = a.iblock_rows;
+        const uint32_t b = i / rows;
+        const uint32_t idx = i % rows;
+        const uint32_t K = w.chunk_tiles;
+        const uint32_t n_chunks = w.n_tiles_total / K;
+        // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        for (uint32_t c = 0; c < n_chunks; ++c) {
+            // the phase whose rotated tile range holds chunk c
+            const uint32_t tile0 = c * K;
+            uint32_t ph = 0, v0 = 0;
+            for (; ph < w.n_phases; ++ph) {
+                v0 = tile0 >= w.phase[ph].tile_offset ? tile0 - w.phase[ph].tile_offset
+                                                      : tile0 + w.n_tiles_total - w.phase[ph].tile_offset;
+                if (v0 < w.phase[ph].n_vtiles) break;
+            }
+            if (ph == w.n_phases) continue;  // not visited (cannot happen for a complete work description)
+            const GravityPhase& P = w.phase[ph];
+            const uint32_t units = w.n_iblocks * P.n_vtiles;
+            const uint32_t u0 = b * P.n_vtiles + v0;
+            const uint32_t g0 = cta_of(u0, w.grid, units);
+            const Span s0 = span_of(g0, w.grid, units);
+            float4 f = __ldcs(a.frags + static_cast<size_t>(P.frag_base + b * (P.n_vtiles / K) + v0 / K) * rows + idx);
+            float cx = f.x, cy = f.y, cz = f.z;
+            // tiles of the chunk beyond the span of the CTA that owns its first tile: stored one by one
+            uint32_t u = min(u0 + K, s0.begin + s0.count);
+            uint32_t g = g0;
+            Span sg = s0;
+            for (; u < u0 + K; ++u) {
+                while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
+                f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx);
+                cx += f.x;
+                cy += f.y;
+                cz += f.z;
+            }
+            sx += cx;
+            sy += cy;
+            sz += cz;
+        }
+        const uint64_t row = a.row_begin + i;
+        float* out = a.acc + 3ull * row;
+        out[0] = sx;
+        out[1] = sy;
+        out[2] = sz;
+        if (a.tail.pos) {
+            // movement: position.point += velocity * dt (crates/n-body/src/lib.rs:92), then
+            // acceleration: velocity += acceleration * dt (:101) -- the order the schedule produced;
+            // separate roundings like the Rust code
+            float* p = a.tail.pos + 3ull * row;
+            float* v = a.tail.vel + 3ull * row;
+            const float vx = v[0], vy = v[1], vz = v[2];
+            const float px = __fadd_rn(p[0], __fmul_rn(vx, a.tail.dt));
+            const float py = __fadd_rn(p[1], __fmul_rn(vy, a.tail.dt));
+            const float pz = __fadd_rn(p[2], __fmul_rn(vz, a.tail.dt));
+            p[0] = px;
+            p[1] = py;
+            p[2] = pz;
+            v[0] = __fadd_rn(vx, __fmul_rn(sx, a.tail.dt));
+            v[1] = __fadd_rn(vy, __fmul_rn(sy, a.tail.dt));
+            v[2] = __fadd_rn(vz, __fmul_rn(sz, a.tail.dt));
+            if (a.tail.posm)
+                store_posm(a.push, a.tail.posm, a.tail.posm_offset + row, px * a.tail.pscale, py * a.tail.pscale,
+                           pz * a.tail.pscale, __fmul_rn(a.tail.g, a.tail.mass[row]));
         }
     }
-    const uint64_t row = a.row_begin + i;
-    float* out = a.acc + 3ull * row;
-    out[0] = sx;
-    out[1] = sy;
-    out[2] = sz;
-    if (a.tail.pos) {
-        // movement: position.point += velocity * dt (crates/n-body/src/lib.rs:92), then
-        // acceleration: velocity += acceleration * dt (:101) -- the order the schedule produced;
-        // separate roundings like the Rust code
-        float* p = a.tail.pos + 3ull * row;
-        float* v = a.tail.vel + 3ull * row;
-        const float vx = v[0], vy = v[1], vz = v[2];
-        const float px = __fadd_rn(p[0], __fmul_rn(vx, a.tail.dt));
-        const float py = __fadd_rn(p[1], __fmul_rn(vy, a.tail.dt));
-        const float pz = __fadd_rn(p[2], __fmul_rn(vz, a.tail.dt));
-        p[0] = px;
-        p[1] = py;
-        p[2] = pz;
-        v[0] = __fadd_rn(vx, __fmul_rn(sx, a.tail.dt));
-        v[1] = __fadd_rn(vy, __fmul_rn(sy, a.tail.dt));
-        v[2] = __fadd_rn(vz, __fmul_rn(sz, a.tail.dt));
-        if (a.tail.posm) {
-            const uint64_t J = a.tail.posm_offset + row;
-            float* d = a.tail.posm + (J >> 1) * 8 + (J & 1);
-            d[0] = px * a.tail.pscale;
-            d[2] = py * a.tail.pscale;
-            d[4] = pz * a.tail.pscale;
-            d[6] = __fmul_rn(a.tail.g, a.tail.mass[row]);
-        }
-    }
+    if (a.tail.posm) push_end(a.push);
 }
 
 __global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict__ pos,
                                                         const float* __restrict__ mass, float g,
                                                         float* __restrict__ posm, uint64_t row_begin,
-                                                        uint64_t n, uint64_t dst_offset, float pscale) {
+                                                        uint64_t n, uint64_t n_pad, uint64_t dst_offset, float pscale,
+                                                        const PeerPush push) {
     const uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (k >= n) return;
-    const uint64_t row = row_begin + k;
-    const uint64_t J = dst_offset + k;
-    float* d = posm + (J >> 1) * 8 + (J & 1);
-    d[0] = pos[3 * row + 0] * pscale;
-    d[2] = pos[3 * row + 1] * pscale;
-    d[4] = pos[3 * row + 2] * pscale;
-    d[6] = __fmul_rn(g, mass[row]);
-}
-
-__global__ void __launch_bounds__(256) pad_posm_kernel(float* __restrict__ posm, uint64_t begin,
-                                                       uint64_t end) {
-    const uint64_t J = begin + blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
-    if (J >= end) return;
-    float* d = posm + (J >> 1) * 8 + (J & 1);
-    d[0] = 0.f;
-    d[2] = 0.f;
-    d[4] = 0.f;
-    d[6] = 0.f;
+    push_begin(push);
+    if (k < n) {
+        const uint64_t row = row_begin + k;
+        store_posm(push, posm, dst_offset + k, pos[3 * row + 0] * pscale, pos[3 * row + 1] * pscale,
+                   pos[3 * row + 2] * pscale, __fmul_rn(g, mass[row]));
+    } else if (k < n + n_pad) {
+        store_posm(push, posm, dst_offset + k, 0.f, 0.f, 0.f, 0.f);  // null body: contributes exactly zero
+    }
+    push_end(push);
 }
 
 }  // namespace
@@ -497,8 +615,12 @@ const GravityVariant kVariants[kGravVariantCount] = {
     {4, 1, 12, false},  // 5  i-packed, exact mask on every pair
     {4, 1, 8, true},    // 6  as 0 with 8 consumer warps
     {8, 1, 8, true},    // 7  as 0 with 4 row pairs per thread (half the LDS, worse ptxas schedule)
-    {4, 1, 12, true},   // 8  TIMING ONLY: 0 without MUFU.RSQ (wrong results)
-    {4, 1, 12, false},  // 9  TIMING ONLY: 4 without the detector (wrong results for coincident bodies)
+    {4, 1, 12, true},   // 8  as 0 with the tile loop unrolled 16 times (half the loop overhead, twice the code)
+    {4, 1, 12, true},   // 9  as 0 with the tile loop unrolled 32 times (30 KB of loop body)
+#ifdef RECS_GPU_ABLATIONS  // never in the shipped library: tools/ builds only (make ablations)
+    {4, 1, 12, true},   // 10 TIMING ONLY: 0 without MUFU.RSQ (wrong results)
+    {4, 1, 12, false},  // 11 TIMING ONLY: 4 without the detector (wrong results for coincident bodies)
+#endif
 };
 GravityKernel variant_kernel(int v) {
     switch (v) {
@@ -519,16 +641,22 @@ GravityKernel variant_kernel(int v) {
         case 7:
             return nbody_gravity_kernel<8, 1, 2, true, 8, true, kAblOverflow>;
         case 8:
-            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow | kAblNoMufu>;
+            return nbody_gravity_kernel<4, 1, 16, true, 12, true, kAblOverflow>;
         case 9:
+            return nbody_gravity_kernel<4, 1, 32, true, 12, true, kAblOverflow>;
+#ifdef RECS_GPU_ABLATIONS
+        case 10:
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow | kAblNoMufu>;
+        case 11:
             return nbody_gravity_kernel<4, 1, 4, true, 12, true, kAblCubeFirst | kAblNoDetector>;
+#endif
     }
     return nullptr;
 }
 }  // namespace
 
 GravityVariant gravity_variant(int index) { return kVariants[index]; }
-// tile ring + the running-sum slots of one i-block
+// tile ring + the running-prefix slots of one i-block
 static int gravity_smem_bytes(int variant) { return kGravSmemBytes + kVariants[variant].rows() * (int)sizeof(float4); }
 
 cudaError_t gravity_prepare() {
@@ -549,31 +677,27 @@ int gravity_max_ctas_per_sm(int variant) {
 }
 
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s) {
-    if (a.launch.n_vtiles == 0 || a.launch.n_iblocks == 0) return cudaSuccess;
-    variant_kernel(a.variant)<<<a.launch.grid, kVariants[a.variant].threads(), gravity_smem_bytes(a.variant), s>>>(a);
+    if (a.work.n_iblocks == 0 || a.phase_begin >= a.phase_end) return cudaSuccess;
+    variant_kernel(a.variant)<<<a.work.grid, kVariants[a.variant].threads(), gravity_smem_bytes(a.variant), s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s) {
-    if (a.row_count == 0) return cudaSuccess;
-    const uint32_t grid = (a.row_count + 255) / 256;
+    if (a.row_count == 0 && !(a.tail.posm && a.push.n)) return cudaSuccess;
+    // a pushing rank always launches (at least one CTA): its peers wait for the generation flag
+    const uint32_t grid = std::max<uint32_t>((a.row_count + 255) / 256, 1u);
     nbody_gravity_reduce_kernel<<<grid, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
-                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, float pscale, cudaStream_t s) {
-    if (n == 0) return cudaSuccess;
-    const uint64_t grid = (n + 255) / 256;
-    pack_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(pos, mass, g, posm, row_begin, n,
-                                                                dst_offset, pscale);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s) {
-    if (end <= begin) return cudaSuccess;
-    const uint64_t grid = (end - begin + 255) / 256;
-    pad_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(posm, begin, end);
+                             uint64_t row_begin, uint64_t n, uint64_t n_pad, uint64_t dst_offset, float pscale,
+                             const PeerPush& push, cudaStream_t s) {
+    if (n + n_pad == 0 && push.n == 0) return cudaSuccess;
+    // a pushing rank always launches (at least one CTA): its peers wait for the generation flag
+    const uint64_t grid = std::max<uint64_t>((n + n_pad + 255) / 256, 1);
+    pack_posm_kernel<<<static_cast<uint32_t>(grid), 256, 0, s>>>(pos, mass, g, posm, row_begin, n, n_pad,
+                                                                dst_offset, pscale, push);
     return cudaGetLastError();
 }
 

@@ -483,7 +483,8 @@ int32_t playback_commands(recs_app* app) {
                 if (mit == app->mirror.end() || mit->second.bound_version != kv.second.version_before || mit->second.host_dirty)
                     continue;  // never bound, structurally out of date, or the host copy is the newer one: regular re-bind
                 resident.insert(ColKey(arch, col.first));
-                if (a.entities.size() > kv.second.len_before) {
+                // zero-sized components (marker types) are bound with no rows: nothing to append, nothing to move
+                if (a.entities.size() > kv.second.len_before && col.second.elem != 0) {
                     st = recs_gpu_column_append(app->gpu, arch, col.first, col.second.data.data(), a.entities.size());
                     if (st != RECS_OK) return gpu_fail(app, st);
                 }
@@ -511,9 +512,8 @@ int32_t playback_commands(recs_app* app) {
             if (a.version == kv.second.version_before) continue;
             std::vector<uint64_t> comps;
             for (auto& col : a.columns)
-                if (resident.count(ColKey(arch, col.first))) comps.push_back(col.first);
-            if (comps.empty()) continue;
-            if (kv.second.removed) {
+                if (resident.count(ColKey(arch, col.first)) && col.second.elem != 0) comps.push_back(col.first);
+            if (kv.second.removed && !comps.empty()) {
                 std::vector<uint32_t> dst, src;
                 kv.second.fold.moves(&dst, &src);
                 st = recs_gpu_archetype_move_rows(app->gpu, arch, comps.data(), (uint32_t)comps.size(), dst.data(), src.data(),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace recs {
 
@@ -14,8 +15,6 @@ constexpr int kGravStages = 4;
 constexpr int kGravTileBytes = kGravTile * 16;                 // 4 KiB
 constexpr int kGravSmemBytes = kGravStages * kGravTileBytes;   // 16 KiB dynamic smem
 
-// One launch of the interaction kernel: rows [row_begin, row_begin+row_count) of the outer
-// Position column against j tiles [tile_offset, tile_offset + n_vtiles) (mod n_tiles_total).
 // Kernel variants (register blocking x resident CTAs per SM), selected per context.
 struct GravityVariant {
     int rows_per_thread;  // bodies i per consumer thread
@@ -26,7 +25,11 @@ struct GravityVariant {
     int threads() const { return consumer_threads() + 32; }
     int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
+#ifdef RECS_GPU_ABLATIONS
+constexpr int kGravVariantCount = 12;  // 10 and 11 are timing-only ablations with WRONG results (tools/ builds only)
+#else
 constexpr int kGravVariantCount = 10;
+#endif
 constexpr int kGravVariantDefault = 0;
 constexpr int kGravVariantSmall = 2;    // up to kGravSmallRows outer rows
 constexpr int kGravVariantMedium = 3;   // up to kGravMediumRows outer rows
@@ -40,13 +43,55 @@ constexpr float kGravPosScale = 2.3283064365386963e-10f;   // 2^-32
 constexpr float kGravPosUnscale = 4294967296.f;            // 2^32
 constexpr float kGravOutScale = 5.4210108624275222e-20f;   // 2^-64 = pos_scale^2
 
-struct GravityLaunch {
-    uint32_t grid;        // persistent CTAs (stream-K workers)
-    uint32_t n_iblocks;   // ceil(row_count / rows per i-block)
-    uint32_t n_vtiles;    // tiles visited by this launch
-    uint32_t tile_offset; // first tile visited
-    uint32_t frag_base;   // first fragment slot of this launch
+// ---- the summation tree of one row (what makes a result independent of grid size, launch split and rank count) --
+//   tile sum   : the 256 bodies of one j tile, in registers, starting from zero
+//   chunk sum  : `chunk_tiles` consecutive tile sums (tiles [c*K, (c+1)*K) of the mirror), added in ascending
+//                tile order starting from zero
+//   row total  : the chunk sums, added in ascending chunk order starting from zero
+// chunk_tiles is a function of the body count alone (gravity_chunk_tiles), so which CTA / launch / GPU produced a
+// tile sum does not change a bit of the result.  The work of a launch is stream-K dealt as before: the units
+// (i-block, tile) of a PHASE -- a rotated run of whole chunks -- are cut into equal contiguous spans, one per
+// persistent CTA.  A CTA that enters a chunk at its first tile accumulates the chunk's running prefix and stores it
+// once ("prefix fragment" of (i-block, chunk)); a CTA whose span begins in the middle of a chunk stores the tile sums of
+// the rest of that chunk one by one ("tile fragments", at most K-1 per CTA and phase), and the reduce kernel continues
+// the prefix with them in tile order.
+constexpr uint32_t kGravTargetChunks = 32;
+inline uint32_t gravity_chunk_tiles(uint64_t n_bodies) {
+    const uint64_t tiles = (n_bodies + kGravTile - 1) / kGravTile;
+    const uint64_t k = (tiles + kGravTargetChunks - 1) / kGravTargetChunks;
+    return (uint32_t)(k ? k : 1);
+}
+
+// One phase: every i-block against tiles [tile_offset, tile_offset + n_vtiles) (mod n_tiles_total).  A single-GPU
+// launch has one phase over all tiles; a rank of a sharded run visits its own slice first (phase 0), then the other
+// ranks' slices in rotated order (phase 1).
+struct GravityPhase {
+    uint32_t n_vtiles;        // tiles visited per i-block: whole chunks
+    uint32_t tile_offset;     // first tile visited: a chunk boundary
+    uint32_t frag_base;       // prefix fragment of (i-block b, chunk cv of the phase): frag_base + b * (n_vtiles / K) + cv
+    uint32_t tile_frag_base;  // tile fragment of CTA g, unit u: tile_frag_base + g * (K - 1) + (u - span begin of g)
 };
+
+struct GravityWork {
+    uint32_t grid;            // persistent CTAs (stream-K workers), the same for every phase
+    uint32_t n_iblocks;       // ceil(row_count / rows per i-block)
+    uint32_t n_tiles_total;   // tiles of the mirror: a multiple of chunk_tiles
+    uint32_t chunk_tiles;     // K
+    uint32_t n_phases;
+    GravityPhase phase[2];
+};
+
+// Number of fragment slots (of rows-per-i-block float4 each) a work description needs; assigns the bases.
+inline uint32_t gravity_assign_frag_slots(GravityWork& w) {
+    uint32_t next = 0;
+    for (uint32_t p = 0; p < w.n_phases; ++p) {
+        w.phase[p].frag_base = next;
+        next += w.n_iblocks * (w.phase[p].n_vtiles / w.chunk_tiles);
+        w.phase[p].tile_frag_base = next;
+        next += w.phase[p].n_vtiles ? w.grid * (w.chunk_tiles - 1) : 0;
+    }
+    return next;
+}
 
 struct GravityArgs {
     const float4* posm;   // pair-interleaved {x0 x1 y0 y1 | z0 z1 gm0 gm1}, n_tiles_total tiles
@@ -54,11 +99,37 @@ struct GravityArgs {
     float4* frags;        // fragment workspace, rows-per-i-block float4 per slot
     uint32_t row_begin;
     uint32_t row_count;
-    uint32_t n_tiles_total;
     float eps;
-    GravityLaunch launch;
+    uint32_t self_offset; // mirror index of outer row 0 when the outer archetype is part of the nested query, else ~0u:
+                          // the tile holding a warp's own bodies goes straight to the exact path
+    GravityWork work;
+    uint32_t phase_begin, phase_end;  // phases this launch runs
+    // sharded run with a peer-pushed mirror (null flags: every tile is ready when the kernel starts)
+    const uint32_t* flags;    // flags[r] = newest mirror generation rank r has pushed into this GPU
+    uint32_t wait_gen;        // generation this launch reads
+    uint32_t tiles_per_rank;
+    uint32_t own_rank;
+    uint32_t* error;          // set to 1 when a wait timed out (host-mapped)
     int variant;
 };
+
+// Where refreshed mirror rows go besides the local mirror: the same slot of every peer's NEXT mirror buffer, followed
+// by a generation flag (release, system scope) once every CTA of the pushing kernel has stored its rows.
+constexpr int kGravMaxPeers = 16;
+struct PeerPush {
+    uint32_t n;                          // 0: single GPU / NCCL exchange, write `posm` of the tail / pack alone
+    uint32_t gen;                        // generation being pushed
+    float* posm[kGravMaxPeers];          // every rank's buffer for `gen` (own rank included)
+    uint32_t* flag[kGravMaxPeers];       // &flags[own rank] on every rank
+    const uint32_t* local_flags;         // own flags: all must have reached gen - 1 before the push overwrites
+    uint32_t* done_counter;              // local: CTAs of the pushing kernel that have stored their rows
+    uint32_t* error;
+};
+inline PeerPush no_peer_push() {
+    PeerPush p;
+    memset(&p, 0, sizeof p);
+    return p;
+}
 
 // Optional fused tail of the n-body tick (schedule order gravity -> movement -> acceleration over the
 // same rows): after the fragment sum the same thread integrates its row and refreshes posm.
@@ -78,25 +149,24 @@ struct GravityReduceArgs {
     float* acc;           // Acceleration column, 3 floats per row
     uint32_t row_begin;
     uint32_t row_count;
-    uint32_t n_launches;  // 1 (single GPU) or 2 (local tiles, then remote tiles)
     uint32_t iblock_rows; // rows per i-block of the variant that produced the fragments
-    GravityLaunch launch[2];
+    GravityWork work;
     GravityTail tail;
+    PeerPush push;
 };
 
-// Number of fragment slots a launch may touch.
-inline uint32_t gravity_frag_slots(const GravityLaunch& l) { return l.grid + l.n_iblocks; }
 int gravity_max_ctas_per_sm(int variant);  // occupancy of the interaction kernel on the current device
 cudaError_t gravity_prepare();  // one-time function attributes
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s);
 cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
 
-// Position(12 B) + Mass(4 B) rows [0, n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
-// gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`.
+// Position(12 B) + Mass(4 B) rows [row_begin, row_begin + n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
+// gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`; bodies [dst_offset + n,
+// dst_offset + n + n_pad) become null bodies (gm = 0) so partially filled tiles contribute nothing.  With
+// push.n > 0 the rows go to every peer's mirror instead of `posm`, followed by the generation flag.
 cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,
-                             uint64_t row_begin, uint64_t n, uint64_t dst_offset, float pscale, cudaStream_t s);
-// Null bodies (gm = 0) for [begin, end) so partially filled tiles contribute nothing.
-cudaError_t launch_pad_posm(float* posm, uint64_t begin, uint64_t end, cudaStream_t s);
+                             uint64_t row_begin, uint64_t n, uint64_t n_pad, uint64_t dst_offset, float pscale,
+                             const PeerPush& push, cudaStream_t s);
 
 // Above this many bytes touched per launch a streaming kernel is HBM-bound (the L2 is 126 MB); below it, its
 // columns stay L2-resident from one tick to the next.  Measured kernel choices hang on it (streaming.cu, context.cu).
@@ -108,12 +178,6 @@ constexpr uint64_t kStreamL2Footprint = 96ull << 20;
 // `*velocity += acceleration * FIXED_TIME_STEP` (:101) and, with a == 1, simple_iter's
 // `position.0 += velocity.0` (crates/ecs_bench_suite/src/recs/simple_iter.rs:48).
 cudaError_t launch_axpy_rn(float* y, const float* x, float a, uint64_t n, cudaStream_t s);
-// movement fused with the posm refresh of the moved rows (n-body tick): pos += vel*dt and
-// posm[dst_offset + row] = {pos, G*m}.
-cudaError_t launch_movement_pack(float* pos, const float* vel, const float* mass, float dt, float g,
-                                 float* posm, uint64_t row_begin, uint64_t n, uint64_t dst_offset,
-                                 cudaStream_t s);
-
 // rain (crates/rain-simulation/src/lib.rs:62-96); vel/pos are 3-float rows.
 cudaError_t launch_rain_gravity(float* vel, uint64_t n, float gravity_dt, float terminal,
                                 cudaStream_t s);

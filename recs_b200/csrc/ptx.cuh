@@ -28,6 +28,16 @@ __device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// a + b with the guarantee that the add stays an add.  ptxas (12.9) contracts `mul.rn.f32x2` + `add.rn.f32x2` into
+// FFMA2 despite the explicit .rn and regardless of -fmad=false (it even rewrites fma(a, b, -0) and fma(a, 1, b) to get
+// there), so where a product must be rounded on its own the sum is formed with two scalar add.rn.f32, which it
+// leaves alone (checked in SASS: FMUL2 x3 + FADD x4 for the reference's (dx*dx + dy*dy) + dz*dz).
+__device__ __forceinline__ f32x2 add2_unfused(f32x2 a, f32x2 b) {
+    float a0, a1, b0, b1;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a0), "=f"(a1) : "l"(a));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(b0), "=f"(b1) : "l"(b));
+    return pack(__fadd_rn(a0, b0), __fadd_rn(a1, b1));
+}
 __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     f32x2 d;
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
@@ -101,6 +111,41 @@ __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_
 // Makes this thread's generic-proxy shared-memory writes visible to the async proxy (TMA) that will read them.
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+
+// ---- cross-GPU flags (peer-mapped memory over NVLink) ------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Orders earlier generic-proxy observations (the acquire of a flag) before later async-proxy (TMA) reads of global memory.
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
+// Spins until *flag has reached generation `gen` (wrap-safe).  Bounded: after `timeout_ns` it raises *error and
+// returns false, so a missing peer ends in a reported error instead of a hung GPU.
+__device__ __forceinline__ bool wait_generation(const uint32_t* flag, uint32_t gen, uint32_t* error,
+                                                unsigned long long timeout_ns = 30000000000ull) {
+    if (static_cast<int32_t>(ld_acquire_sys(flag) - gen) >= 0) return true;
+    const unsigned long long t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (static_cast<int32_t>(ld_acquire_sys(flag) - gen) < 0) {
+        __nanosleep(64);
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) {
+            if (error) *reinterpret_cast<volatile uint32_t*>(error) = 1u;
+            return false;
+        }
+    }
+    return true;
 }
 
 }  // namespace ptx

@@ -216,6 +216,21 @@ class GpuContext:
         buf = (C.c_uint8 * _lib.NCCL_ID_BYTES)(*unique_id)
         self._check(lib.recs_gpu_comm_init(self._ctx, buf), "recs_gpu_comm_init")
 
+    def exchange_export(self, max_bodies: int) -> bytes:
+        """Allocates the peer-push exchange buffers; returns this rank's CUDA IPC handle (recs_gpu_exchange_export)."""
+        buf = (C.c_uint8 * _lib.IPC_HANDLE_BYTES)()
+        self._check(lib.recs_gpu_exchange_export(self._ctx, max_bodies, buf), "recs_gpu_exchange_export")
+        return bytes(buf)
+
+    def exchange_import(self, handles: Sequence[bytes]) -> None:
+        """Maps every rank's exchange buffers; `handles` in rank order (recs_gpu_exchange_import)."""
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob))(*blob)
+        self._check(lib.recs_gpu_exchange_import(self._ctx, buf, len(handles)), "recs_gpu_exchange_import")
+
+    def exchange_mode(self) -> str:
+        return {0: "single", 1: "nccl-allgather", 2: "peer-push"}[lib.recs_gpu_exchange_mode(self._ctx)]
+
     def shard_rows(self, n_rows: int) -> tuple[int, int]:
         b, e = C.c_uint64(), C.c_uint64()
         self._check(lib.recs_gpu_shard_rows(self._ctx, n_rows, C.byref(b), C.byref(e)), "recs_gpu_shard_rows")

@@ -114,3 +114,17 @@ def reference_order_gravity(ctx: GpuContext, outer_pos: np.ndarray, qpos: np.nda
     ctx.run_system(sid)
     ctx.download(outer_archetype, ACCELERATION)
     return acc
+
+
+class ReferenceOrderNBodyApp(NBodyGpuApp):
+    """The same three systems with `gravity` replaced by the generic reference-order system above: the reference's own
+    arithmetic and summation order, executed on the device (bit-identical to the CPU oracle; about 7x slower than the
+    hand-written kernel).  Used where the reference trajectory is needed at sizes the CPU oracle takes minutes for."""
+
+    def __init__(self, ctx: GpuContext, pos, mass, vel, acc, tick_order=("gravity", "movement", "acceleration")):
+        super().__init__(ctx, pos, mass, vel, acc, tick_order)
+        self.systems["gravity"] = ctx.create_pair_kernel_system(
+            "gravity_reference_order", REFERENCE_ORDER_GRAVITY_SOURCE, "Total", "pair", "finish", REFERENCE_ORDER_GRAVITY_PARAMS)
+        ctx.set_archetypes(self.systems["gravity"], [BODY_ARCHETYPE])
+        ctx.set_query_archetypes(self.systems["gravity"], [BODY_ARCHETYPE])
+        self.set_tick_order(tick_order)

@@ -1,4 +1,4 @@
-"""Index-sharded n-body over NCCL on >= 2 GPUs (skipped on a single-GPU box)."""
+"""Index-sharded n-body: peer-push exchange (also on a single-GPU box, ranks time-slicing it) and NCCL exchange (>= 2 GPUs)."""
 import os
 import socket
 import subprocess
@@ -18,20 +18,35 @@ def _gpu_count():
         return 0
 
 
-@pytest.mark.parametrize("bodies,ticks,mode", [(10000, 1, "full"), (5000, 4, "full"), (300, 2, "full"), (7000, 3, "own")])
-def test_sharded_ticks_match_oracle(bodies, ticks, mode):
-    """mode "own": every rank uploads / downloads only the rows it owns (recs_gpu_upload_rows) and its host copy of
-    every other row is NaN -- nothing outside the shard may be read from the host."""
-    n_gpu = _gpu_count()
-    if n_gpu < 2:
-        pytest.skip("needs at least 2 GPUs")
-    world = 2 if n_gpu < 4 else 4
+def _torchrun(world, script, args, env=None, timeout=420):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), "tests/tools/multi_gpu_check.py", str(bodies), str(ticks), mode]
-    proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+           "--master-port", str(port), script] + [str(a) for a in args]
+    full_env = dict(os.environ)
+    full_env.update(env or {})
+    return subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=timeout, env=full_env)
+
+
+@pytest.mark.parametrize("bodies,ticks,mode", [(10000, 1, "full"), (5000, 4, "full"), (300, 2, "full"), (7000, 3, "own"),
+                                               (70000, 2, "own")])
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
+def test_sharded_ticks_match_oracle(bodies, ticks, mode, exchange):
+    """mode "own": every rank uploads / downloads only the rows it owns (recs_gpu_upload_rows) and its host copy of
+    every other row is NaN -- nothing outside the shard may be read from the host.  Every rank also compares its rows
+    with the single-GPU result of the same ticks bit for bit.
+
+    On a single-GPU box the ranks are separate processes time-slicing GPU 0, which covers the peer-push exchange
+    (CUDA IPC mapping, generation flags, one persistent launch per tick); the NCCL exchange needs one GPU per rank."""
+    n_gpu = _gpu_count()
+    if n_gpu < 1:
+        pytest.skip("needs a GPU")
+    if n_gpu < 2 and exchange == "nccl":
+        pytest.skip("NCCL needs one GPU per rank")
+    world = 2 if n_gpu < 4 else 4
+    env = {"RECS_TEST_SAME_DEVICE": "1"} if n_gpu < 2 else {}
+    proc = _torchrun(world, "tests/tools/multi_gpu_check.py", [bodies, ticks, mode, exchange], env)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
 
 
@@ -39,13 +54,8 @@ def test_sharded_streaming_systems_need_no_exchange():
     """Rain tick, simple_iter and a generic system: each rank streams its own contiguous slice of every archetype
     (independent units, no data-path collective), bit-exact, other rows untouched."""
     n_gpu = _gpu_count()
-    if n_gpu < 2:
-        pytest.skip("needs at least 2 GPUs")
+    if n_gpu < 1:
+        pytest.skip("needs a GPU")
     world = 2 if n_gpu < 4 else 4
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        port = s.getsockname()[1]
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(port), "tests/tools/multi_gpu_stream_check.py", "100003"]
-    proc = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    proc = _torchrun(world, "tests/tools/multi_gpu_stream_check.py", [100003], {"RECS_TEST_SAME_DEVICE": "1"} if n_gpu < 2 else {})
     assert proc.returncode == 0 and "MULTI_GPU_STREAM_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
