@@ -11,21 +11,31 @@ interactions per second, one interaction = one ordered pair (i, j) including j =
 
   value      device-resident: columns already in HBM, K ticks, CUDA-event time per tick summed,
              L2 flushed between ticks outside the events; max over ranks.
-  e2e        the same tick through the C ABI with HOST (pinned) columns: upload of all four
-             columns, tick, download of Position/Velocity/Acceleration inside the timed region.
+  e2e        the same tick through the C ABI with HOST (pinned) columns: upload of the tick's
+             input columns (Position, Mass, Velocity), tick, download of Position / Velocity /
+             Acceleration inside the timed region.
   roofline   the interaction kernel alone (CUDA events around its launches) against the FP32 FMA
              rate measured live on the same GPU with a register-resident FFMA loop.
+  parity     4 096 sampled rows of the first tick against the oracle: counts of rows
+             over 1e-4 vs the reference-order f32 sum and vs the f64 sum, and the arbitration of
+             rows where the reference's own f32 rounding is the larger error.
+  configs    (N = 1) sub-records for configs[0] (1 000 bodies x 100 ticks) and configs[1]
+             (65 536 bodies), each with value, roofline, parity, clocks and its cpu_baseline.
   cpu_baseline / --impl reference
              oracle/nbody_oracle.c (C restatement of the reference's CPU systems driven with its
              worker-pool policy) on the box's host cores, on a bounded row sample of the same
-             workload.  The Rust reference itself cannot be built here (no cargo/rustc).
+             workload, built on the box with -march=native (the reference's .cargo/config.toml
+             asks for target-cpu=native).  The Rust reference itself cannot be built here.
 
-N > 1 (torchrun, one rank per GPU): the B bodies are index-sharded, each rank computes its rows
-and positions are exchanged with an NCCL all-gather every tick ("scaling": "strong").
+N > 1 (torchrun, one rank per GPU): the B bodies are index-sharded, each rank computes its rows;
+refreshed positions are pushed into every rank's mirror over NVLink by the tick's integration tail
+(peer push over CUDA IPC; `RECS_GPU_EXCHANGE=nccl` selects the ncclAllGather exchange), "scaling":
+"strong".
 """
 from __future__ import annotations
 
 import argparse
+import importlib.util
 import json
 import os
 import subprocess
@@ -40,12 +50,10 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_INTERACTION = 20.0  # all-pairs convention; the kernel issues 12 FMA-pipe lane-ops
 FMA_LANE_OPS_PER_INTERACTION = 12.0
-# dram__bytes_read.sum + dram__bytes_write.sum of one interaction-kernel launch on one GPU, from ncu
-# (profiles/r01_gravity_traffic_1M.csv, profiles/r01_gravity_default_ncu_summary.txt); the kernel is
-# FP32-bound, the figure only shows there are no wasted re-reads (posm + outer positions = 28 MB at 1 M)
-KERNEL_DRAM_TRAFFIC_BYTES = {1_048_576: 29_457_664 + 49_920, 65_536: 1_854_208}
 DEFAULT_BODIES = 1_048_576
 SEED = 1
+PARITY_ROWS = 4096  # "At 1 M: 4 096 sampled rows"
+ACC_TOL = 1e-4
 
 
 def parse_args():
@@ -57,7 +65,27 @@ def parse_args():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0] / configs[1] sub-records")
     return ap.parse_args()
+
+
+def load_scenes():
+    """recs_b200/scenes.py as a stand-alone module: the reference arm must not map librecs_gpu.so, which importing
+    the recs_b200 package does."""
+    spec = importlib.util.spec_from_file_location("recs_scenes", os.path.join(ROOT, "recs_b200", "scenes.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["recs_scenes"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def measured_traffic() -> dict:
+    """dram bytes per launch of the dominant kernels, from the kept ncu captures (profiles/r02_traffic.json names the
+    CSV each figure was read from)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+    except Exception:
+        return {}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -72,15 +100,17 @@ class ClockSampler:
         "clocks_event_reasons.sw_power_cap"
     )
 
-    def __init__(self, device: int):
+    def __init__(self, device: int, period_ms: int = 100):
         self.device = device
+        self.period_ms = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms",
+                 str(self.period_ms)],
                 stdout=subprocess.PIPE,
                 stderr=subprocess.DEVNULL,
                 text=True,
@@ -127,27 +157,25 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU side (oracle) -- reported baseline and the --impl reference arm
 # --------------------------------------------------------------------------------------------------
-def cpu_sample_rate(n_bodies: int, budget_s: float, threads: int):
-    """Times one tick of the oracle's worker pool on rows [0, S) x all n_bodies j (a bounded row
-    sample of the workload).  Returns (interactions/s, S, seconds)."""
-    import oracle
-    from recs_b200 import scenes
+def host_threads() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
-    orc = oracle.load_nbody()
-    pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n_bodies), SEED)
-    # calibrate on a small row block
-    cal_rows = min(n_bodies, max(64, threads * 16))
-    t0 = time.perf_counter()
-    _pool_rows(orc, pos, mass, vel, acc, cal_rows, threads)
-    cal = time.perf_counter() - t0
-    rate = cal_rows * n_bodies / max(cal, 1e-9)
-    rows = int(min(n_bodies, max(cal_rows, rate * budget_s / n_bodies)))
-    rows = max(threads * 4 * 16, rows // (threads * 4) * (threads * 4)) if rows < n_bodies else rows
-    rows = min(rows, n_bodies)
-    t0 = time.perf_counter()
-    _pool_rows(orc, pos, mass, vel, acc, rows, threads)
-    sec = time.perf_counter() - t0
-    return rows * n_bodies / sec, rows, sec, (orc, pos, mass, vel, acc)
+
+def load_cpu_baseline_oracle():
+    """The oracle built ON THIS BOX with -march=native (the reference's .cargo/config.toml asks for
+    target-cpu=native), still -ffp-contract=off.  Falls back to the portable build when no compiler is present.
+    Returns (NBodyOracle, note)."""
+    import oracle
+    from oracle import nbody as onb
+
+    try:
+        orc = onb.load_native()
+        return orc, "built on this box: gcc -O2 -march=native -ffp-contract=off (oracle/liboracle.so rebuilt in place)"
+    except Exception as exc:  # no gcc on the box: the portable build that travelled with the repo
+        return oracle.load_nbody(), f"portable build (no -march=native: {exc!r})"
 
 
 def _pool_rows(orc, pos, mass, vel, acc, rows, threads):
@@ -159,7 +187,6 @@ def _pool_rows(orc, pos, mass, vel, acc, rows, threads):
     if rows >= n:
         orc.run_pool(pos, mass, vel, acc, 1, threads)
         return
-    # outer iteration restricted to `rows` rows: columns of the sampled archetype slice + full query
     lib = orc.lib
     if not hasattr(lib, "_sample_ready"):
         z = C.c_size_t
@@ -170,22 +197,35 @@ def _pool_rows(orc, pos, mass, vel, acc, rows, threads):
     lib.oracle_nbody_run_pool_rows(pos, mass, vel, acc, n, rows, 1, threads, (C.c_int * 3)(0, 1, 2))
 
 
-def host_threads() -> int:
-    try:
-        return len(os.sched_getaffinity(0))
-    except AttributeError:
-        return os.cpu_count() or 1
+def cpu_sample_rate(orc, scenes, n_bodies: int, budget_s: float, threads: int):
+    """Times one tick of the oracle's worker pool on rows [0, S) x all n_bodies j (a bounded row
+    sample of the workload).  Returns (interactions/s, S, seconds, state)."""
+    pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n_bodies), SEED)
+    cal_rows = min(n_bodies, max(64, threads * 16))
+    t0 = time.perf_counter()
+    _pool_rows(orc, pos, mass, vel, acc, cal_rows, threads)
+    cal = time.perf_counter() - t0
+    rate = cal_rows * n_bodies / max(cal, 1e-9)
+    rows = int(min(n_bodies, max(cal_rows, rate * budget_s / n_bodies)))
+    rows = max(threads * 4 * 16, rows // (threads * 4) * (threads * 4)) if rows < n_bodies else rows
+    rows = min(rows, n_bodies)
+    t0 = time.perf_counter()
+    _pool_rows(orc, pos, mass, vel, acc, rows, threads)
+    sec = time.perf_counter() - t0
+    return rows * n_bodies / sec, rows, sec, (pos, mass, vel, acc)
 
 
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    scenes = load_scenes()
+    orc, build_note = load_cpu_baseline_oracle()
     threads = host_threads()
     steps = args.steps or 3
     per_step_budget = max(1.0, min(20.0, 90.0 / (steps + args.warmup)))
-    rate, rows, sec, state = cpu_sample_rate(args.bodies, per_step_budget, threads)
-    orc, pos, mass, vel, acc = state
+    rate, rows, sec, state = cpu_sample_rate(orc, scenes, args.bodies, per_step_budget, threads)
+    pos, mass, vel, acc = state
     for _ in range(max(args.warmup - 1, 0)):
         _pool_rows(orc, pos, mass, vel, acc, rows, threads)
     t0 = time.perf_counter()
@@ -215,7 +255,8 @@ def run_reference_arm(args) -> None:
             "cores": threads,
             "kind": "port",
             "sample": sample,
-            "note": "C restatement of recs' CPU systems + worker-pool segment policy (oracle/nbody_oracle.c); the Rust reference cannot be built here",
+            "note": "C restatement of recs' CPU systems + worker-pool segment policy (oracle/nbody_oracle.c); the Rust "
+                    "reference cannot be built here; " + build_note,
         },
         "e2e": {"value": value, "unit": "G interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -226,39 +267,259 @@ def run_reference_arm(args) -> None:
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def sampled_parity(app, host_state, rb, re, n_rows=32):
-    """Parity gate of the run: accelerations of sampled rows of this rank's shard after
-    the first tick against the oracle, all j.  Returns max norm-wise relative errors
-    (gpu vs reference-order f32, gpu vs f64, reference-order f32 vs f64)."""
+def _rel(a, b):
+    return np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)
+
+
+def sampled_parity(app, host_state, rb, re, n_rows, device, check_exact=True):
+    """Parity gate of the run: accelerations of `n_rows` sampled rows of this rank's shard after the
+    first tick against the oracle, all j.  Returns per-row error arrays (gpu vs reference-order f32, gpu vs f64,
+    reference-order f32 vs f64) and whether the generic reference-order kernel reproduces the oracle bit for bit."""
     import oracle
 
     orc = oracle.load_nbody()
     pos0, mass0 = host_state
-    rows = np.random.default_rng(11).choice(np.arange(rb, re), size=min(n_rows, re - rb), replace=False)
+    rows = np.sort(np.random.default_rng(11).choice(np.arange(rb, re), size=min(n_rows, re - rb), replace=False))
     ref32, ref64 = orc.gravity_sample(pos0, mass0, rows)
     got = app.acc[rows].astype(np.float64)
-
-    def rel(a, b):
-        return float((np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-30)).max())
-
-    # the same rows through the generic reference-order system (recs_b200/nbody.py): sequential fold in query order,
-    # IEEE division and square root -- must equal the oracle's f32 result bit for bit, at full problem size
+    # a subset of the rows through the generic reference-order system (recs_b200/nbody.py): sequential fold in query
+    # order, IEEE division and square root -- must equal the oracle's f32 result bit for bit, at full problem size
     exact = None
-    try:
-        from recs_b200 import GpuContext
-        from recs_b200.nbody import reference_order_gravity
+    if check_exact:
+        try:
+            from recs_b200 import GpuContext
+            from recs_b200.nbody import reference_order_gravity
 
-        with GpuContext(device=int(os.environ.get("LOCAL_RANK", "0")), use_cuda_graph=False) as check_ctx:
-            got_exact = reference_order_gravity(check_ctx, np.ascontiguousarray(pos0[rows]), pos0, mass0)
-        exact = bool(np.array_equal(got_exact.view(np.uint32), ref32.view(np.uint32)))
-    except Exception as exc:  # the check never invalidates the headline line
-        exact = repr(exc)
-    return rel(got, ref32.astype(np.float64)), rel(got, ref64), rel(ref32.astype(np.float64), ref64), exact
+            sub = rows[:: max(1, len(rows) // 128)]
+            with GpuContext(device=device, use_cuda_graph=False) as check_ctx:
+                got_exact = reference_order_gravity(check_ctx, np.ascontiguousarray(pos0[sub]), pos0, mass0)
+            want = ref32[:: max(1, len(rows) // 128)]
+            exact = bool(np.array_equal(got_exact.view(np.uint32), want.view(np.uint32)))
+        except Exception as exc:  # the check never invalidates the headline line
+            exact = repr(exc)
+    return _rel(got, ref32.astype(np.float64)), _rel(got, ref64), _rel(ref32.astype(np.float64), ref64), exact, rows
+
+
+def parity_record(err32, err64, ref_err64, exact, pos_exact, reduce_max, reduce_sum):
+    """The parity block of a bench line.  Arbitration rule: a row over the literal 1e-4 tolerance against
+    the reference-order f32 sum is attributed to the reference's own sequential-sum rounding when that sum is further
+    from the f64 sum than the GPU result is AND the GPU result is within 1e-5 of the f64 sum; any other row over the
+    tolerance is a failure of this implementation."""
+    over32 = err32 > ACC_TOL
+    explained = over32 & (ref_err64 > err64) & (err64 <= 1e-5)
+    return {
+        "rows": int(reduce_sum(len(err32))),
+        "tolerance": ACC_TOL,
+        "acc_max_rel_err_vs_oracle": reduce_max(float(err32.max())),
+        "acc_max_rel_err_vs_f64": reduce_max(float(err64.max())),
+        "oracle_f32_order_vs_f64_max": reduce_max(float(ref_err64.max())),
+        "rows_over_tol_vs_ref32": int(reduce_sum(int(over32.sum()))),
+        "rows_over_tol_vs_f64": int(reduce_sum(int((err64 > ACC_TOL).sum()))),
+        "rows_over_tol_where_reference_f32_is_the_inaccurate_side": int(reduce_sum(int(explained.sum()))),
+        "rows_failing_after_arbitration": int(reduce_sum(int((over32 & ~explained).sum()))),
+        "arbitration": "row passes if <= 1e-4 vs reference-order f32, or if the reference-order f32 sum is further from the f64 "
+                       "sum than the GPU result and the GPU result is <= 1e-5 from the f64 sum",
+        "pos_bit_exact_after_tick1": pos_exact,
+        "reference_order_generic_kernel_bit_exact": exact,
+    }
+
+
+def kernel_roofline(ctx, app, n, rows_here, k_steps, traffic):
+    tf_peak, mhz = ctx.measure_fp32_peak(packed=True)
+    ctx.enable_timing(True)
+    ctx.reset_timing()
+    for _ in range(k_steps):
+        app.tick(1)
+    t = ctx.timing()
+    ctx.enable_timing(False)
+    grav_ms = t["gravity_ms"] / k_steps  # all interaction-kernel launches of one tick on this rank
+    kernel_flops = FLOPS_PER_INTERACTION * rows_here * n
+    achieved_tf = kernel_flops / (grav_ms * 1e-3) / 1e12
+    fma_lane_rate = FMA_LANE_OPS_PER_INTERACTION * rows_here * n / (grav_ms * 1e-3)
+    return {
+        "bound": "fp32",
+        "kernel": "nbody_gravity_kernel",
+        "achieved": achieved_tf,
+        "peak": tf_peak,
+        "unit": "TFLOP/s",
+        "frac": achieved_tf / tf_peak,
+        "peak_source": "measured live on this GPU: register-resident FFMA2 loop (MEASURED_PEAKS.json has no FP32 figure)",
+        "peak_derived": 148 * 128 * 2 * mhz * 1e6 / 1e12,
+        "peak_derived_source": "148 SMs x 128 lanes x 2 FLOP x SM clock seen by the probe (SURVEY 8d formula)",
+        "flops_per_interaction": FLOPS_PER_INTERACTION,
+        "fma_pipe_frac": fma_lane_rate / (tf_peak * 1e12 / 2.0),
+        "kernel_ms_per_step": grav_ms,
+        "kernel_launches_per_step": t["gravity_launches"] / k_steps,
+        "kernel_share_of_step": grav_ms / (t["last_tick_chain_ms"] / k_steps) if t["last_tick_chain_ms"] else None,
+        "traffic": traffic,
+        "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, single GPU, "
+                        "profiles/r02_traffic.json)",
+        "sm_mhz_during_peak_probe": mhz,
+    }, t
+
+
+def config_subrecord(n, ticks_per_step, steps, device, traffic, scenes, cpu_orc, cpu_note):
+    """One secondary config on a fresh single-GPU context: value, roofline, parity, clocks, cpu_baseline."""
+    import oracle
+    from recs_b200 import GpuContext
+    from recs_b200.nbody import NBodyGpuApp
+
+    scene = scenes.EVERYTHING_HEAVY if n == 1000 else scenes.all_heavy_random_cube_with_bodies(n)
+    pos0, mass0, vel0, acc0 = scenes.spawn_bodies(scene, SEED)
+    orc = oracle.load_nbody()
+    with GpuContext(device=device, use_cuda_graph=True) as ctx:
+        cols = [ctx.pinned_empty(a.shape) for a in (pos0, mass0, vel0, acc0)]
+        for dst, src in zip(cols, (pos0, mass0, vel0, acc0)):
+            dst[...] = src
+        app = NBodyGpuApp(ctx, *cols)
+        app.upload()
+        app.tick(1)
+        app.download()
+        pref = pos0.copy()
+        orc.axpy(pref, vel0, orc.dt)
+        pos_exact = bool(np.array_equal(app.pos.view(np.uint32), pref.view(np.uint32)))
+        e32, e64, r64, exact, _ = sampled_parity(app, (pos0, mass0), 0, n, min(n, 1024), device, check_exact=False)
+        ident = lambda x: x
+        parity = parity_record(e32, e64, r64, exact, pos_exact, ident, ident)
+        if ticks_per_step > 1:
+            # the whole config: ticks_per_step ticks from the initial state against the oracle (drift)
+            for dst, src in zip(cols, (pos0, mass0, vel0, acc0)):
+                dst[...] = src
+            app.upload()
+            app.tick(ticks_per_step)
+            app.download()
+            ref = [a.copy() for a in (pos0, mass0, vel0, acc0)]
+            orc.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks_per_step)
+            den = lambda r: np.maximum(np.linalg.norm(r, axis=1), 1.0)
+            parity[f"drift_after_{ticks_per_step}_ticks"] = {
+                "pos_max": float((np.linalg.norm(app.pos.astype(np.float64) - ref[0], axis=1) / den(ref[0])).max()),
+                "vel_max": float((np.linalg.norm(app.vel.astype(np.float64) - ref[2], axis=1) / den(ref[2])).max()),
+                "bound": 1e-4,
+                "norm": "max_i |x_gpu - x_ref| / max(|x_ref|, 1)",
+            }
+        for _ in range(3):
+            app.tick(ticks_per_step)
+        ctx.synchronize()
+        sampler = ClockSampler(device, period_ms=20)
+        sampler.start()
+        ms = []
+        t_end = time.perf_counter() + 0.6  # at least this long under load, so the clock sampler sees it
+        while len(ms) < steps or time.perf_counter() < t_end:
+            ctx.flush_l2()
+            ctx.timer_start()
+            app.tick(ticks_per_step)
+            ms.append(ctx.timer_stop())
+            if len(ms) >= 20 * steps:
+                break
+        clocks = sampler.stop()
+        ms_step = float(np.mean(ms))
+        value = n * n * ticks_per_step / (ms_step * 1e-3) / 1e9
+        roof, _ = kernel_roofline(ctx, app, n, n, 10, traffic)
+        if ticks_per_step > 1:
+            roof["note"] = "launch-bound at this size: the tick is two small launches inside a CUDA graph (interaction kernel, reduce + integration tail)"
+        # end to end at this size: upload inputs, tick(s), download results
+        e0 = time.perf_counter()
+        e_steps = max(3, min(steps, 20))
+        for _ in range(e_steps):
+            app.upload(comps=app.INPUT_COMPONENTS)
+            app.tick(ticks_per_step)
+            app.download()
+        e2e_s = (time.perf_counter() - e0) / e_steps
+    threads = host_threads()
+    cpu = None
+    if cpu_orc is not None:
+        if n * n * ticks_per_step <= 2e9:  # measured directly: the whole config on the host cores
+            ref = [a.copy() for a in (pos0, mass0, vel0, acc0)]
+            t0 = time.perf_counter()
+            cpu_orc.run_pool(ref[0], ref[1], ref[2], ref[3], ticks_per_step, threads)
+            sec = time.perf_counter() - t0
+            cpu = {"value": n * n * ticks_per_step / sec / 1e9, "unit": "G interactions/s", "cores": threads, "kind": "port",
+                   "sample": f"the whole config: {n} bodies x {ticks_per_step} ticks, {sec:.2f} s", "note": cpu_note}
+        else:
+            rate, rows, sec, _ = cpu_sample_rate(cpu_orc, scenes, n, 6.0, threads)
+            cpu = {"value": rate / 1e9, "unit": "G interactions/s", "cores": threads, "kind": "port",
+                   "sample": f"{rows} of {n} outer rows x all {n} bodies, one tick, {sec:.1f} s", "note": cpu_note}
+    return {
+        "workload": f"nbody_{n}" + (f"_x{ticks_per_step}_ticks" if ticks_per_step > 1 else ""),
+        "value": value,
+        "unit": "G interactions/s",
+        "ms_per_step": ms_step,
+        "ticks_per_step": ticks_per_step,
+        "steps": len(ms),
+        "e2e": {"value": n * n * ticks_per_step / e2e_s / 1e9, "unit": "G interactions/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": int(28 * n), "d2h_bytes_per_step": int(36 * n)},
+        "roofline": roof,
+        "parity": parity,
+        "clocks": clocks,
+        "cpu_baseline": cpu,
+    }
+
+
+def sharded_small_check(rank, world, local_rank, dist, scenes):
+    """Every SCALE line carries it: 16 384 bodies, 2 ticks, sharded over the same ranks with the same exchange; every rank
+    checks ALL the rows it owns against the oracle and against the single-GPU result of the same library (bit for bit)."""
+    import oracle
+    from recs_b200 import GpuContext
+    from recs_b200.nbody import NBodyGpuApp
+
+    n, ticks = 16384, 2
+    start = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 5)
+    cols = [a.copy() for a in start]
+    ctx = GpuContext(device=local_rank, rank=rank, world_size=world, use_cuda_graph=False)
+    mode = setup_exchange(ctx, dist, rank, world, n)
+    rb, re = ctx.shard_rows(n)
+    app = NBodyGpuApp(ctx, *cols)
+    app.upload(rows=(rb, re))
+    app.tick(ticks)
+    app.download(rows=(rb, re))
+    ctx.synchronize()
+    dist.barrier()
+    ctx.close()
+    single = [a.copy() for a in start]
+    with GpuContext(device=local_rank, use_cuda_graph=False) as one:
+        app1 = NBodyGpuApp(one, *single)
+        app1.upload()
+        app1.tick(ticks)
+        app1.download()
+    same = all(np.array_equal(a[rb:re].view(np.uint32), b[rb:re].view(np.uint32))
+               for a, b in ((cols[0], single[0]), (cols[2], single[2]), (cols[3], single[3])))
+    ref = [a.copy() for a in start]
+    orc = oracle.load_nbody()
+    orc.run_pool(ref[0], ref[1], ref[2], ref[3], ticks, host_threads() // max(world, 1) or 1)
+    den = lambda r, f: np.maximum(np.linalg.norm(r[rb:re].astype(np.float64), axis=1), f)
+    err = lambda g, r, f: float((np.linalg.norm(g[rb:re].astype(np.float64) - r[rb:re], axis=1) / den(r, f)).max()) if re > rb else 0.0
+    mine = {"pos": err(cols[0], ref[0], 1.0), "vel": err(cols[2], ref[2], 1.0), "acc": err(cols[3], ref[3], 1e-30), "same": bool(same)}
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine)
+    return {
+        "bodies": n, "ticks": ticks, "rows_checked": "every row of every rank's shard", "exchange": mode,
+        "pos_max_rel_err": max(e["pos"] for e in everyone), "vel_max_rel_err": max(e["vel"] for e in everyone),
+        "acc_max_rel_err": max(e["acc"] for e in everyone),
+        "bit_identical_to_single_gpu_run": all(e["same"] for e in everyone),
+        "ok": all(e["same"] and e["pos"] <= 1e-4 and e["vel"] <= 1e-4 and e["acc"] <= 1e-3 for e in everyone),
+    }
+
+
+def setup_exchange(ctx, dist, rank, world, n):
+    """Peer push (CUDA IPC handles exchanged through torch.distributed) unless RECS_GPU_EXCHANGE=nccl."""
+    if os.environ.get("RECS_GPU_EXCHANGE") != "nccl":
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ctx.exchange_export(n))
+            ctx.exchange_import(handles)
+            return ctx.exchange_mode()
+        except Exception as exc:  # IPC mapping refused on this box: the NCCL exchange is the other GPU path
+            ctx.clear_error()
+            sys.stderr.write(f"[bench] peer-push exchange unavailable ({exc!r}); using the NCCL all-gather exchange\n")
+    uid = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    ctx.comm_init(uid[0])
+    return ctx.exchange_mode()
 
 
 def run_gpu_arm(args) -> None:
     from recs_b200 import GpuContext, scenes
-    from recs_b200.nbody import ACCELERATION, BODY_ARCHETYPE, MASS, POSITION, VELOCITY, NBodyGpuApp
+    from recs_b200.nbody import NBodyGpuApp
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -266,6 +527,7 @@ def run_gpu_arm(args) -> None:
     n = args.bodies
     steps = args.steps or (10 if n >= 500_000 else 50)
     warmup = max(args.warmup, 3)
+    traffic = measured_traffic()
 
     dist = None
     if world > 1:
@@ -276,11 +538,10 @@ def run_gpu_arm(args) -> None:
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    small = sharded_small_check(rank, world, local_rank, dist, scenes) if world > 1 else None
+
     ctx = GpuContext(device=local_rank, rank=rank, world_size=world, use_cuda_graph=True)
-    if world > 1:
-        uid = [ctx.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(uid[0])
+    exchange = setup_exchange(ctx, dist, rank, world, n) if world > 1 else "single"
     rb, re = ctx.shard_rows(n)
 
     # synthetic bodies in pinned host columns (the host side of the e2e path)
@@ -298,22 +559,23 @@ def run_gpu_arm(args) -> None:
             dist.barrier()
             torch.cuda.synchronize()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce_over_ranks(x: float, op: str) -> float:
         if dist is None:
             return x
         import torch
 
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM)
         return float(t.item())
+
+    max_over_ranks = lambda x: reduce_over_ranks(x, "max")
+    sum_over_ranks = lambda x: reduce_over_ranks(float(x), "sum")
 
     # ---- parity gate: first tick against the oracle on sampled rows -----------------------------
     app.upload()
     app.tick(1)
     app.download()
-    perr = sampled_parity(app, (pos0, mass0), rb, re)
-    parity_err, parity_f64, oracle_f64 = (max_over_ranks(x) for x in perr[:3])
-    reference_order_exact = perr[3]
+    e32, e64, r64, exact, _ = sampled_parity(app, (pos0, mass0), rb, re, max(PARITY_ROWS // world, 1), local_rank)
     # positions after tick 1 must be bit-exact (movement precedes acceleration)
     import oracle
 
@@ -321,6 +583,13 @@ def run_gpu_arm(args) -> None:
     pref = pos0.copy()
     orc.axpy(pref, vel0, orc.dt, rows=(rb, re))
     pos_exact = bool(np.array_equal(app.pos[rb:re].view(np.uint32), pref[rb:re].view(np.uint32)))
+    pos_exact = bool(max_over_ranks(0.0 if pos_exact else 1.0) == 0.0)
+    if isinstance(exact, bool):
+        exact = bool(max_over_ranks(0.0 if exact else 1.0) == 0.0)
+    parity = parity_record(e32, e64, r64, exact, pos_exact, max_over_ranks, sum_over_ranks)
+    parity["rows_per_rank"] = int(len(e32))
+    if small is not None:
+        parity["sharded_small_check"] = small
 
     # ---- device-resident timed region ------------------------------------------------------------
     for _ in range(warmup):
@@ -350,89 +619,85 @@ def run_gpu_arm(args) -> None:
 
     # ---- end to end: host columns in, host columns out, every step --------------------------------
     # A rank moves the rows it owns (all rows on one GPU): the other ranks' positions and masses reach it through the
-    # all-gather, and it never touches their velocities or accelerations.
+    # exchange, and it never touches their velocities or accelerations.  Inputs of a tick are Position, Mass and
+    # Velocity; Acceleration is overwritten by gravity (crates/n-body/src/lib.rs:134) and only comes back.
     e2e_steps = steps
     own = None if world == 1 else (rb, re)
     for _ in range(2):
-        app.upload(rows=own)
+        app.upload(rows=own, comps=app.INPUT_COMPONENTS)
         app.tick(1)
         app.download(rows=own)
     barrier()
     e0 = time.perf_counter()
     for _ in range(e2e_steps):
-        app.upload(rows=own)
+        app.upload(rows=own, comps=app.INPUT_COMPONENTS)
         app.tick(1)
         app.download(rows=own)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - e0)
     e2e_value = n * n * e2e_steps / e2e_s / 1e9
-    # whole-job bytes per step, counted from what is copied: 40 B up and 36 B down per body
-    h2d = int(pos.nbytes + mass.nbytes + vel.nbytes + acc.nbytes)
+    # whole-job bytes per step, counted from what is copied: 28 B up and 36 B down per body
+    h2d = int(pos.nbytes + mass.nbytes + vel.nbytes)
     d2h = int(pos.nbytes + vel.nbytes + acc.nbytes)
 
     # ---- roofline of the interaction kernel (events around its launches only) --------------------
-    tf_peak, mhz = ctx.measure_fp32_peak(packed=True)
-    ctx.enable_timing(True)
-    ctx.reset_timing()
     k_steps = max(3, min(steps, 10))
-    for _ in range(k_steps):
-        app.tick(1)
-    t = ctx.timing()
-    ctx.enable_timing(False)
-    grav_ms = t["gravity_ms"] / k_steps  # all interaction-kernel launches of one tick on this rank
-    rows_here = re - rb
-    kernel_flops = FLOPS_PER_INTERACTION * rows_here * n
-    achieved_tf = kernel_flops / (grav_ms * 1e-3) / 1e12
-    fma_lane_rate = FMA_LANE_OPS_PER_INTERACTION * rows_here * n / (grav_ms * 1e-3)
-    roofline = {
-        "bound": "fp32",
-        "kernel": "nbody_gravity_kernel",
-        "achieved": achieved_tf,
-        "peak": tf_peak,
-        "unit": "TFLOP/s",
-        "frac": achieved_tf / tf_peak,
-        "peak_source": "measured live on this GPU: register-resident FFMA2 loop (MEASURED_PEAKS.json has no FP32 figure)",
-        "flops_per_interaction": FLOPS_PER_INTERACTION,
-        "fma_pipe_frac": fma_lane_rate / (tf_peak * 1e12 / 2.0),
-        "kernel_ms_per_step": grav_ms,
-        "kernel_share_of_step": grav_ms / (t["last_tick_chain_ms"] / k_steps) if t["last_tick_chain_ms"] else None,
-        "traffic": KERNEL_DRAM_TRAFFIC_BYTES.get(n) if world == 1 else None,
-        "traffic_unit": "bytes of DRAM traffic per launch (ncu, single GPU)",
-        "sm_mhz_during_peak_probe": mhz,
-    }
+    roofline, t = kernel_roofline(ctx, app, n, re - rb, k_steps, traffic.get(f"nbody_gravity_kernel_{n}") if world == 1 else None)
 
     comm = None
     if world > 1:
         comm = {
-            "collective": "ncclAllGather of the pair-interleaved position/mass mirror, in place, once per tick",
-            "bytes_per_rank_per_step": int((re - rb) * 16),
-            "bytes_total_per_step": int(n * 16),
-            "gather_ms_per_step_incl_peer_wait": t["gather_ms"] / k_steps,
-            "overlap": "enqueued after the local-tile launch; never on the critical path before it",
+            "exchange": exchange,
+            "bytes_per_rank_per_step": int((re - rb) * 16 * (world if exchange == "peer-push" else 1)),
+            "bytes_total_per_step": int(n * 16 * (world if exchange == "peer-push" else 1)),
+            "interaction_launches_per_tick": t["gravity_launches"] / k_steps,
         }
+        if exchange == "peer-push":
+            comm["how"] = ("the integration tail stores every refreshed {position, G*m} entry into all ranks' next mirror buffer "
+                           "(P2P stores over NVLink) and raises a generation flag; the next tick is ONE persistent launch that starts on "
+                           "its own tiles and acquires a peer's flag before the first tile of that peer's slice")
+            comm["residual"] = ("time a rank's producer warp spends waiting for the slowest peer's flag (inside the interaction kernel), "
+                                "plus the P2P stores of the tail: ms_per_step - kernel time of the fastest rank")
+            comm["residual_ms_per_step"] = total_ms / steps - min(per_rank_ms) if per_rank_ms else None
+        else:
+            comm["how"] = "ncclAllGather of the mirror, in place, between the own-tile launch and the launch over the other ranks' tiles"
+            comm["gather_ms_per_step_incl_peer_wait"] = t["gather_ms"] / k_steps
 
-    # ---- secondary configs (streaming systems), reported as extras ---------------------------------
+    # ---- secondary configs: configs[0], configs[1] (N = 1) and the streaming systems ---------------------
     extras = {}
+    configs = None
+    cpu = None
     if world > 1:
         extras = {"skipped": "the streaming configs are reported by the N=1 run (a sharded context streams only its own slice)"}
-    elif not args.no_extras and rank == 0:
+    cpu_orc, cpu_note = (None, None)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the contract: rank 0 at N=1 only
+        cpu_orc, cpu_note = load_cpu_baseline_oracle()
+    if world == 1 and rank == 0 and not args.no_extras:
         try:
-            extras = streaming_extras(ctx)
+            extras = streaming_extras(ctx, traffic)
         except Exception as exc:  # extras never invalidate the headline line
             extras = {"error": repr(exc)}
+    ctx.close()
+    if world == 1 and rank == 0 and not args.no_configs and n == DEFAULT_BODIES:
+        configs = {}
+        for key, (cn, tps, csteps) in {"configs[0]": (1000, 100, 20), "configs[1]": (65536, 1, 50)}.items():
+            try:
+                configs[key] = config_subrecord(cn, tps, csteps, local_rank, traffic.get(f"nbody_gravity_kernel_{cn}"), scenes,
+                                                cpu_orc, cpu_note)
+            except Exception as exc:
+                configs[key] = {"error": repr(exc)}
 
     # ---- CPU baseline (rank 0, bounded sample) ---------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # the contract: rank 0 at N=1 only
+    if cpu_orc is not None:
         threads = host_threads()
-        rate, rows, sec, _ = cpu_sample_rate(n, 12.0, threads)
+        rate, rows, sec, _ = cpu_sample_rate(cpu_orc, scenes, n, 12.0, threads)
         cpu = {
             "value": rate / 1e9,
             "unit": "G interactions/s",
             "cores": threads,
             "kind": "port",
             "sample": f"{rows} of {n} outer rows x all {n} bodies, one tick, {sec:.1f} s",
-            "note": "oracle/nbody_oracle.c: C restatement of recs' CPU systems + worker-pool segment policy",
+            "note": "oracle/nbody_oracle.c: C restatement of recs' CPU systems + worker-pool segment policy; " + cpu_note,
         }
 
     if rank == 0:
@@ -453,7 +718,7 @@ def run_gpu_arm(args) -> None:
                 "workload": f"nbody_{n}",
                 "bodies": n,
                 "systems": "gravity->movement->acceleration",
-                "parallelism": f"index-sharded x{world}, NCCL all-gather of positions per tick" if world > 1 else "single GPU",
+                "parallelism": f"index-sharded x{world}, {exchange} exchange of positions per tick" if world > 1 else "single GPU",
                 "l2": "flushed between timed ticks (256 MiB write + 256 MiB read sweep outside the event bracket)",
                 "seed": SEED,
             },
@@ -463,23 +728,28 @@ def run_gpu_arm(args) -> None:
             "gpu_launches": int(round(launches_per_step * steps)),
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "parity": {"acc_max_rel_err_vs_oracle": parity_err, "tolerance": 1e-4, "pos_bit_exact_after_tick1": pos_exact,
-                       "acc_max_rel_err_vs_f64": parity_f64, "oracle_f32_order_vs_f64": oracle_f64, "rows_per_rank": 32,
-                       "reference_order_generic_kernel_bit_exact": reference_order_exact},
+            "parity": parity,
             "step_ms": [round(x, 3) for x in step_ms],
             "ms_per_step_by_rank": [round(x, 3) for x in per_rank_ms],
             "wall_ms_per_step_incl_flush": wall / steps * 1e3,
             "comm": comm,
+            "configs": configs,
             "extras": extras,
         }
         print(json.dumps(line), flush=True)
-    ctx.close()
     if dist is not None:
+        dist.barrier()
         dist.destroy_process_group()
 
 
-def streaming_extras(ctx) -> dict:
-    """HBM-bound systems of configs[3] / configs[4]: achieved GB/s on algorithmic bytes."""
+def hbm_roofline(kernel, gbs, peak, ms, traffic):
+    return {"bound": "hbm", "kernel": kernel, "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+            "ms_per_launch": ms, "traffic": traffic,
+            "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_traffic.json)"}
+
+
+def streaming_extras(ctx, traffic) -> dict:
+    """HBM-bound systems of configs[3] / configs[4]: achieved GB/s on algorithmic bytes, each with its own roofline block."""
     from recs_b200 import _lib, scenes
 
     out = {}
@@ -505,6 +775,8 @@ def streaming_extras(ctx) -> dict:
     #     126 MB L2, so every pass is cold and also pays for the write-backs the previous one left in L2.
     passes = 20
     ctx.synchronize()
+    sampler = ClockSampler(ctx.config.device, period_ms=20)
+    sampler.start()
     ctx.timer_start()
     for _ in range(passes):
         ctx.run_system(sid, sync=False)
@@ -525,6 +797,7 @@ def streaming_extras(ctx) -> dict:
         "how": "20 passes back to back in one CUDA-event bracket; inputs (240 MB) larger than L2",
         "single_pass_after_flush_ms": float(np.median(ms)),
         "single_pass_after_flush_GBps": 36.0 * n / (np.median(ms) * 1e-3) / 1e9,
+        "roofline": hbm_roofline("axpy_rn_vec_kernel", gbs, peak, float(steady_ms), traffic.get("axpy_rn_vec_kernel_10M")),
     }
     # the same system as a GENERIC GPU system: its body handed over as source, compiled with NVRTC at registration,
     # run through the TMA-pipelined generated kernel (recs_gpu_system_create_kernel)
@@ -546,6 +819,7 @@ def streaming_extras(ctx) -> dict:
         "ms": float(generic_ms),
         "bytes_per_entity": 36,
         "how": "same 20-pass bracket; NVRTC-compiled body in the generated TMA-pipelined kernel",
+        "roofline": hbm_roofline("recs_generic_system (generated)", ggbs, peak, float(generic_ms), traffic.get("recs_generic_system_simple_iter_10M")),
     }
     # rain: 4 Mi drops, fused wind -> gravity -> movement, 48 B / entity / tick
     n = 4 * 1024 * 1024
@@ -584,6 +858,8 @@ def streaming_extras(ctx) -> dict:
         "back_to_back_ms": float(resident_ms),
         "back_to_back_note": "the two 50 MB columns fit the 126 MB L2, so consecutive ticks run L2-resident and even a flushed tick "
                              "keeps its writes in L2: see rain_16Mi_fused for the HBM-bound rate",
+        "roofline": dict(hbm_roofline("rain_tma_kernel<2>", gbs, peak, float(np.median(ms)), traffic.get("rain_tma_kernel_4Mi")),
+                         note="NOT an HBM figure: at this size the written half of the columns stays in L2 (traffic < algorithmic bytes)"),
     }
     # the same tick HBM-bound: 16 Mi drops (2 x 200 MB columns, larger than L2), 20 ticks back to back
     n = 16 * 1024 * 1024
@@ -606,7 +882,9 @@ def streaming_extras(ctx) -> dict:
         "ms": float(big_ms),
         "bytes_per_entity": 48,
         "how": "20 ticks back to back in one CUDA-event bracket; columns (400 MB) larger than L2: the HBM-bound rate",
+        "roofline": hbm_roofline("rain_tma_kernel<2>", bgbs, peak, float(big_ms), traffic.get("rain_tma_kernel_16Mi")),
     }
+    out["clocks"] = sampler.stop()
     out["hbm_peak_GBps"] = peak
     return out
 

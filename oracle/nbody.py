@@ -123,6 +123,24 @@ class NBodyOracle:
         return d
 
 
+def load_native() -> NBodyOracle:
+    """The oracle compiled on THIS machine with -march=native (the reference's .cargo/config.toml:2 asks for
+    target-cpu=native), for the timed CPU baseline.  Same source, same -ffp-contract=off: the sequential f32 fold cannot be
+    vectorised, so results are bit-identical to the portable build (checked here on a small sample before use)."""
+    native = os.path.join(_HERE, "liboracle_native.so")
+    src = os.path.join(_HERE, "nbody_oracle.c")
+    subprocess.run(["make", "-B", "-C", _HERE, "native"], check=True, capture_output=True)  # always for THIS cpu
+    if not os.path.exists(native) or os.path.getmtime(native) < os.path.getmtime(src):
+        raise RuntimeError("native oracle build produced no library")
+    orc = NBodyOracle(C.CDLL(native))
+    rng = np.random.default_rng(0)
+    pos = rng.uniform(-100, 100, size=(257, 3)).astype(np.float32)
+    mass = rng.uniform(1e14, 2e14, size=257).astype(np.float32)
+    if not np.array_equal(orc.gravity(pos, mass).view(np.uint32), load().gravity(pos, mass).view(np.uint32)):
+        raise RuntimeError("native oracle build differs from the portable build")
+    return orc
+
+
 _cached = None
 
 

@@ -607,7 +607,7 @@ typedef void (*GravityKernel)(const GravityArgs);
 // numbering used while sweeping to this table).
 //                    rows/thread, CTAs/SM, consumer warps, range-shifted posm
 const GravityVariant kVariants[kGravVariantCount] = {
-    {4, 1, 12, true},   // 0  default: i-packed, overflow detector on range-shifted data, unroll 8
+    {4, 1, 12, true},   // 0  default: i-packed, overflow detector on range-shifted data, tile loop unrolled 16 times
     {2, 1, 12, false},  // 1  j-packed, FMNMX detector (the default before the i-packed rewrite; A/B)
     {2, 3, 4, false},   // 2  small problems: j-packed, 256-row i-blocks, exact mask on every pair
     {2, 4, 4, true},    // 3  medium problems: i-packed overflow detector, 256-row i-blocks, 4 CTAs/SM
@@ -615,17 +615,17 @@ const GravityVariant kVariants[kGravVariantCount] = {
     {4, 1, 12, false},  // 5  i-packed, exact mask on every pair
     {4, 1, 8, true},    // 6  as 0 with 8 consumer warps
     {8, 1, 8, true},    // 7  as 0 with 4 row pairs per thread (half the LDS, worse ptxas schedule)
-    {4, 1, 12, true},   // 8  as 0 with the tile loop unrolled 16 times (half the loop overhead, twice the code)
-    {4, 1, 12, true},   // 9  as 0 with the tile loop unrolled 32 times (30 KB of loop body)
+    {4, 1, 12, true},   // 8  as 0 with the tile loop unrolled 8 times: ptxas then rotates two accumulators through MOVs
+                        //    (9 non-FMA instructions per 473 against 7 per 935): 1 % slower, profiles/r02_gravity_unroll_sweep.txt
 #ifdef RECS_GPU_ABLATIONS  // never in the shipped library: tools/ builds only (make ablations)
-    {4, 1, 12, true},   // 10 TIMING ONLY: 0 without MUFU.RSQ (wrong results)
-    {4, 1, 12, false},  // 11 TIMING ONLY: 4 without the detector (wrong results for coincident bodies)
+    {4, 1, 12, true},   // 9  TIMING ONLY: 0 without MUFU.RSQ (wrong results)
+    {4, 1, 12, false},  // 10 TIMING ONLY: 4 without the detector (wrong results for coincident bodies)
 #endif
 };
 GravityKernel variant_kernel(int v) {
     switch (v) {
         case 0:
-            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow>;
+            return nbody_gravity_kernel<4, 1, 16, true, 12, true, kAblOverflow>;
         case 1:
             return nbody_gravity_kernel<2, 1, 8, true, 12>;
         case 2:
@@ -641,13 +641,11 @@ GravityKernel variant_kernel(int v) {
         case 7:
             return nbody_gravity_kernel<8, 1, 2, true, 8, true, kAblOverflow>;
         case 8:
-            return nbody_gravity_kernel<4, 1, 16, true, 12, true, kAblOverflow>;
-        case 9:
-            return nbody_gravity_kernel<4, 1, 32, true, 12, true, kAblOverflow>;
+            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow>;
 #ifdef RECS_GPU_ABLATIONS
+        case 9:
+            return nbody_gravity_kernel<4, 1, 16, true, 12, true, kAblOverflow | kAblNoMufu>;
         case 10:
-            return nbody_gravity_kernel<4, 1, 8, true, 12, true, kAblOverflow | kAblNoMufu>;
-        case 11:
             return nbody_gravity_kernel<4, 1, 4, true, 12, true, kAblCubeFirst | kAblNoDetector>;
 #endif
     }

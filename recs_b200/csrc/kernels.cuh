@@ -26,9 +26,9 @@ struct GravityVariant {
     int rows() const { return consumer_threads() * rows_per_thread; }  // rows per i-block
 };
 #ifdef RECS_GPU_ABLATIONS
-constexpr int kGravVariantCount = 12;  // 10 and 11 are timing-only ablations with WRONG results (tools/ builds only)
+constexpr int kGravVariantCount = 11;  // 9 and 10 are timing-only ablations with WRONG results (tools/ builds only)
 #else
-constexpr int kGravVariantCount = 10;
+constexpr int kGravVariantCount = 9;
 #endif
 constexpr int kGravVariantDefault = 0;
 constexpr int kGravVariantSmall = 2;    // up to kGravSmallRows outer rows

@@ -42,9 +42,13 @@ class NBodyGpuApp:
         self.tick_order = tuple(names)
         self.ctx.set_tick_order([self.systems[name] for name in names])
 
-    def upload(self, rows=None) -> None:
-        """All four columns host -> device; `rows=(begin, end)` moves only that row range (a rank's own shard)."""
-        for comp in (POSITION, MASS, VELOCITY, ACCELERATION):
+    # what a tick reads before writing it: gravity overwrites Acceleration (`*acceleration = total_acceleration`,
+    # crates/n-body/src/lib.rs:134), so it never has to go up
+    INPUT_COMPONENTS = (POSITION, MASS, VELOCITY)
+
+    def upload(self, rows=None, comps=(POSITION, MASS, VELOCITY, ACCELERATION)) -> None:
+        """Columns host -> device (default all four); `rows=(begin, end)` moves only that row range (a rank's own shard)."""
+        for comp in comps:
             if rows is None:
                 self.ctx.upload(BODY_ARCHETYPE, comp)
             else:

@@ -88,3 +88,23 @@ def test_only_tests_bench_and_smoke_touch_the_oracle():
         path = os.path.join(ROOT, f)
         if f.endswith(".py") and path not in allowed:
             assert "import oracle" not in open(path).read(), f
+
+
+def test_reference_arm_never_maps_the_product_library():
+    """`bench.py --impl reference` times the CPU port alone: the process must not even load librecs_gpu.so (round-1 did,
+    through `from recs_b200 import scenes`)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, runpy\n"
+        "sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--bodies', '3000']\n"
+        "runpy.run_path('bench.py', run_name='__main__')\n"
+        "libs = sorted({l.split()[-1] for l in open('/proc/self/maps') if '.so' in l and sys.argv[0] and '/recs_b200/' in l})\n"
+        "print('MAPPED', libs)\n"
+    )
+    proc = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    assert '"impl": "reference"' in proc.stdout
+    assert "MAPPED []" in proc.stdout, proc.stdout[-500:]
