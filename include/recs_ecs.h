@@ -224,6 +224,18 @@ int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const 
 int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
                                        const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
                                        const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index);
+/* The same with `Commands::create` (crates/ecs/src/systems/command_buffers.rs:53-66): `create_components` lists the
+ * components of the tuple the body hands to `commands.create(record)`; `create_record_type` names the POD struct in
+ * `source` that holds them packed in that order (checked against the registry's element sizes at compile time).  The
+ * records of a tick are played back with the tick's other commands, system by system in registration order, in the
+ * order a sequential run would have recorded them -- rain's drop spawning (crates/rain-simulation/src/lib.rs:128-148)
+ * runs on the device this way and the new rows reach the resident columns as appends. */
+int32_t recs_app_add_gpu_kernel_system_creating(recs_app* app, const char* name, const char* source, const char* body,
+                                                const recs_param_token* tokens, uint32_t n_tokens,
+                                                const char* const* type_names, const char* uniform_type,
+                                                uint32_t uniform_bytes, const uint64_t* create_components,
+                                                uint32_t n_create_components, const char* create_record_type,
+                                                uint32_t* out_index);
 /* The nested-query form (recs_gpu_system_create_pair_kernel): `tokens` holds one Query<...> group; type_names lists the
  * C++ types of the outer Read / Write / Entity parameters and of the query's parameters in token order. */
 int32_t recs_app_add_gpu_pair_kernel_system(recs_app* app, const char* name, const char* source, const char* acc_type,

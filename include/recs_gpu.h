@@ -215,6 +215,16 @@ int32_t recs_gpu_system_set_query_archetypes(recs_gpu_ctx* ctx, uint32_t system_
 int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t archetype_index,
                                  uint32_t* out_rows, uint32_t cap, uint32_t* out_count);
 
+/* `Commands::create(components)` calls of a generic system's last run (rain spawns its drops this way,
+ * crates/rain-simulation/src/lib.rs:128-148): *out_count records of *out_record_bytes bytes each, in the order a
+ * sequential run of the system would have recorded them (entity order, then call order within an entity), so
+ * the entity ids the host World hands out at playback do not depend on thread timing.  out_records may be NULL
+ * to ask for the count.  Synchronises the stream.  More records than the buffer holds is an error
+ * (RECS_ERR_SIZE_MISMATCH): raise it with recs_gpu_system_set_create_capacity (default 65 536 per run). */
+int32_t recs_gpu_system_creates(recs_gpu_ctx* ctx, uint32_t system_id, void* out_records, uint32_t cap_records,
+                                uint32_t* out_count, uint32_t* out_record_bytes);
+int32_t recs_gpu_system_set_create_capacity(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t max_records);
+
 /* ------------------------------------------------------------------------------------------
  * Generic GPU systems: any per-entity function over `Read<T>` / `Write<T>` / `Entity` parameters
  * (crates/ecs/src/systems/mod.rs:457-566 Read, 627-739 Write, 868-912 Entity), iterated over the
@@ -234,9 +244,12 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
 #define RECS_KPARAM_READ 0u
 #define RECS_KPARAM_WRITE 1u
 #define RECS_KPARAM_ENTITY 2u
-#define RECS_KPARAM_COMMANDS 3u /* `Commands` restricted to remove(): the body receives `const recs_commands&` and may call
-                                 * .remove() for its own entity (crates/ecs/src/systems/command_buffers.rs:53-112); the rows
-                                 * are fetched with recs_gpu_system_removals like for the built-in removal-deciding kinds */
+#define RECS_KPARAM_COMMANDS 3u /* `Commands` (crates/ecs/src/systems/command_buffers.rs:53-112): the body receives
+                                 * `const recs_commands&` and may call .remove() for its own entity (rows fetched with
+                                 * recs_gpu_system_removals like for the built-in removal-deciding kinds) and, when the
+                                 * parameter names a record type (type_name, elem_size = sizeof), .create(record): the
+                                 * tuple of components of a new entity as one POD struct, fetched with
+                                 * recs_gpu_system_creates and played back by the host World */
 /* Component id under which the host binds an archetype's entity column for `Entity` parameters:
  * one uint64 per row, generation << 32 | id, the value `Entity::hash` feeds
  * (crates/ecs/src/lib.rs:918-927). */
@@ -244,8 +257,8 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* ctx, uint32_t system_id, uint32_t
 typedef struct recs_gpu_kernel_param {
     uint64_t component_id; /* ignored for RECS_KPARAM_ENTITY (RECS_GPU_ENTITY_COMPONENT is used)  */
     uint32_t elem_size;    /* sizeof(T) on the host == sizeof(type_name) in `source`              */
-    uint32_t kind;         /* RECS_KPARAM_READ / _WRITE / _ENTITY / _COMMANDS (type_name, elem_size unused) /
-                            * _QUERY_READ / _QUERY_ENTITY (pair kernels only)                                 */
+    uint32_t kind;         /* RECS_KPARAM_READ / _WRITE / _ENTITY / _COMMANDS (type_name + elem_size: the create()
+                            * record, or NULL / 0) / _QUERY_READ / _QUERY_ENTITY (pair kernels only)          */
     const char* type_name; /* C++ type of this parameter in `source`                              */
 } recs_gpu_kernel_param;
 /* Registers a generic system.  `uniform_type` (may be NULL) names a POD struct of at most 256 bytes
@@ -269,7 +282,8 @@ int32_t recs_gpu_system_set_uniform(recs_gpu_ctx* ctx, uint32_t system_id, const
  * For every outer entity: ACC acc{}; pair(...) for every query entity IN QUERY ORDER (archetype order, then
  * row order); finish(...).  One thread per outer entity, query entities staged through shared memory in tiles, so a
  * body that accumulates in call order reproduces the reference's sequential fold bit for bit (--fmad=false, IEEE
- * division and square root).  Single-GPU contexts only. */
+ * division and square root).  In a sharded context every rank folds the whole query for the outer rows it owns; the
+ * query's columns must be complete on every rank (recs_gpu_column_allgather after a sharded write). */
 #define RECS_KPARAM_QUERY_READ 4u
 #define RECS_KPARAM_QUERY_ENTITY 5u
 int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* ctx, const char* name, const char* source,
@@ -344,6 +358,11 @@ int32_t recs_gpu_exchange_export(recs_gpu_ctx* ctx, uint64_t max_bodies,
 int32_t recs_gpu_exchange_import(recs_gpu_ctx* ctx, const uint8_t* handles, uint32_t n_handles);
 /* 0 = single GPU, 1 = NCCL all-gather, 2 = peer push. */
 int32_t recs_gpu_exchange_mode(recs_gpu_ctx* ctx);
+/* Delivers every rank's own rows of a column (its recs_gpu_shard_rows slice) to all ranks: grouped in-place
+ * ncclBroadcasts on the context stream (needs recs_gpu_comm_init).  Row-sharded systems write only the rows a
+ * rank owns; a generic system's nested Query<...> reads whole columns, so a column such a system wrote is
+ * gathered before the next nested query over it.  No-op on single-GPU contexts. */
+int32_t recs_gpu_column_allgather(recs_gpu_ctx* ctx, uint32_t archetype_index, uint64_t component_id);
 /* Rows [row_begin, row_end) of gravity / movement / acceleration that this rank computes. */
 int32_t recs_gpu_shard_rows(recs_gpu_ctx* ctx, uint64_t n_rows, uint64_t* row_begin,
                             uint64_t* row_end);

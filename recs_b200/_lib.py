@@ -153,6 +153,8 @@ GPU_SYMBOLS = {
     "recs_gpu_system_set_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_system_set_query_archetypes": (C.c_int32, [_ctx, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_system_removals": (C.c_int32, [_ctx, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]),
+    "recs_gpu_system_creates": (C.c_int32, [_ctx, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
+    "recs_gpu_system_set_create_capacity": (C.c_int32, [_ctx, C.c_uint32, C.c_uint32]),
     "recs_gpu_run_system": (C.c_int32, [_ctx, C.c_uint32, C.c_uint32]),
     "recs_gpu_set_tick_order": (C.c_int32, [_ctx, C.POINTER(C.c_uint32), C.c_uint32]),
     "recs_gpu_tick": (C.c_int32, [_ctx, C.c_uint32]),
@@ -163,6 +165,7 @@ GPU_SYMBOLS = {
     "recs_gpu_exchange_export": (C.c_int32, [_ctx, C.c_uint64, C.POINTER(C.c_uint8)]),
     "recs_gpu_exchange_import": (C.c_int32, [_ctx, C.POINTER(C.c_uint8), C.c_uint32]),
     "recs_gpu_exchange_mode": (C.c_int32, [_ctx]),
+    "recs_gpu_column_allgather": (C.c_int32, [_ctx, C.c_uint32, C.c_uint64]),
     "recs_gpu_shard_rows": (C.c_int32, [_ctx, C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_shard_plan": (C.c_int32, [C.c_uint64, C.c_int32, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "recs_gpu_enable_timing": (C.c_int32, [_ctx, C.c_int32]),

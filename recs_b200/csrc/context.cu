@@ -46,6 +46,13 @@ struct KernelSys {
     std::vector<unsigned char> uniform;    // bytes passed by value to every launch
     bool has_uniform = false;
     bool has_commands = false;             // one RECS_KPARAM_COMMANDS parameter: the system decides removals
+    // Commands::create: device append buffer {count, cap, record_bytes, bad | records}, see kernel_gen.cpp
+    uint32_t create_bytes = 0;             // sizeof of the record create() takes (0: the system only removes)
+    uint32_t create_cap = 65536;           // records per launch (recs_gpu_system_set_create_capacity)
+    unsigned char* create_buf = nullptr;
+    size_t create_buf_cap = 0;
+    bool create_valid = false;             // the buffer holds the records of the last run
+    uint32_t create_stride() const { return 16u + ((create_bytes + 7u) & ~7u); }
     // nested Query<(...)> form (recs_gpu_system_create_pair_kernel)
     bool is_pair = false;
     std::vector<KernelParamSpec> qparams;
@@ -66,6 +73,7 @@ struct KernelSys {
     ~KernelSys() {
         if (table) cudaFree(table);
         if (qtable) cudaFree(qtable);
+        if (create_buf) cudaFree(create_buf);
         if (lib) cudaLibraryUnload(lib);
     }
 };
@@ -183,6 +191,13 @@ struct recs_gpu_ctx {
     unsigned char* move_tmp = nullptr;
     size_t move_tmp_cap = 0;
     uint64_t h2d_bytes = 0, d2h_bytes = 0;  // component-column traffic over PCIe since create / reset
+    // small host -> device copies (archetype tables, row-move lists, appended rows) go through a pinned two-half
+    // staging buffer, so the source may be pageable / short-lived and the stream is never synchronised for them
+    unsigned char* stage = nullptr;
+    size_t stage_half = 0, stage_used = 0;
+    int stage_cur = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool stage_busy[2] = {false, false};
 };
 
 namespace {
@@ -288,6 +303,40 @@ int32_t ensure(recs_gpu_ctx* c, T** p, size_t* cap, size_t bytes) {
     return RECS_OK;
 }
 
+// Asynchronous copy of a small host block whose lifetime ends with the call.
+int32_t staged_h2d(recs_gpu_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return RECS_OK;
+    const size_t kHalf = 1u << 20;
+    if (!c->stage) {
+        RECS_CUDA(c, cudaHostAlloc((void**)&c->stage, 2 * kHalf, cudaHostAllocDefault));
+        RECS_CUDA(c, cudaEventCreateWithFlags(&c->stage_ev[0], cudaEventDisableTiming));
+        RECS_CUDA(c, cudaEventCreateWithFlags(&c->stage_ev[1], cudaEventDisableTiming));
+        c->stage_half = kHalf;
+    }
+    const size_t need = (bytes + 255) & ~(size_t)255;
+    if (need > c->stage_half || c->capturing) {  // too large to stage: copy straight from the caller's memory and wait
+        RECS_CUDA(c, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+        return RECS_OK;
+    }
+    if (c->stage_used + need > c->stage_half) {
+        // this half is full: mark where its copies end, move to the other half once ITS copies are done
+        RECS_CUDA(c, cudaEventRecord(c->stage_ev[c->stage_cur], c->stream));
+        c->stage_busy[c->stage_cur] = true;
+        c->stage_cur ^= 1;
+        c->stage_used = 0;
+        if (c->stage_busy[c->stage_cur]) {
+            RECS_CUDA(c, cudaEventSynchronize(c->stage_ev[c->stage_cur]));
+            c->stage_busy[c->stage_cur] = false;
+        }
+    }
+    unsigned char* at = c->stage + (size_t)c->stage_cur * c->stage_half + c->stage_used;
+    memcpy(at, src, bytes);
+    c->stage_used += need;
+    RECS_CUDA(c, cudaMemcpyAsync(dst, at, bytes, cudaMemcpyHostToDevice, c->stream));
+    return RECS_OK;
+}
+
 // Equal slices of the padded body range, one per rank: whole chunks of the summation tree (kernels.cuh), so a rank's
 // own tiles and the other ranks' tiles are two runs of whole chunks and the result does not depend on the rank count.
 void shard_rows_for(int rank, int world_size, uint64_t n, uint64_t* slice, uint64_t* rb, uint64_t* re) {
@@ -346,6 +395,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     const uint64_t n_jpad = slice * (uint64_t)lay_R;
     const uint32_t n_tiles = (uint32_t)(n_jpad / kGravTile);
     const uint32_t slice_tiles = (uint32_t)(slice / kGravTile);
+    if (n_tiles / K > 64) return fail(c, RECS_ERR_UNSUPPORTED, "summation tree has more than 64 chunks");  // (kGravMaxChunks of the reduce kernel)
 
     int32_t st = RECS_OK;
     if (p2p) {
@@ -745,7 +795,7 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         }
         const size_t n_arch = archs.size();
         std::vector<unsigned long long>& t = k.table_host;
-        t.assign(2 * n_arch + 1 + n_params * n_arch, 0ull);
+        t.assign(2 * n_arch + 1 + n_params * n_arch + 1, 0ull);  // + the create buffer
         unsigned long long items = 0;
         for (size_t i = 0; i < n_arch; ++i) {
             const unsigned long long count = ranges[i].second - ranges[i].first;
@@ -776,6 +826,14 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
             }
         }
         t[n_arch] = items;
+        if (k.create_bytes) {
+            const size_t bytes = 16 + (size_t)k.create_cap * k.create_stride();
+            int32_t cst = ensure(c, &k.create_buf, &k.create_buf_cap, bytes);
+            if (cst != RECS_OK) return cst;
+            const uint32_t header[4] = {0u, k.create_cap, k.create_bytes, 0u};
+            if ((cst = staged_h2d(c, k.create_buf, header, sizeof header)) != RECS_OK) return cst;
+            t[2 * n_arch + 1 + n_params * n_arch] = (unsigned long long)(uintptr_t)k.create_buf;
+        }
         k.footprint_bytes = 0;
         for (size_t i = 0; i < n_arch; ++i)
             for (size_t p = 0; p < n_params; ++p)
@@ -783,9 +841,7 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
                     k.footprint_bytes += (ranges[i].second - ranges[i].first) * k.params[p].elem_size;
         int32_t st = ensure(c, &k.table, &k.table_cap, std::max<size_t>(t.size() * sizeof(unsigned long long), 64));
         if (st != RECS_OK) return st;
-        RECS_CUDA(c, cudaMemcpyAsync(k.table, t.data(), t.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice,
-                                     c->stream));
-        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // t is pageable host memory
+        if ((st = staged_h2d(c, k.table, t.data(), t.size() * sizeof(unsigned long long))) != RECS_OK) return st;
         k.n_items = items;
         k.n_arch = (uint32_t)n_arch;
         k.table_archs = archs;
@@ -813,8 +869,7 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
             }
             q[nqa] = rows;
             if ((st = ensure(c, &k.qtable, &k.qtable_cap, std::max<size_t>(q.size() * sizeof(unsigned long long), 64))) != RECS_OK) return st;
-            RECS_CUDA(c, cudaMemcpyAsync(k.qtable, q.data(), q.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-            RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+            if ((st = staged_h2d(c, k.qtable, q.data(), q.size() * sizeof(unsigned long long))) != RECS_OK) return st;
             k.n_qarch = (uint32_t)nqa;
         }
         k.table_epoch = c->epoch;
@@ -834,6 +889,10 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
             System::Removals& r = sys.removals[a];
             RECS_CUDA(c, cudaMemsetAsync(r.flags, 0, (size_t)r.n_rows * sizeof(uint32_t), c->stream));
         }
+    }
+    if (k.create_bytes) {
+        RECS_CUDA(c, cudaMemsetAsync(k.create_buf, 0, sizeof(uint32_t), c->stream));  // count of this run
+        k.create_valid = true;
     }
     if (k.n_items == 0) return RECS_OK;
     // grid: persistent CTAs for the pipelined form (three per SM while shared memory allows), one resident wave of
@@ -1223,6 +1282,9 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
         if (c->l2_flush) cudaFree(c->l2_flush);
         if (c->move_idx) cudaFree(c->move_idx);
         if (c->move_tmp) cudaFree(c->move_tmp);
+        if (c->stage) cudaFreeHost(c->stage);
+        for (int h = 0; h < 2; ++h)
+            if (c->stage_ev[h]) cudaEventDestroy(c->stage_ev[h]);
         for (auto& s : c->spans) {
             cudaEventDestroy(s.a);
             cudaEventDestroy(s.b);
@@ -1369,9 +1431,8 @@ int32_t recs_gpu_archetype_move_rows(recs_gpu_ctx* c, uint32_t arch, const uint6
         int32_t st = ensure(c, &c->move_idx, &c->move_idx_cap, (size_t)n_moves * 2 * sizeof(uint32_t));
         if (st != RECS_OK) return st;
         if ((st = ensure(c, &c->move_tmp, &c->move_tmp_cap, (size_t)n_moves * max_elem)) != RECS_OK) return st;
-        RECS_CUDA(c, cudaMemcpyAsync(c->move_idx, dst, (size_t)n_moves * 4, cudaMemcpyHostToDevice, c->stream));
-        RECS_CUDA(c, cudaMemcpyAsync(c->move_idx + n_moves, src, (size_t)n_moves * 4, cudaMemcpyHostToDevice, c->stream));
-        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // the lists are pageable host memory
+        if ((st = staged_h2d(c, c->move_idx, dst, (size_t)n_moves * 4)) != RECS_OK) return st;
+        if ((st = staged_h2d(c, c->move_idx + n_moves, src, (size_t)n_moves * 4)) != RECS_OK) return st;
         c->h2d_bytes += (uint64_t)n_moves * 8;
     }
     for (Column* col : cols) {
@@ -1407,9 +1468,10 @@ int32_t recs_gpu_column_append(recs_gpu_ctx* c, uint32_t arch, uint64_t comp, vo
         col->cap = cap;
     }
     if (new_bytes > old_bytes) {
-        RECS_CUDA(c, cudaMemcpyAsync((unsigned char*)col->dev + old_bytes, (const unsigned char*)host_ptr + old_bytes,
-                                     new_bytes - old_bytes, cudaMemcpyHostToDevice, c->stream));
-        RECS_CUDA(c, cudaStreamSynchronize(c->stream));  // the host rows may be pageable and short-lived
+        // (the host rows may be pageable and short-lived: staged, or waited for when large)
+        int32_t st = staged_h2d(c, (unsigned char*)col->dev + old_bytes, (const unsigned char*)host_ptr + old_bytes,
+                                new_bytes - old_bytes);
+        if (st != RECS_OK) return st;
         c->h2d_bytes += new_bytes - old_bytes;
     }
     col->host = host_ptr;
@@ -1488,7 +1550,8 @@ int32_t recs_gpu_system_create_kernel(recs_gpu_ctx* c, const char* name, const c
             if (ks->has_commands) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_kernel: more than one Commands parameter");
             if (c->cfg.world_size > 1) return fail(c, RECS_ERR_UNSUPPORTED, "removal-deciding systems are single-GPU");
             ks->has_commands = true;
-            ks->params.push_back({"recs_commands", 4u, p.kind});
+            ks->params.push_back(commands_param_spec(p));
+            ks->create_bytes = ks->params.back().elem_size;
             ks->comp.push_back(0);
             continue;
         }
@@ -1536,8 +1599,9 @@ int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* c, const char* name, co
         return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: bad argument");
     if ((uniform_type != nullptr && uniform_type[0]) != (uniform_bytes != 0) || uniform_bytes > 256)
         return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: uniform type / size (<= 256 bytes) mismatch");
-    if (c->cfg.world_size > 1)
-        return fail(c, RECS_ERR_UNSUPPORTED, "generic nested-query systems are single-GPU (the built-in gravity kind is the sharded one)");
+    // Sharded contexts: every rank folds the WHOLE nested query for the outer rows it owns (run_kernel_system shards the
+    // outer archetypes), so the query's columns must be complete on every rank -- recs_gpu_column_allgather after a
+    // sharded system wrote one of them.
     auto ks = std::make_shared<KernelSys>();
     ks->is_pair = true;
     System s;
@@ -1551,7 +1615,8 @@ int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* c, const char* name, co
         if (p.kind == RECS_KPARAM_COMMANDS) {
             if (ks->has_commands) return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_create_pair_kernel: more than one Commands parameter");
             ks->has_commands = true;
-            ks->params.push_back({"recs_commands", 4u, p.kind});
+            ks->params.push_back(commands_param_spec(p));
+            ks->create_bytes = ks->params.back().elem_size;
             ks->comp.push_back(0);
             continue;
         }
@@ -1663,6 +1728,61 @@ int32_t recs_gpu_system_removals(recs_gpu_ctx* c, uint32_t id, uint32_t arch, ui
         std::sort(rows.begin(), rows.end());  // playback order: ascending component index
         for (uint32_t i = 0; i < n && i < cap; ++i) out_rows[i] = rows[i];
     }
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_set_create_capacity(recs_gpu_ctx* c, uint32_t id, uint32_t max_records) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || !c->systems[id].ks || !c->systems[id].ks->create_bytes || max_records == 0)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_set_create_capacity: not a generic system with a create record");
+    KernelSys& k = *c->systems[id].ks;
+    if (k.create_cap != max_records) {
+        k.create_cap = max_records;
+        k.table_epoch = ~0ull;  // the buffer is (re)allocated with the table
+        k.create_valid = false;
+        drop_graph(c);
+    }
+    return RECS_OK;
+}
+
+int32_t recs_gpu_system_creates(recs_gpu_ctx* c, uint32_t id, void* out_records, uint32_t cap_records, uint32_t* out_count,
+                                uint32_t* out_record_bytes) {
+    RECS_ENTER(c);
+    if (id >= c->systems.size() || !c->systems[id].ks || !out_count)
+        return fail(c, RECS_ERR_INVALID_ARGUMENT, "system_creates: not a generic system");
+    KernelSys& k = *c->systems[id].ks;
+    if (out_record_bytes) *out_record_bytes = k.create_bytes;
+    *out_count = 0;
+    if (!k.create_bytes || !k.create_valid || !k.create_buf) return RECS_OK;  // nothing recorded (or never run)
+    uint32_t header[4] = {0, 0, 0, 0};
+    RECS_CUDA(c, cudaMemcpyAsync(header, k.create_buf, sizeof header, cudaMemcpyDeviceToHost, c->stream));
+    RECS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (header[3]) return fail(c, RECS_ERR_SIZE_MISMATCH, "Commands::create was called with a record whose size differs from the registered one");
+    const uint32_t n = header[0];
+    if (n > k.create_cap) {
+        char buf[200];
+        snprintf(buf, sizeof buf, "Commands::create: %u records in one run, the buffer holds %u (recs_gpu_system_set_create_capacity)", n, k.create_cap);
+        return fail(c, RECS_ERR_SIZE_MISMATCH, buf);
+    }
+    *out_count = n;
+    if (!out_records || n == 0) return RECS_OK;
+    const uint32_t stride = k.create_stride();
+    std::vector<unsigned char> raw((size_t)n * stride);
+    RECS_CUDA(c, cudaMemcpy(raw.data(), k.create_buf + 16, raw.size(), cudaMemcpyDeviceToHost));
+    c->d2h_bytes += raw.size();
+    // playback order = the order a sequential run would have recorded them in: entity order, then call order
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; ++i) order[i] = i;
+    auto key = [&](uint32_t i) {
+        unsigned long long k64;
+        uint32_t call;
+        memcpy(&k64, raw.data() + (size_t)i * stride, 8);
+        memcpy(&call, raw.data() + (size_t)i * stride + 8, 4);
+        return std::make_pair(k64, call);
+    };
+    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    for (uint32_t i = 0; i < n && i < cap_records; ++i)
+        memcpy((unsigned char*)out_records + (size_t)i * k.create_bytes, raw.data() + (size_t)order[i] * stride + 16, k.create_bytes);
     return RECS_OK;
 }
 
@@ -1832,6 +1952,31 @@ int32_t recs_gpu_exchange_mode(recs_gpu_ctx* c) {
     std::lock_guard<std::mutex> lock(c->mu);
     if (c->cfg.world_size <= 1) return 0;
     return c->xchg.imported && !c->exchange_nccl_forced ? 2 : 1;
+}
+
+// Every rank's own rows of a column (its recs_gpu_shard_rows slice), delivered to all ranks: what makes a column
+// written by a row-sharded system complete again (the nested Query of a generic system reads all of it).
+int32_t recs_gpu_column_allgather(recs_gpu_ctx* c, uint32_t arch, uint64_t comp) {
+    RECS_ENTER(c);
+    if (c->cfg.world_size <= 1) return RECS_OK;
+    if (!c->comm) return fail(c, RECS_ERR_NCCL, "column_allgather: recs_gpu_comm_init was not called");
+    Column* col = find_column(c, arch, comp);
+    if (!col || !col->dev) return fail(c, RECS_ERR_MISSING_PARAMETER, "column_allgather: column is not bound");
+    if (col->stale) return fail(c, RECS_ERR_STALE_BINDING, "column_allgather: column binding is stale");
+    // one in-place broadcast per owner, grouped: slices are contiguous row ranges, the last ones may be short or empty
+    int r = c->nccl.GroupStart();
+    for (int root = 0; root < c->cfg.world_size && r == 0; ++root) {
+        uint64_t slice, rb, re;
+        shard_rows_for(root, c->cfg.world_size, col->count, &slice, &rb, &re);
+        if (re == rb) continue;
+        unsigned char* p = (unsigned char*)col->dev + rb * col->elem;
+        r = c->nccl.Broadcast(p, p, (size_t)(re - rb) * col->elem, /*ncclUint8*/ 1, root, c->comm, c->stream);
+    }
+    const int e = c->nccl.GroupEnd();
+    if (r == 0) r = e;
+    if (r != 0) return fail(c, RECS_ERR_NCCL, std::string("ncclBroadcast: ") + c->nccl.GetErrorString(r));
+    col->version++;
+    return RECS_OK;
 }
 
 int32_t recs_gpu_shard_rows(recs_gpu_ctx* c, uint64_t n_rows, uint64_t* row_begin, uint64_t* row_end) {

@@ -508,46 +508,63 @@ __device__ __forceinline__ void store_posm(const PeerPush& p, float* local, uint
     }
 }
 
+__device__ __forceinline__ bool valid_work(const GravityWork& w) { return w.n_iblocks != 0 && w.grid != 0; }
+constexpr uint32_t kGravMaxChunks = 64;  // chunks of the summation tree: kGravTargetChunks plus the padding of up to 16 ranks
+
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.row_count;
+    const GravityWork& w = a.work;
+    const uint32_t rows = a.iblock_rows;  // a multiple of the CTA size: one i-block per CTA
+    const uint32_t b = (blockIdx.x * blockDim.x) / rows;
+    const uint32_t K = w.chunk_tiles;
+    const uint32_t n_chunks = w.n_tiles_total / K;
+    // Where the pieces of every chunk sum of this i-block are: the same for all rows of the CTA, worked out once.
+    //   s_slot[c]            prefix fragment of chunk c
+    //   [s_ext_lo, s_ext_hi) units of the chunk beyond the span of the CTA that owns its first tile (tile fragments);
+    //                        empty for all but the <= grid chunks a span boundary falls into
+    __shared__ uint32_t s_slot[kGravMaxChunks], s_ext_lo[kGravMaxChunks], s_ext_hi[kGravMaxChunks], s_phase[kGravMaxChunks];
+    if (threadIdx.x < n_chunks && valid_work(w)) {
+        const uint32_t c = threadIdx.x;
+        const uint32_t tile0 = c * K;
+        uint32_t ph = 0, v0 = 0;
+        for (; ph < w.n_phases; ++ph) {  // the phase whose rotated tile range holds the chunk
+            v0 = tile0 >= w.phase[ph].tile_offset ? tile0 - w.phase[ph].tile_offset
+                                                  : tile0 + w.n_tiles_total - w.phase[ph].tile_offset;
+            if (v0 < w.phase[ph].n_vtiles) break;
+        }
+        const GravityPhase& P = w.phase[ph < w.n_phases ? ph : 0];
+        const uint32_t units = w.n_iblocks * P.n_vtiles;
+        const uint32_t u0 = b * P.n_vtiles + v0;
+        const Span s0 = span_of(cta_of(u0, w.grid, units), w.grid, units);
+        s_phase[c] = ph;
+        s_slot[c] = P.frag_base + b * (P.n_vtiles / K) + v0 / K;
+        s_ext_lo[c] = min(u0 + K, s0.begin + s0.count);
+        s_ext_hi[c] = u0 + K;
+    }
+    __syncthreads();
     if (a.tail.posm) push_begin(a.push);
     if (valid) {
-        const GravityWork& w = a.work;
-        const uint32_t rows = a.iblock_rows;
-        const uint32_t b = i / rows;
-        const uint32_t idx = i % rows;
-        const uint32_t K = w.chunk_tiles;
-        const uint32_t n_chunks = w.n_tiles_total / K;
+        const uint32_t idx = i - b * rows;
         // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
         float sx = 0.f, sy = 0.f, sz = 0.f;
         for (uint32_t c = 0; c < n_chunks; ++c) {
-            // the phase whose rotated tile range holds chunk c
-            const uint32_t tile0 = c * K;
-            uint32_t ph = 0, v0 = 0;
-            for (; ph < w.n_phases; ++ph) {
-                v0 = tile0 >= w.phase[ph].tile_offset ? tile0 - w.phase[ph].tile_offset
-                                                      : tile0 + w.n_tiles_total - w.phase[ph].tile_offset;
-                if (v0 < w.phase[ph].n_vtiles) break;
-            }
-            if (ph == w.n_phases) continue;  // not visited (cannot happen for a complete work description)
-            const GravityPhase& P = w.phase[ph];
-            const uint32_t units = w.n_iblocks * P.n_vtiles;
-            const uint32_t u0 = b * P.n_vtiles + v0;
-            const uint32_t g0 = cta_of(u0, w.grid, units);
-            const Span s0 = span_of(g0, w.grid, units);
-            float4 f = __ldcs(a.frags + static_cast<size_t>(P.frag_base + b * (P.n_vtiles / K) + v0 / K) * rows + idx);
+            float4 f = __ldcs(a.frags + static_cast<size_t>(s_slot[c]) * rows + idx);
             float cx = f.x, cy = f.y, cz = f.z;
-            // tiles of the chunk beyond the span of the CTA that owns its first tile: stored one by one
-            uint32_t u = min(u0 + K, s0.begin + s0.count);
-            uint32_t g = g0;
-            Span sg = s0;
-            for (; u < u0 + K; ++u) {
-                while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
-                f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx);
-                cx += f.x;
-                cy += f.y;
-                cz += f.z;
+            if (s_ext_lo[c] < s_ext_hi[c]) {
+                // continue the prefix with the tile sums other CTAs stored one by one, in tile order
+                const GravityPhase& P = w.phase[s_phase[c]];
+                const uint32_t units = w.n_iblocks * P.n_vtiles;
+                uint32_t u = s_ext_lo[c];
+                uint32_t g = cta_of(u, w.grid, units);
+                Span sg = span_of(g, w.grid, units);
+                for (; u < s_ext_hi[c]; ++u) {
+                    while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
+                    f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx);
+                    cx += f.x;
+                    cy += f.y;
+                    cz += f.z;
+                }
             }
             sx += cx;
             sy += cy;

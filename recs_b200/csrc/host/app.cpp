@@ -39,7 +39,19 @@ struct AppSystem {
     recs_cpu_system_fn fn = nullptr;
     recs_cpu_segment_fn segment_fn = nullptr;  // par-iter form: may be cut into segments (SegmentIterable)
     bool decides_removals = false;             // generic GPU system with a Commands parameter
+    // generic GPU system whose Commands parameter creates entities: the components of a create() record, in record order
+    std::vector<uint64_t> create_comps;
+    std::vector<uint32_t> create_sizes;
     void* user = nullptr;
+};
+
+// The system whose function is running on this thread: commands are recorded into ITS buffer, and playback drains the
+// buffers in system registration order (receive_all_commands, crates/ecs/src/lib.rs:325-336).
+thread_local uint32_t t_current_system = 0xffffffffu;
+struct CurrentSystem {
+    uint32_t saved;
+    explicit CurrentSystem(uint32_t index) : saved(t_current_system) { t_current_system = index; }
+    ~CurrentSystem() { t_current_system = saved; }
 };
 
 // `WorkerPool` (crates/scheduler/src/executor/mod.rs:101-188, worker.rs:141-168) reduced to what the executor
@@ -145,12 +157,14 @@ std::vector<recs_param_token> gpu_kind_tokens(recs_gpu_system_kind kind, const u
 struct CreateCommand {
     std::vector<uint64_t> ids;
     std::vector<std::vector<uint8_t>> values;
+    uint32_t system = 0xffffffffu;  // index of the recording system (commands recorded outside a system come last)
 };
 
 struct recs_app {
     std::vector<CreateCommand> creates;   // EntityCommand::Create, record order
     std::vector<recs_entity> removes;     // EntityCommand::Remove, record order
     std::vector<std::pair<uint32_t, std::vector<uint32_t>>> gpu_removal_sources;  // (system index, outer archetypes) run this tick
+    std::vector<uint32_t> gpu_create_sources;  // generic GPU systems with a create() record run this tick
     uint64_t last_created = 0, last_removed = 0;
     recs_gpu_ctx* gpu = nullptr;
     recs_world* world = nullptr;
@@ -278,6 +292,7 @@ int32_t run_gpu_system(recs_app* app, AppSystem& s) {
     app->gpu_chain.push_back(s.gpu_id);  // launched by flush_gpu_chain
     if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION || s.decides_removals)
         app->gpu_removal_sources.push_back(std::make_pair((uint32_t)(&s - app->systems.data()), archs));
+    if (!s.create_comps.empty()) app->gpu_create_sources.push_back((uint32_t)(&s - app->systems.data()));
     for (const Param& p : s.params)
         if (p.op == RECS_PARAM_WRITE)
             for (uint32_t a : archs) app->mirror[ColKey(a, p.comp)].device_dirty = true;
@@ -348,16 +363,24 @@ void finish_cpu_system(recs_app* app, CpuRun& run) {
 // the concatenation of the matched archetypes' columns cut by split_borrowed_data (:473-540).
 void cpu_system_tasks(recs_app* app, CpuRun& run, std::vector<std::function<void()>>* tasks) {
     AppSystem& s = *run.sys;
+    const uint32_t self = (uint32_t)(&s - app->systems.data());
     if (!params_controls_iteration(s.params)) {
         // no iterating parameter: the function runs exactly once (iterate_once, iteration.rs:43)
         if (s.segment_fn)
-            tasks->push_back([&s] { s.segment_fn(s.user, 0, 0, 0, nullptr, 0); });
+            tasks->push_back([&s, self] {
+                CurrentSystem cur(self);
+                s.segment_fn(s.user, 0, 0, 0, nullptr, 0);
+            });
         else
-            tasks->push_back([&s] { s.fn(s.user, 0, 0, nullptr, 0); });
+            tasks->push_back([&s, self] {
+                CurrentSystem cur(self);
+                s.fn(s.user, 0, 0, nullptr, 0);
+            });
         return;
     }
     if (!s.segment_fn) {
-        tasks->push_back([&s, &run] {
+        tasks->push_back([&s, &run, self] {
+            CurrentSystem cur(self);
             for (size_t k = 0; k < run.cols.size(); ++k)
                 s.fn(s.user, run.archs[k], run.counts[k], run.cols[k].data(), (uint32_t)run.cols[k].size());
         });
@@ -376,7 +399,8 @@ void cpu_system_tasks(recs_app* app, CpuRun& run, std::vector<std::function<void
         for (const recs_segment_slice& sl : slices)
             if (sl.segment == seg && sl.len) mine.push_back(sl);
         if (mine.empty()) continue;
-        tasks->push_back([&s, &run, mine] {
+        tasks->push_back([&s, &run, mine, self] {
+            CurrentSystem cur(self);
             for (const recs_segment_slice& sl : mine)
                 s.segment_fn(s.user, run.archs[sl.column], sl.begin, sl.len, run.cols[sl.column].data(),
                              (uint32_t)run.cols[sl.column].size());
@@ -439,6 +463,31 @@ int32_t playback_commands(recs_app* app) {
     }
     app->gpu_removal_sources.clear();
     app->removes.clear();
+    // `Commands::create` calls of generic GPU systems: records fetched in sequential-run order, split into components
+    for (uint32_t index : app->gpu_create_sources) {
+        AppSystem& s = app->systems[index];
+        uint32_t n = 0, bytes = 0;
+        int32_t st = recs_gpu_system_creates(app->gpu, s.gpu_id, nullptr, 0, &n, &bytes);
+        if (st != RECS_OK) return gpu_fail(app, st);
+        if (!n) continue;
+        std::vector<uint8_t> records((size_t)n * bytes);
+        if ((st = recs_gpu_system_creates(app->gpu, s.gpu_id, records.data(), n, &n, &bytes)) != RECS_OK) return gpu_fail(app, st);
+        for (uint32_t r = 0; r < n; ++r) {
+            CreateCommand cmd;
+            cmd.system = index;
+            size_t off = (size_t)r * bytes;
+            for (size_t k = 0; k < s.create_comps.size(); ++k) {
+                cmd.ids.push_back(s.create_comps[k]);
+                cmd.values.push_back(std::vector<uint8_t>(records.begin() + off, records.begin() + off + s.create_sizes[k]));
+                off += s.create_sizes[k];
+            }
+            app->creates.push_back(std::move(cmd));
+        }
+    }
+    app->gpu_create_sources.clear();
+    // command buffers are drained system by system, in registration order (crates/ecs/src/lib.rs:325-336)
+    std::stable_sort(app->creates.begin(), app->creates.end(),
+                     [](const CreateCommand& a, const CreateCommand& b) { return a.system < b.system; });
     if (app->creates.empty() && to_remove.empty()) return RECS_OK;
     // The host World stays the authority on entity ids and row indices; resident device columns follow it WITHOUT a
     // round trip: appended rows are uploaded alone, swap-removes are replayed on the device as row moves.  A column
@@ -597,7 +646,18 @@ int32_t recs_app_add_gpu_system(recs_app* app, recs_gpu_system_kind kind, const 
 int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const char* source, const char* body,
                                        const recs_param_token* tokens, uint32_t n_tokens, const char* const* type_names,
                                        const char* uniform_type, uint32_t uniform_bytes, uint32_t* out_index) {
+    return recs_app_add_gpu_kernel_system_creating(app, name, source, body, tokens, n_tokens, type_names, uniform_type,
+                                                   uniform_bytes, nullptr, 0, nullptr, out_index);
+}
+
+int32_t recs_app_add_gpu_kernel_system_creating(recs_app* app, const char* name, const char* source, const char* body,
+                                                const recs_param_token* tokens, uint32_t n_tokens,
+                                                const char* const* type_names, const char* uniform_type,
+                                                uint32_t uniform_bytes, const uint64_t* create_components,
+                                                uint32_t n_create_components, const char* create_record_type,
+                                                uint32_t* out_index) {
     if (!app || !name || !source || !body || (n_tokens && !tokens) || !type_names) return RECS_ERR_INVALID_ARGUMENT;
+    if (n_create_components && (!create_components || !create_record_type)) return RECS_ERR_INVALID_ARGUMENT;
     if (!app->gpu) return app->fail(RECS_ERR_NO_DEVICE, "no GPU context: GPU systems cannot be registered (there is no CPU fallback)");
     AppSystem s;
     s.gpu = true;
@@ -621,11 +681,21 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
         } else if (p.op == RECS_PARAM_ENTITY) {
             k.elem_size = 8;
             k.kind = RECS_KPARAM_ENTITY;
-        } else if (p.op == RECS_PARAM_COMMANDS) {  // remove() only; no type name consumed
+        } else if (p.op == RECS_PARAM_COMMANDS) {  // no type name consumed from type_names
             k.component_id = 0;
             k.elem_size = 0;
             k.kind = RECS_KPARAM_COMMANDS;
             k.type_name = nullptr;
+            // Commands::create: the record is the tuple of components of the new entity, packed in the given order
+            for (uint32_t ci = 0; ci < n_create_components; ++ci) {
+                auto it = app->world->registry.find(create_components[ci]);
+                if (it == app->world->registry.end())
+                    return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: a component of the create record is not registered");
+                s.create_comps.push_back(create_components[ci]);
+                s.create_sizes.push_back(it->second.elem);
+                k.elem_size += it->second.elem;
+            }
+            if (n_create_components) k.type_name = create_record_type;
             kp.push_back(k);
             s.decides_removals = true;
             continue;
@@ -638,6 +708,8 @@ int32_t recs_app_add_gpu_kernel_system(recs_app* app, const char* name, const ch
         kp.push_back(k);
         ++n_typed;
     }
+    if (n_create_components && s.create_comps.empty())
+        return app->fail(RECS_ERR_INVALID_ARGUMENT, "kernel system: a create record needs a Commands parameter");
     int32_t st = recs_gpu_system_create_kernel(app->gpu, name, source, body, kp.data(), (uint32_t)kp.size(), uniform_type,
                                                uniform_bytes, &s.gpu_id);
     if (st != RECS_OK) return gpu_fail(app, st);
@@ -790,6 +862,7 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
     std::vector<uint32_t> batch(app->systems.size() + 1);
     for (uint32_t tick = 0; tick < n_ticks; ++tick) {
         app->gpu_chain.clear();  // nothing survives a tick (or an error return)
+        app->gpu_create_sources.clear();
         app->last_order.clear();
         app->last_batch.clear();
         uint32_t batch_no = 0;
@@ -855,6 +928,7 @@ int32_t recs_app_command_create(recs_app* app, const uint64_t* ids, const void* 
         if (it->second.elem && values && values[i]) memcpy(bytes.data(), values[i], it->second.elem);
         cmd.values.push_back(bytes);
     }
+    cmd.system = t_current_system;
     std::lock_guard<std::mutex> lock(app->command_mu);
     app->creates.push_back(cmd);
     return RECS_OK;

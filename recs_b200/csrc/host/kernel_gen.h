@@ -11,6 +11,8 @@
 #include <string>
 #include <vector>
 
+struct recs_gpu_kernel_param;
+
 namespace recs {
 
 struct KernelParamSpec {
@@ -27,6 +29,9 @@ struct KernelPlan {
     std::vector<uint32_t> smem_offset;  // per parameter
     std::string source;        // user source + generated kernel `recs_generic_system`
 };
+
+// A `Commands` parameter: type_name / elem_size describe the create() record (elem_size 0: remove() only).
+KernelParamSpec commands_param_spec(const recs_gpu_kernel_param& p);
 
 // Decides the kernel form and generates the translation unit.
 KernelPlan plan_kernel_system(const std::string& user_source, const std::string& body,

@@ -18,6 +18,9 @@ struct NcclApi {
     int (*CommInitRank)(comm_t*, int, unique_id, int) = nullptr;
     int (*CommDestroy)(comm_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, comm_t, cudaStream_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     void* handle = nullptr;
 
@@ -38,8 +41,11 @@ struct NcclApi {
         CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(handle, "ncclCommInitRank"));
         CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(handle, "ncclCommDestroy"));
         AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(handle, "ncclAllGather"));
+        Broadcast = reinterpret_cast<decltype(Broadcast)>(dlsym(handle, "ncclBroadcast"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(dlsym(handle, "ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(dlsym(handle, "ncclGroupEnd"));
         GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(handle, "ncclGetErrorString"));
-        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) {
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString || !Broadcast || !GroupStart || !GroupEnd) {
             *why = "libnccl is missing a required symbol";
             return false;
         }

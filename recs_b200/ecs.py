@@ -94,6 +94,11 @@ ECS_SYMBOLS = {
         C.c_int32,
         [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32, _u32p],
     ),
+    "recs_app_add_gpu_kernel_system_creating": (
+        C.c_int32,
+        [_a, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(ParamToken), C.c_uint32, C.POINTER(C.c_char_p), C.c_char_p, C.c_uint32,
+         _u64p, C.c_uint32, C.c_char_p, _u32p],
+    ),
     "recs_app_set_system_uniform": (C.c_int32, [_a, C.c_uint32, C.c_void_p, C.c_uint32]),
     "recs_app_add_gpu_pair_kernel_system": (
         C.c_int32,
@@ -485,17 +490,22 @@ class Application:
         return int(idx.value)
 
     def add_gpu_kernel_system(self, name: str, source: str, body: str, params, type_names: Sequence[str],
-                              uniform_type: str | None = None, uniform_bytes: int = 0) -> int:
+                              uniform_type: str | None = None, uniform_bytes: int = 0, creates: Sequence[int] = (),
+                              create_record_type: str | None = None) -> int:
         """A generic GPU system: `params` is the function's parameter list (same grammar as CPU systems, filters
-        included); `type_names` are the C++ types of its Read / Write / Entity arguments in `source`, in order."""
+        included); `type_names` are the C++ types of its Read / Write / Entity arguments in `source`, in order.
+        `creates` / `create_record_type`: the components of the tuple its Commands parameter hands to create(), and the POD
+        struct in `source` holding them in that order (recs_app_add_gpu_kernel_system_creating)."""
         arr, n = tokens(params)
         names = (C.c_char_p * max(len(type_names), 1))(*[t.encode() for t in type_names])
         idx = C.c_uint32()
+        comps = (C.c_uint64 * max(len(creates), 1))(*creates)
         self._check(
-            lib.recs_app_add_gpu_kernel_system(
+            lib.recs_app_add_gpu_kernel_system_creating(
                 self._h, name.encode(), source.encode(), body.encode(), arr, n, names,
-                uniform_type.encode() if uniform_type else None, uniform_bytes, C.byref(idx)),
-            "recs_app_add_gpu_kernel_system",
+                uniform_type.encode() if uniform_type else None, uniform_bytes, comps, len(creates),
+                create_record_type.encode() if create_record_type else None, C.byref(idx)),
+            "recs_app_add_gpu_kernel_system_creating",
         )
         self.system_names.append(name)
         return int(idx.value)

@@ -184,6 +184,21 @@ class GpuContext:
         self._check(lib.recs_gpu_system_removals(self._ctx, system, archetype, out, n.value, C.byref(n)), "recs_gpu_system_removals")
         return np.array(out[: n.value], dtype=np.uint32)
 
+    def system_creates(self, system: int, dtype) -> np.ndarray:
+        """Records the system's last run handed to `Commands::create`, in sequential-run order, as a structured array."""
+        n, size = C.c_uint32(), C.c_uint32()
+        self._check(lib.recs_gpu_system_creates(self._ctx, system, None, 0, C.byref(n), C.byref(size)), "recs_gpu_system_creates")
+        dtype = np.dtype(dtype)
+        assert n.value == 0 or dtype.itemsize == size.value, (dtype.itemsize, size.value)
+        out = np.zeros(n.value, dtype=dtype)
+        if n.value:
+            self._check(lib.recs_gpu_system_creates(self._ctx, system, out.ctypes.data_as(C.c_void_p), n.value, C.byref(n), C.byref(size)),
+                        "recs_gpu_system_creates")
+        return out
+
+    def set_create_capacity(self, system: int, max_records: int) -> None:
+        self._check(lib.recs_gpu_system_set_create_capacity(self._ctx, system, max_records), "recs_gpu_system_set_create_capacity")
+
     def run_system(self, system: int, sync: bool = True) -> None:
         self._check(
             lib.recs_gpu_run_system(self._ctx, system, _lib.GPU_SYNC if sync else _lib.GPU_ASYNC), "recs_gpu_run_system"
@@ -230,6 +245,10 @@ class GpuContext:
 
     def exchange_mode(self) -> str:
         return {0: "single", 1: "nccl-allgather", 2: "peer-push"}[lib.recs_gpu_exchange_mode(self._ctx)]
+
+    def column_allgather(self, archetype: int, component: int) -> None:
+        """Every rank's own rows of the column to all ranks (recs_gpu_column_allgather)."""
+        self._check(lib.recs_gpu_column_allgather(self._ctx, archetype, component), "recs_gpu_column_allgather")
 
     def shard_rows(self, n_rows: int) -> tuple[int, int]:
         b, e = C.c_uint64(), C.c_uint64()
@@ -296,7 +315,7 @@ def kernel_params(params):
         arr[i].component_id = comp
         arr[i].elem_size = elem
         arr[i].kind = _KPARAM_KINDS[kind]
-        arr[i].type_name = type_name.encode() if type_name else None
+        arr[i].type_name = type_name.encode() if type_name else None  # ("commands", size, record type): Commands::create record
     arr._n = len(params)
     return arr
 

@@ -59,3 +59,14 @@ def test_sharded_streaming_systems_need_no_exchange():
     world = 2 if n_gpu < 4 else 4
     proc = _torchrun(world, "tests/tools/multi_gpu_stream_check.py", [100003], {"RECS_TEST_SAME_DEVICE": "1"} if n_gpu < 2 else {})
     assert proc.returncode == 0 and "MULTI_GPU_STREAM_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+
+
+def test_generic_nested_query_systems_on_a_sharded_context():
+    """recs_gpu_system_create_pair_kernel with world_size > 1: own outer rows x the whole nested query, the written
+    column gathered with recs_gpu_column_allgather; bit-exact against the oracle after several ticks."""
+    n_gpu = _gpu_count()
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs (NCCL)")
+    world = 2 if n_gpu < 4 else 4
+    proc = _torchrun(world, "tests/tools/multi_gpu_pair_check.py", [6000, 3])
+    assert proc.returncode == 0 and "MULTI_GPU_PAIR_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]

@@ -129,10 +129,30 @@ def test_nbody_demo_with_collision_through_application(gpu_ctx, nbody_oracle):
 # the complete rain tick: clouds spawn drops (CPU, Commands::create), drops fall (GPU), drops that
 # reach the ground are removed (GPU decides, host plays back)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("worker_threads", [0, 3])
-def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle, worker_threads):
+RAIN_ON_DEVICE = """
+struct Cloud { float vapor_accumulation_rate, width, height; };
+struct Position { float x, y, z; };
+struct Mass { float m; };
+struct Drop { float vx, vy, vz; float mass; float px, py, pz; };   // (Velocity::default(), Mass(0.1), Position { drop_position })
+// crates/rain-simulation/src/lib.rs:128-148
+void rain(const Cloud& cloud, const Position& position, Mass& mass, const recs_commands& commands) {
+    while (mass.m > 0.1f) {
+        commands.create(Drop{0.0f, 0.0f, 0.0f, 0.1f, position.x, position.y, position.z});  // deterministic_point_on_surface = center (:45-47)
+        mass.m -= 0.1f;
+    }
+}
+// crates/rain-simulation/src/lib.rs:158-160
+void vapor_accumulation(const Cloud& cloud, Mass& mass) { mass.m += cloud.vapor_accumulation_rate * 0.05f; }
+"""
+
+
+@pytest.mark.parametrize("worker_threads,rain_on_device", [(0, False), (3, False), (0, True), (3, True)])
+def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle, worker_threads, rain_on_device):
     """worker_threads = 0: Sequential executor; 3: WorkerPool -- the CPU systems of a batch run on worker threads
-    while the GPU systems of the same batch are enqueued from the scheduling thread."""
+    while the GPU systems of the same batch are enqueued from the scheduling thread.
+    rain_on_device: `rain` (which spawns the drops with Commands::create) and `vapor_accumulation` are generic GPU
+    systems too, so the WHOLE tick of the reference runs on the device; only the create records and the removal
+    rows come back for playback on the host World."""
     VEL, POS, MASS, CLOUD = 20, 21, 22, 23
     n_clouds, ticks = 9, 60
     app = ecs.Application(gpu=gpu_ctx)
@@ -159,9 +179,17 @@ def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle, worker_thread
     app.add_gpu_system(_lib.SYS_RAIN_WIND, [VEL], "wind")
     app.add_gpu_system(_lib.SYS_RAIN_WIND_DIRECTION, [], "wind_direction")
     app.add_gpu_system(_lib.SYS_RAIN_MOVEMENT, [POS, VEL], "movement")
-    app.add_cpu_system("rain", [("read", CLOUD), ("read", POS), ("write", MASS), ("commands",)], rain)
+    if rain_on_device:
+        app.add_gpu_kernel_system("rain", RAIN_ON_DEVICE, "rain", [("read", CLOUD), ("read", POS), ("write", MASS), ("commands",)],
+                                  ["Cloud", "Position", "Mass"], creates=[VEL, MASS, POS], create_record_type="Drop")
+    else:
+        app.add_cpu_system("rain", [("read", CLOUD), ("read", POS), ("write", MASS), ("commands",)], rain)
     app.add_gpu_system(_lib.SYS_RAIN_GROUND_COLLISION, [POS], "ground_collision")
-    app.add_cpu_system("vapor_accumulation", [("read", CLOUD), ("write", MASS)], vapor)
+    if rain_on_device:
+        app.add_gpu_kernel_system("vapor_accumulation", RAIN_ON_DEVICE, "vapor_accumulation", [("read", CLOUD), ("write", MASS)],
+                                  ["Cloud", "Mass"])
+    else:
+        app.add_cpu_system("vapor_accumulation", [("read", CLOUD), ("write", MASS)], vapor)
     app.add_cpu_system("benchmark_system", [], lambda a, c, cols: ticks_seen.append(1))
     # create_evenly_interspersed_clouds (crates/rain-simulation/src/scene.rs:27-54); low clouds so drops land soon
     side = int(np.sqrt(n_clouds))
@@ -222,7 +250,8 @@ def test_full_rain_tick_through_application(gpu_ctx, nbody_oracle, worker_thread
     # rows of new drops (12 B velocity + 12 B position each), the swap-remove move lists (8 B per move) and the nine
     # clouds' columns crossed PCIe, and nothing was downloaded before the final sync
     h2d, d2h = gpu_ctx.transfer_bytes()
-    assert d2h == 0
+    # (on the device, every create record comes back once: 16-byte order tag + the 28-byte tuple rounded up to 8)
+    assert d2h == (total_created * 48 if rain_on_device else 0)
     assert h2d <= total_created * 24 + total_removed * 8 + 9 * 12 * 4, (h2d, total_created, total_removed)
     app.sync_to_host()
     assert len(ticks_seen) == ticks and total_created > 20 and total_removed > 5
@@ -306,7 +335,8 @@ def test_resident_columns_follow_random_creates_and_removes(gpu_ctx, seed):
                 ow.delete_entity(e)
         assert app.last_playback() == (len(creates), len(done)), tick
     h2d, d2h = gpu_ctx.transfer_bytes()
-    assert d2h == 0  # nothing came back before the final sync
+    # (on the device, every create record comes back once: 16-byte order tag + the 28-byte tuple rounded up to 8)
+    assert d2h == (total_created * 48 if rain_on_device else 0)  # nothing came back before the final sync
     assert h2d <= (700 + serial[0]) * (12 + 8 + 6) + 25 * 120 * 8 + 1024
     app.sync_to_host()
     arch = ow.archetypes[1]

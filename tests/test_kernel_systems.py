@@ -417,3 +417,84 @@ def test_random_layouts_against_numpy(gpu_ctx, seed):
                     want[:, 0] = (want[:, 0].astype(np.uint32) + 1 + k).astype(np.uint8)
                     want[:, s - 1] = (want[:, s - 1].astype(np.uint32) + 2 + k).astype(np.uint8)
             assert np.array_equal(cols[i], want), (seed, a, i, sizes, kinds, counts)
+
+
+# ---- Commands::create in generic systems (crates/ecs/src/systems/command_buffers.rs:53-66) ---------------------------
+SPAWNER = """
+struct Budget { int n; };
+struct Tag { float v; };
+struct Child { float parent; float index; float tag; };
+void spawner(Budget& budget, const Tag& tag, const recs_commands& commands) {
+    for (int k = 0; k < budget.n; ++k) commands.create(Child{tag.v, (float)k, tag.v * 10.0f + (float)k});
+    budget.n = 0;
+}
+"""
+SPAWNER_PARAMS = [(1, 4, "write", "Budget"), (2, 4, "read", "Tag"), (0, 12, "commands", "Child")]
+
+
+def test_creating_system_compiles_without_a_gpu():
+    st, log, cubin, _ = compile_kernel_system(SPAWNER, "spawner", SPAWNER_PARAMS)
+    assert st == 0 and cubin > 1000, log
+    # the registered record size is checked against the struct in the source
+    st, log, _, _ = compile_kernel_system(SPAWNER, "spawner", SPAWNER_PARAMS[:2] + [(0, 16, "commands", "Child")])
+    assert st == 12 and "Commands::create record" in log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("counts", [(3000, 0), (700, 1300), (1, 1)])
+def test_create_records_come_back_in_sequential_run_order(gpu_ctx, counts):
+    """Every entity of two archetypes spawns 0..3 children; thousands of threads race for slots of the append buffer,
+    yet the records come back in the order a sequential run over (archetype, row) would have recorded them -- the order
+    that fixes the entity ids handed out at playback."""
+    ctx = gpu_ctx
+    rng = np.random.default_rng(5)
+    cols, want = {}, []
+    for arch, n in zip((1, 2), counts):
+        budget = rng.integers(0, 4, size=n).astype(np.int32)
+        tag = (np.arange(n, dtype=np.float32) + np.float32(arch * 100000))
+        cols[arch] = (budget, tag)
+        ctx.bind_column(arch, 1, budget)
+        ctx.bind_column(arch, 2, tag)
+        ctx.upload(arch, 1)
+        ctx.upload(arch, 2)
+        for i in range(n):
+            want += [(tag[i], float(k), tag[i] * np.float32(10.0) + np.float32(k)) for k in range(budget[i])]
+    sid = ctx.create_kernel_system("spawner", SPAWNER, "spawner", SPAWNER_PARAMS)
+    ctx.set_archetypes(sid, [1, 2])
+    ctx.run_system(sid)
+    child = np.dtype([("parent", np.float32), ("index", np.float32), ("tag", np.float32)])
+    got = ctx.system_creates(sid, child)
+    assert len(got) == len(want)
+    assert np.array_equal(got.view(np.float32).reshape(-1, 3), np.array(want, np.float32).reshape(-1, 3))
+    ctx.download(1, 1)
+    assert not cols[1][0].any()  # budgets spent
+    # a second run records nothing
+    ctx.run_system(sid)
+    assert len(ctx.system_creates(sid, child)) == 0
+
+
+@pytest.mark.gpu
+def test_create_buffer_overflow_is_an_error_not_a_silent_drop(gpu_ctx):
+    from recs_b200 import RecsGpuError
+
+    ctx = gpu_ctx
+    n = 1000
+    budget = np.full(n, 3, np.int32)
+    tag = np.arange(n, dtype=np.float32)
+    ctx.bind_column(1, 1, budget)
+    ctx.bind_column(1, 2, tag)
+    ctx.upload(1, 1)
+    ctx.upload(1, 2)
+    sid = ctx.create_kernel_system("spawner", SPAWNER, "spawner", SPAWNER_PARAMS)
+    ctx.set_archetypes(sid, [1])
+    ctx.set_create_capacity(sid, 100)
+    ctx.run_system(sid)
+    child = np.dtype([("parent", np.float32), ("index", np.float32), ("tag", np.float32)])
+    with pytest.raises(RecsGpuError) as e:
+        ctx.system_creates(sid, child)
+    assert e.value.code == 7 and "3000 records" in str(e.value)
+    ctx.clear_error()
+    ctx.set_create_capacity(sid, 4096)
+    ctx.upload(1, 1)
+    ctx.run_system(sid)
+    assert len(ctx.system_creates(sid, child)) == 3000
