@@ -1,4 +1,4 @@
-"""Index-sharded n-body: peer-push exchange (also on a single-GPU box, ranks time-slicing it) and NCCL exchange (>= 2 GPUs)."""
+"""Index-sharded n-body on >= 2 GPUs (one per rank): peer-push exchange and NCCL exchange; skipped on a single-GPU box."""
 import os
 import socket
 import subprocess
@@ -37,15 +37,16 @@ def test_sharded_ticks_match_oracle(bodies, ticks, mode, exchange):
     every other row is NaN -- nothing outside the shard may be read from the host.  Every rank also compares its rows
     with the single-GPU result of the same ticks bit for bit.
 
-    On a single-GPU box the ranks are separate processes time-slicing GPU 0, which covers the peer-push exchange
-    (CUDA IPC mapping, generation flags, one persistent launch per tick); the NCCL exchange needs one GPU per rank."""
+    One GPU per rank, always: kernels of different ranks wait on one another (generation flags, NCCL), and several such
+    ranks time-slicing ONE GPU can end in a context-switch timeout (Xid 109, B200_PROFILING.md).  What a single GPU can
+    check of the sharded walk -- the two-phase, rotated tile order and its summation tree -- is in
+    tests/test_gpu_nbody.py::test_result_does_not_depend_on_grid_or_rank_split; the host-side protocol is in
+    tests/test_sharding.py (gloo, CPU)."""
     n_gpu = _gpu_count()
-    if n_gpu < 1:
-        pytest.skip("needs a GPU")
-    if n_gpu < 2 and exchange == "nccl":
-        pytest.skip("NCCL needs one GPU per rank")
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs (one per rank)")
     world = 2 if n_gpu < 4 else 4
-    env = {"RECS_TEST_SAME_DEVICE": "1"} if n_gpu < 2 else {}
+    env = {}
     proc = _torchrun(world, "tests/tools/multi_gpu_check.py", [bodies, ticks, mode, exchange], env)
     assert proc.returncode == 0 and "MULTI_GPU_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
 
@@ -54,10 +55,10 @@ def test_sharded_streaming_systems_need_no_exchange():
     """Rain tick, simple_iter and a generic system: each rank streams its own contiguous slice of every archetype
     (independent units, no data-path collective), bit-exact, other rows untouched."""
     n_gpu = _gpu_count()
-    if n_gpu < 1:
-        pytest.skip("needs a GPU")
+    if n_gpu < 2:
+        pytest.skip("needs at least 2 GPUs (one per rank)")
     world = 2 if n_gpu < 4 else 4
-    proc = _torchrun(world, "tests/tools/multi_gpu_stream_check.py", [100003], {"RECS_TEST_SAME_DEVICE": "1"} if n_gpu < 2 else {})
+    proc = _torchrun(world, "tests/tools/multi_gpu_stream_check.py", [100003])
     assert proc.returncode == 0 and "MULTI_GPU_STREAM_CHECK OK" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
 
 

@@ -23,20 +23,31 @@ def _arr(ptr, count, width):
 # ---------------------------------------------------------------------------------------------------
 # collision kernel alone
 # ---------------------------------------------------------------------------------------------------
-def _collision_mask(pos, radius=f32(0.1)):
-    d = pos[None, :, :] - pos[:, None, :]  # other - self, f32
-    d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
-    np.fill_diagonal(d2, np.inf)
-    return (d2 < radius * radius).any(axis=1)
+def _collision_mask(pos, radius=f32(0.1), qpos=None, same=True):
+    """cgmath's `distance2` = (dx*dx + dy*dy) + dz*dz, every product and sum rounded on its own; in row blocks."""
+    qpos = pos if qpos is None else qpos
+    out = np.zeros(len(pos), bool)
+    for b in range(0, len(pos), 1024):
+        d = qpos[None, :, :] - pos[b:b + 1024, None, :]  # other - self, f32
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        if same:
+            idx = np.arange(b, min(b + 1024, len(pos)))
+            d2[idx - b, idx] = np.inf
+        out[b:b + 1024] = (d2 < radius * radius).any(axis=1)
+    return out
 
 
-@pytest.mark.parametrize("n", [1, 2, 257, 1500])
-def test_collision_flags_match_oracle_bit_exact(gpu_ctx, n):
+@pytest.mark.parametrize("n,box", [(1, 1.5), (2, 1.5), (257, 1.5), (1500, 1.5), (1024, 2.0), (9001, 4.0), (30000, 6.0)])
+def test_collision_flags_match_oracle_bit_exact(gpu_ctx, n, box):
+    """Sizes on both sides of the kernel's tile (256), CTA (1024 rows) and query-split boundaries; densities from
+    "nearly everything collides" (the warp-level early exit) to a few per cent."""
     POS = 1
     rng = np.random.default_rng(n)
-    pos = (rng.random((n, 3), dtype=np.float32) * f32(1.5)).astype(np.float32)
+    pos = (rng.random((n, 3), dtype=np.float32) * f32(box)).astype(np.float32)
     if n >= 2:
         pos[1] = pos[0]  # coincident distinct entities do collide (only the entity itself is skipped)
+    if n >= 2000:
+        pos[n // 2 : n // 2 + 300] = pos[n // 2]  # a clump: whole warps hit early
     gpu_ctx.bind_column(1, POS, pos)
     gpu_ctx.upload(1, POS)
     sid = gpu_ctx.create_system(_lib.SYS_NBODY_COLLISION, [POS])
@@ -48,6 +59,30 @@ def test_collision_flags_match_oracle_bit_exact(gpu_ctx, n):
     assert np.array_equal(rows, want)
     if n >= 2:
         assert 0 in rows and 1 in rows
+    if n >= 2000:
+        assert 0 < len(want) < n  # neither trivial case
+
+
+def test_collision_over_two_archetypes(gpu_ctx):
+    """Outer rows in two archetypes, the nested query over both: an entity is only skipped against ITSELF (same row of
+    the same archetype); rows with equal index in the other archetype are ordinary neighbours."""
+    POS = 1
+    rng = np.random.default_rng(77)
+    a = (rng.random((1300, 3), dtype=np.float32) * f32(3.0)).astype(np.float32)
+    b = (rng.random((700, 3), dtype=np.float32) * f32(3.0)).astype(np.float32)
+    b[5] = a[5]  # same row index, other archetype: a collision
+    for arch, col in ((1, a), (2, b)):
+        gpu_ctx.bind_column(arch, POS, col)
+        gpu_ctx.upload(arch, POS)
+    sid = gpu_ctx.create_system(_lib.SYS_NBODY_COLLISION, [POS])
+    gpu_ctx.set_archetypes(sid, [1, 2])
+    gpu_ctx.set_query_archetypes(sid, [1, 2])
+    gpu_ctx.run_system(sid)
+    want_a = _collision_mask(a) | _collision_mask(a, qpos=b, same=False)
+    want_b = _collision_mask(b) | _collision_mask(b, qpos=a, same=False)
+    assert np.array_equal(gpu_ctx.system_removals(sid, 1), np.flatnonzero(want_a).astype(np.uint32))
+    assert np.array_equal(gpu_ctx.system_removals(sid, 2), np.flatnonzero(want_b).astype(np.uint32))
+    assert want_a[5] and want_b[5]
 
 
 def test_ground_collision_flags(gpu_ctx):

@@ -498,3 +498,134 @@ def test_create_buffer_overflow_is_an_error_not_a_silent_drop(gpu_ctx):
     ctx.upload(1, 1)
     ctx.run_system(sid)
     assert len(ctx.system_creates(sid, child)) == 3000
+
+
+# ---- heavy_compute (crates/ecs_bench_suite/src/recs/heavy_compute.rs:47-52) as a generic system ----------------------
+# fn heavy_computation_system(mut position: Write<Position>, mut affine: Write<Affine>) {
+#     for _ in 0..100 { affine.0 = affine.0.invert().unwrap(); }
+#     position.0 = affine.0.transform_vector(position.0);
+# }
+# Matrix4::invert / transform_vector are cgmath 0.18.0 (Cargo.lock:1025-1026, not vendored): restated from its published
+# source (matrix.rs: `det_sub_proc_unsafe`, `SquareMatrix::invert`, `Mul<Vector4> for Matrix4` as the sum of the columns
+# scaled by the vector's components) -- the unverifiable third-party assumption of SURVEY 8(c).  The device body and the
+# numpy restatement below are written independently from that description, one operation per line.
+HEAVY_COMPUTE = """
+struct Position { float x, y, z; };
+struct Affine { float m[16]; };                       // Matrix4<f32>, column major: m[4 * column + row]
+struct V4 { float x, y, z, w; };
+static V4 det_sub_proc(const float* s, int x, int y, int z) {
+    const V4 a{s[4 + x], s[12 + x], s[x], s[8 + x]};
+    const V4 b{s[8 + y], s[8 + y], s[4 + y], s[4 + y]};
+    const V4 c{s[12 + z], s[z], s[12 + z], s[z]};
+    const V4 d{s[8 + x], s[8 + x], s[4 + x], s[4 + x]};
+    const V4 e{s[12 + y], s[y], s[12 + y], s[y]};
+    const V4 f{s[4 + z], s[12 + z], s[z], s[8 + z]};
+    const V4 g{s[12 + x], s[x], s[12 + x], s[x]};
+    const V4 h{s[4 + y], s[12 + y], s[y], s[8 + y]};
+    const V4 i{s[8 + z], s[8 + z], s[4 + z], s[4 + z]};
+    V4 t{a.x * (b.x * c.x), a.y * (b.y * c.y), a.z * (b.z * c.z), a.w * (b.w * c.w)};
+    t.x += d.x * (e.x * f.x); t.y += d.y * (e.y * f.y); t.z += d.z * (e.z * f.z); t.w += d.w * (e.w * f.w);
+    t.x += g.x * (h.x * i.x); t.y += g.y * (h.y * i.y); t.z += g.z * (h.z * i.z); t.w += g.w * (h.w * i.w);
+    t.x -= a.x * (e.x * i.x); t.y -= a.y * (e.y * i.y); t.z -= a.z * (e.z * i.z); t.w -= a.w * (e.w * i.w);
+    t.x -= d.x * (h.x * c.x); t.y -= d.y * (h.y * c.y); t.z -= d.z * (h.z * c.z); t.w -= d.w * (h.w * c.w);
+    t.x -= g.x * (b.x * f.x); t.y -= g.y * (b.y * f.y); t.z -= g.z * (b.z * f.z); t.w -= g.w * (b.w * f.w);
+    return t;
+}
+static void invert(float* s) {
+    const V4 t0 = det_sub_proc(s, 1, 2, 3);
+    const float det = ((t0.x * s[0] + t0.y * s[4]) + t0.z * s[8]) + t0.w * s[12];    // tmp0.dot(row 0)
+    const float inv_det = 1.0f / det;                                                 // (.unwrap(): det != 0)
+    const V4 t1 = det_sub_proc(s, 0, 3, 2), t2 = det_sub_proc(s, 0, 1, 3), t3 = det_sub_proc(s, 0, 2, 1);
+    const V4 cols[4] = {t0, t1, t2, t3};
+    for (int c = 0; c < 4; ++c) {
+        s[4 * c + 0] = cols[c].x * inv_det; s[4 * c + 1] = cols[c].y * inv_det;
+        s[4 * c + 2] = cols[c].z * inv_det; s[4 * c + 3] = cols[c].w * inv_det;
+    }
+}
+void heavy_computation_system(Position& position, Affine& affine) {
+    for (int k = 0; k < 100; ++k) invert(affine.m);
+    const float* m = affine.m;   // transform_vector: (m * v.extend(0)).truncate(), columns scaled and summed
+    const float vx = position.x, vy = position.y, vz = position.z;
+    position.x = ((m[0] * vx + m[4] * vy) + m[8] * vz) + m[12] * 0.0f;
+    position.y = ((m[1] * vx + m[5] * vy) + m[9] * vz) + m[13] * 0.0f;
+    position.z = ((m[2] * vx + m[6] * vy) + m[10] * vz) + m[14] * 0.0f;
+}
+"""
+
+
+def _heavy_compute_numpy(pos, aff, inversions=100):
+    """The same operations on whole columns in numpy float32 (every * and + rounds on its own, like rustc's code)."""
+    s = aff.copy()  # (n, 16)
+
+    def dsp(x, y, z):
+        col = lambda k: s[:, k]
+        a = np.stack([col(4 + x), col(12 + x), col(x), col(8 + x)], 1)
+        b = np.stack([col(8 + y), col(8 + y), col(4 + y), col(4 + y)], 1)
+        c = np.stack([col(12 + z), col(z), col(12 + z), col(z)], 1)
+        d = np.stack([col(8 + x), col(8 + x), col(4 + x), col(4 + x)], 1)
+        e = np.stack([col(12 + y), col(y), col(12 + y), col(y)], 1)
+        f = np.stack([col(4 + z), col(12 + z), col(z), col(8 + z)], 1)
+        g = np.stack([col(12 + x), col(x), col(12 + x), col(x)], 1)
+        h = np.stack([col(4 + y), col(12 + y), col(y), col(8 + y)], 1)
+        i = np.stack([col(8 + z), col(8 + z), col(4 + z), col(4 + z)], 1)
+        t = a * (b * c)
+        t = t + d * (e * f)
+        t = t + g * (h * i)
+        t = t - a * (e * i)
+        t = t - d * (h * c)
+        t = t - g * (b * f)
+        return t
+
+    for _ in range(inversions):
+        t0 = dsp(1, 2, 3)
+        det = ((t0[:, 0] * s[:, 0] + t0[:, 1] * s[:, 4]) + t0[:, 2] * s[:, 8]) + t0[:, 3] * s[:, 12]
+        inv_det = (np.float32(1.0) / det)[:, None]
+        t1, t2, t3 = dsp(0, 3, 2), dsp(0, 1, 3), dsp(0, 2, 1)
+        s = np.concatenate([t0 * inv_det, t1 * inv_det, t2 * inv_det, t3 * inv_det], 1).astype(np.float32)
+    v = pos
+    zero = np.float32(0.0)
+    out = np.stack([((s[:, r] * v[:, 0] + s[:, 4 + r] * v[:, 1]) + s[:, 8 + r] * v[:, 2]) + s[:, 12 + r] * zero for r in range(3)], 1)
+    return out.astype(np.float32), s
+
+
+def test_heavy_compute_compiles_without_a_gpu():
+    st, log, cubin, chunk = compile_kernel_system(HEAVY_COMPUTE, "heavy_computation_system",
+                                                  [(1, 12, "write", "Position"), (2, 64, "write", "Affine")])
+    assert st == 0 and cubin > 1000 and chunk > 0, log
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1000, 4097])
+def test_heavy_compute_as_generic_system_bit_exact(gpu_ctx, n):
+    """The benchmark's 1 000 entities (Affine = from_angle_x(1.2 rad), Position = unit_x), and a larger set of random
+    well-conditioned matrices: 100 inversions + transform_vector on the device equal the numpy restatement bit for bit,
+    and the matrix really is an inverse pair (A^-1 A = I), which pins the index pattern of det_sub_proc."""
+    ctx = gpu_ctx
+    rng = np.random.default_rng(n)
+    aff = np.zeros((n, 16), np.float32)
+    c, sn = np.float32(np.cos(np.float32(1.2))), np.float32(np.sin(np.float32(1.2)))
+    aff[:] = np.array([1, 0, 0, 0, 0, c, sn, 0, 0, -sn, c, 0, 0, 0, 0, 1], np.float32)  # Matrix4::from_angle_x, column major
+    pos = np.zeros((n, 3), np.float32)
+    pos[:, 0] = 1.0
+    if n != 1000:
+        aff += (rng.standard_normal((n, 16)) * 0.2).astype(np.float32)
+        pos = rng.standard_normal((n, 3)).astype(np.float32)
+    start = aff.copy()
+    want_pos, want_aff = _heavy_compute_numpy(pos, aff)
+    ctx.bind_column(1, 1, pos)
+    ctx.bind_column(1, 2, aff)
+    ctx.upload(1, 1)
+    ctx.upload(1, 2)
+    sid = ctx.create_kernel_system("heavy_compute", HEAVY_COMPUTE, "heavy_computation_system",
+                                   [(1, 12, "write", "Position"), (2, 64, "write", "Affine")])
+    ctx.set_archetypes(sid, [1])
+    ctx.run_system(sid)
+    ctx.download(1, 1)
+    ctx.download(1, 2)
+    assert np.array_equal(aff.view(np.uint32), want_aff.view(np.uint32))
+    assert np.array_equal(pos.view(np.uint32), want_pos.view(np.uint32))
+    # 100 inversions = 50 round trips: back at the start up to rounding; and one inversion really inverts
+    assert np.allclose(aff, start, rtol=0, atol=5e-3)
+    one_step = _heavy_compute_numpy(pos[:64], start[:64], inversions=1)[1]
+    as_matrix = lambda flat: flat.astype(np.float64).reshape(-1, 4, 4).transpose(0, 2, 1)  # column major -> matrices
+    assert np.allclose(as_matrix(one_step) @ as_matrix(start[:64]), np.eye(4), atol=1e-4)

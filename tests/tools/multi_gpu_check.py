@@ -1,6 +1,5 @@
-"""Multi-rank parity check of the index-sharded n-body path (run under torchrun, one rank per GPU -- or, with
-RECS_TEST_SAME_DEVICE=1, every rank on GPU 0: separate processes time-slice one device, which exercises the
-peer-push exchange on a single-GPU box; NCCL refuses two ranks on one device).
+"""Multi-rank parity check of the index-sharded n-body path (run under torchrun, ONE RANK PER GPU: the ranks' kernels
+wait on one another, so they must never share a device).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port P \
         tests/tools/multi_gpu_check.py [bodies] [ticks] [full|own] [p2p|nccl]
@@ -26,8 +25,7 @@ ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 own_rows_only = len(sys.argv) > 3 and sys.argv[3] == "own"  # every rank's host holds (and moves) only its own rows
 exchange = sys.argv[4] if len(sys.argv) > 4 else "p2p"
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-same_device = os.environ.get("RECS_TEST_SAME_DEVICE") == "1"
-device = 0 if same_device else local
+device = local
 dist.init_process_group("gloo")
 ctx = GpuContext(device=device, rank=rank, world_size=world, use_cuda_graph=False)
 if exchange == "nccl":
@@ -90,7 +88,7 @@ if rank == 0:
     for r in results:
         print(r)
     print("MULTI_GPU_CHECK", "OK" if all(r[-1] for r in results) else "FAILED",
-          f"bodies={n} ticks={ticks} world={world} own_rows_only={own_rows_only} exchange={mode} same_device={same_device}")
+          f"bodies={n} ticks={ticks} world={world} own_rows_only={own_rows_only} exchange={mode}")
 ctx.close()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

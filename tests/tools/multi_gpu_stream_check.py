@@ -19,7 +19,7 @@ from recs_b200 import GpuContext, _lib, scenes  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100_003
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 dist.init_process_group("gloo")
-ctx = GpuContext(device=0 if os.environ.get("RECS_TEST_SAME_DEVICE") == "1" else local, rank=rank, world_size=world, use_cuda_graph=False)
+ctx = GpuContext(device=local, rank=rank, world_size=world, use_cuda_graph=False)
 orc = oracle.load_nbody()
 ok = True
 report = {}

@@ -7,4 +7,4 @@ import bench  # noqa: E402
 from recs_b200 import GpuContext  # noqa: E402
 
 with GpuContext(device=0, use_cuda_graph=False) as ctx:
-    print(json.dumps(bench.streaming_extras(ctx)))
+    print(json.dumps(bench.streaming_extras(ctx, bench.measured_traffic())))
