@@ -277,6 +277,14 @@ int32_t recs_app_last_tick_order(recs_app* app, uint32_t* out_order, uint32_t* o
                                  uint32_t* out_count);
 /* Makes the host columns current (downloads every device-dirty column). */
 int32_t recs_app_sync_to_host(recs_app* app);
+/* Application::add_component / remove_component (crates/ecs/src/lib.rs:213-228) between ticks.  The entity moves to
+ * another archetype (crates/ecs/src/archetypes.rs:474-518, 556-651); device-resident columns of both archetypes follow
+ * without a re-upload: one row per column comes down where the device held the newest copy, the source archetype
+ * replays its swap_remove as a row move, the target's resident columns get the pushed row appended.  (Calling
+ * recs_world_add_components directly instead leaves the mirror to the invalidate / re-bind path.) */
+int32_t recs_app_add_components(recs_app* app, recs_entity entity, const uint64_t* component_ids, const void* const* values,
+                                uint32_t n);
+int32_t recs_app_remove_components(recs_app* app, recs_entity entity, const uint64_t* component_ids, uint32_t n);
 /* Tells the app the host columns of an archetype were modified outside of systems. */
 int32_t recs_app_mark_host_dirty(recs_app* app, uint32_t archetype);
 

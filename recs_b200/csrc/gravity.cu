@@ -548,27 +548,36 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
         const uint32_t idx = i - b * rows;
         // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
         float sx = 0.f, sy = 0.f, sz = 0.f;
-        for (uint32_t c = 0; c < n_chunks; ++c) {
-            float4 f = __ldcs(a.frags + static_cast<size_t>(s_slot[c]) * rows + idx);
-            float cx = f.x, cy = f.y, cz = f.z;
-            if (s_ext_lo[c] < s_ext_hi[c]) {
-                // continue the prefix with the tile sums other CTAs stored one by one, in tile order
-                const GravityPhase& P = w.phase[s_phase[c]];
-                const uint32_t units = w.n_iblocks * P.n_vtiles;
-                uint32_t u = s_ext_lo[c];
-                uint32_t g = cta_of(u, w.grid, units);
-                Span sg = span_of(g, w.grid, units);
-                for (; u < s_ext_hi[c]; ++u) {
-                    while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
-                    f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx);
-                    cx += f.x;
-                    cy += f.y;
-                    cz += f.z;
+        // prefix fragments of eight chunks are fetched together (independent loads in flight), then added in chunk order
+        for (uint32_t c0 = 0; c0 < n_chunks; c0 += 8) {
+            float4 pre[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (c0 + u < n_chunks) pre[u] = __ldcs(a.frags + static_cast<size_t>(s_slot[c0 + u]) * rows + idx);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const uint32_t c = c0 + u;
+                if (c >= n_chunks) break;
+                float cx = pre[u].x, cy = pre[u].y, cz = pre[u].z;
+                if (s_ext_lo[c] < s_ext_hi[c]) {
+                    // continue the prefix with the tile sums other CTAs stored one by one, in tile order
+                    const GravityPhase& P = w.phase[s_phase[c]];
+                    const uint32_t units = w.n_iblocks * P.n_vtiles;
+                    uint32_t u_ = s_ext_lo[c];
+                    uint32_t g = cta_of(u_, w.grid, units);
+                    Span sg = span_of(g, w.grid, units);
+                    for (; u_ < s_ext_hi[c]; ++u_) {
+                        while (u_ >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
+                        const float4 f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u_ - sg.begin)) * rows + idx);
+                        cx += f.x;
+                        cy += f.y;
+                        cz += f.z;
+                    }
                 }
+                sx += cx;
+                sy += cy;
+                sz += cz;
             }
-            sx += cx;
-            sy += cy;
-            sz += cz;
         }
         const uint64_t row = a.row_begin + i;
         float* out = a.acc + 3ull * row;

@@ -977,6 +977,79 @@ int32_t recs_app_sync_to_host(recs_app* app) {
     return RECS_OK;
 }
 
+// Application::add_component / remove_component (crates/ecs/src/lib.rs:213-228): the entity moves to another archetype
+// (crates/ecs/src/archetypes.rs:474-518, 556-651: swap_remove from the source, push onto the target).  Resident device
+// columns of both archetypes follow WITHOUT a re-upload: the moved row is fetched from the device where the device holds
+// the newest copy (one row per column), the source archetype replays its swap_remove as a row move, the target's
+// resident columns receive the pushed row as an append.
+namespace {
+int32_t move_entity_between_archetypes(recs_app* app, recs_entity e, const std::function<int32_t()>& host_op) {
+    recs_world* w = app->world;
+    if (!app->gpu) {
+        const int32_t st = host_op();
+        return st == RECS_OK ? RECS_OK : app->fail(st, recs_world_last_error(w));
+    }
+    int32_t st = flush_gpu_chain(app);
+    if (st != RECS_OK) return st;
+    uint32_t src = 0;
+    uint64_t row = 0;
+    if (recs_world_entity_archetype(w, e, &src) != RECS_OK || recs_world_entity_component_index(w, e, &row) != RECS_OK)
+        return app->fail(RECS_ERR_WORLD, recs_world_last_error(w));
+    std::vector<uint64_t> version_before(w->archetypes.size());
+    for (size_t a = 0; a < w->archetypes.size(); ++a) version_before[a] = w->archetypes[a].version;
+    auto is_resident = [&](uint32_t arch, uint64_t comp, uint32_t elem) {
+        auto mit = app->mirror.find(ColKey(arch, comp));
+        return elem != 0 && mit != app->mirror.end() && arch < version_before.size() &&
+               mit->second.bound_version == version_before[arch] && !mit->second.host_dirty;
+    };
+    // the row about to move: make the host copy current where the device copy is the newer one
+    const uint64_t last = w->archetypes[src].entities.size() - 1;
+    std::vector<uint64_t> src_resident;
+    for (auto& col : w->archetypes[src].columns) {
+        if (!is_resident(src, col.first, col.second.elem)) continue;
+        src_resident.push_back(col.first);
+        if (app->mirror[ColKey(src, col.first)].device_dirty)
+            if ((st = recs_gpu_download_rows(app->gpu, src, col.first, row, row + 1)) != RECS_OK) return gpu_fail(app, st);
+    }
+    if ((st = host_op()) != RECS_OK) return app->fail(st, recs_world_last_error(w));
+    uint32_t dst = 0;
+    if (recs_world_entity_archetype(w, e, &dst) != RECS_OK) return app->fail(RECS_ERR_WORLD, recs_world_last_error(w));
+    // source: swap_remove(row) replayed on the device
+    Archetype& sa = w->archetypes[src];
+    if (!src_resident.empty()) {
+        const uint32_t d = (uint32_t)row, s_ = (uint32_t)last;
+        st = recs_gpu_archetype_move_rows(app->gpu, src, src_resident.data(), (uint32_t)src_resident.size(), &d, &s_, row != last ? 1u : 0u,
+                                          sa.entities.size());
+        if (st != RECS_OK) return gpu_fail(app, st);
+        for (uint64_t comp : src_resident) {
+            if ((st = recs_gpu_column_rebind_host(app->gpu, src, comp, sa.columns[comp].data.data())) != RECS_OK) return gpu_fail(app, st);
+            app->mirror[ColKey(src, comp)].bound_version = sa.version;
+        }
+    }
+    // target: the pushed row goes up alone (an archetype created by this move has nothing resident yet)
+    if (dst < version_before.size()) {
+        Archetype& da = w->archetypes[dst];
+        for (auto& col : da.columns) {
+            if (!is_resident(dst, col.first, col.second.elem)) continue;
+            if ((st = recs_gpu_column_append(app->gpu, dst, col.first, col.second.data.data(), da.entities.size())) != RECS_OK)
+                return gpu_fail(app, st);
+            app->mirror[ColKey(dst, col.first)].bound_version = da.version;
+        }
+    }
+    return RECS_OK;
+}
+}  // namespace
+
+int32_t recs_app_add_components(recs_app* app, recs_entity entity, const uint64_t* ids, const void* const* values, uint32_t n) {
+    if (!app || (n && !ids)) return RECS_ERR_INVALID_ARGUMENT;
+    return move_entity_between_archetypes(app, entity, [&] { return recs_world_add_components(app->world, entity, ids, values, n); });
+}
+
+int32_t recs_app_remove_components(recs_app* app, recs_entity entity, const uint64_t* ids, uint32_t n) {
+    if (!app || (n && !ids)) return RECS_ERR_INVALID_ARGUMENT;
+    return move_entity_between_archetypes(app, entity, [&] { return recs_world_remove_components(app->world, entity, ids, n); });
+}
+
 int32_t recs_app_mark_host_dirty(recs_app* app, uint32_t archetype) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
     for (auto& kv : app->mirror)

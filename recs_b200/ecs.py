@@ -115,6 +115,8 @@ ECS_SYMBOLS = {
     "recs_app_last_playback": (C.c_int32, [_a, _u64p, _u64p]),
     "recs_app_last_tick_order": (C.c_int32, [_a, _u32p, _u32p, C.c_uint32, _u32p]),
     "recs_app_sync_to_host": (C.c_int32, [_a]),
+    "recs_app_add_components": (C.c_int32, [_a, Entity, _u64p, _vpp, C.c_uint32]),
+    "recs_app_remove_components": (C.c_int32, [_a, Entity, _u64p, C.c_uint32]),
     "recs_app_mark_host_dirty": (C.c_int32, [_a, C.c_uint32]),
 }
 _lib._bind(ECS_SYMBOLS)
@@ -588,6 +590,15 @@ class Application:
 
     def sync_to_host(self) -> None:
         self._check(lib.recs_app_sync_to_host(self._h), "recs_app_sync_to_host")
+
+    def add_components(self, e: Entity, components: dict) -> None:
+        """Application::add_component between ticks; resident device columns of both archetypes follow the move."""
+        ids, ptrs, keep = self.world._marshal(components)
+        self._check(lib.recs_app_add_components(self._h, e, ids, ptrs, len(components)), "recs_app_add_components")
+
+    def remove_components(self, e: Entity, components: Sequence[int]) -> None:
+        ids = (C.c_uint64 * max(len(components), 1))(*components)
+        self._check(lib.recs_app_remove_components(self._h, e, ids, len(components)), "recs_app_remove_components")
 
     def mark_host_dirty(self, archetype: int) -> None:
         self._check(lib.recs_app_mark_host_dirty(self._h, archetype), "recs_app_mark_host_dirty")
