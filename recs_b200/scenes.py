@@ -49,6 +49,39 @@ def all_heavy_random_cube_with_bodies(body_count: int) -> Scene:
     return replace(EVERYTHING_HEAVY, body_count=body_count)
 
 
+# crates/n-body/src/scenes.rs:29-40
+ONE_HEAVY_BODY = Scene(
+    body_count=1,
+    initial_position_min=-10.0,
+    initial_position_max=10.0,
+    position_offset=(0.0, 0.0, 0.0),
+    minimum_mass=1.900e20,
+    maximum_mass=1.989e20,
+    initial_velocity_min=0.0,
+    initial_velocity_max=1e-30,
+    initial_acceleration_min=0.0,
+    initial_acceleration_max=1e-30,
+)
+
+
+@dataclass(frozen=True)
+class ClusterSpawner:
+    """`struct ClusterSpawner` (crates/n-body/src/scenes.rs:171-177)."""
+
+    cluster_count: int
+    cluster_size: float
+    cluster_distance: float
+    scene: Scene
+
+
+# crates/n-body/src/scenes.rs:179-206
+SMALL_HEAVY_CLUSTERS = ClusterSpawner(cluster_count=4, cluster_size=10.0, cluster_distance=100.0, scene=EVERYTHING_HEAVY)
+SMALL_LIGHT_CLUSTERS = replace(SMALL_HEAVY_CLUSTERS, scene=EVERYTHING_LIGHT)
+HUGE_HEAVY_CLUSTERS = ClusterSpawner(cluster_count=4, cluster_size=100.0, cluster_distance=1000.0,
+                                     scene=replace(EVERYTHING_HEAVY, minimum_mass=100_000.0, maximum_mass=1_000_000.0))
+HUGE_LIGHT_CLUSTERS = replace(HUGE_HEAVY_CLUSTERS, scene=EVERYTHING_LIGHT)
+
+
 def _uniform(u: np.ndarray, low: float, high: float) -> np.ndarray:
     low32, high32 = np.float32(low), np.float32(high)
     return (low32 + u * (high32 - low32)).astype(np.float32)
@@ -62,7 +95,7 @@ def spawn_bodies(scene: Scene, seed: int):
     which `create_planet_entity` (scenes.rs:108-117) inserts as entity id k / component index k.
     """
     n = scene.body_count
-    rng = np.random.default_rng(seed)
+    rng = seed if isinstance(seed, np.random.Generator) else np.random.default_rng(seed)
     u = rng.random((n, 10), dtype=np.float32)
     pos = _uniform(u[:, 0:3], scene.initial_position_min, scene.initial_position_max)
     pos = (pos + np.asarray(scene.position_offset, dtype=np.float32)).astype(np.float32)
@@ -75,6 +108,24 @@ def spawn_bodies(scene: Scene, seed: int):
         np.ascontiguousarray(vel),
         np.ascontiguousarray(acc),
     )
+
+
+def spawn_clusters(spawner: ClusterSpawner, seed: int):
+    """`ClusterSpawner::spawn_bodies` (crates/n-body/src/scenes.rs:208-250): per cluster three draws in [-1, 1) for a
+    direction, normalised; the cluster sits at direction * cluster_distance from the ORIGIN (`previous_cluster_position`
+    is never advanced, :224) and is a random cube of +- cluster_size with body_count / cluster_count bodies.  One seeded
+    generator supplies the draws in the reference's order.  Returns the concatenated columns like `spawn_bodies`."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for _ in range(spawner.cluster_count):
+        d = (np.float32(-1.0) + rng.random(3, dtype=np.float32) * np.float32(2.0)).astype(np.float32)
+        mag = np.float32(np.sqrt(np.float32(np.float32(d[0] * d[0] + d[1] * d[1]) + d[2] * d[2])))
+        d = d * (np.float32(1.0) / mag)  # normalize() = self * (1 / magnitude)
+        centre = tuple(float(x) for x in (d * np.float32(spawner.cluster_distance)))
+        scene = replace(spawner.scene, body_count=spawner.scene.body_count // spawner.cluster_count, position_offset=centre,
+                        initial_position_min=-spawner.cluster_size, initial_position_max=spawner.cluster_size)
+        parts.append(spawn_bodies(scene, rng))
+    return tuple(np.ascontiguousarray(np.concatenate([p[i] for p in parts])) for i in range(4))
 
 
 def rain_drops(n: int, seed: int):

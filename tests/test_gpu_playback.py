@@ -160,6 +160,66 @@ def test_nbody_demo_with_collision_through_application(gpu_ctx, nbody_oracle):
     assert removed_total > 10  # the scene does collide
 
 
+def test_nbody_demo_scenes_two_body_archetypes(gpu_ctx, nbody_oracle):
+    """The demo's own scenes (crates/n-body/examples/n_body_demo.rs:44-45): SMALL_HEAVY_CLUSTERS planets and the
+    SINGLE_HEAVY_BODY_AT_ORIGIN sun, which carries a PointLight and therefore lives in a SECOND body archetype
+    (crates/n-body/src/scenes.rs:146-168).  Every system of the demo matches both archetypes; the nested queries of
+    gravity and collision run over their concatenation in archetype order."""
+    POS, MASS, VEL, ACC, LIGHT = 1, 2, 3, 4, 5
+    from recs_b200 import scenes
+
+    planets = scenes.spawn_clusters(scenes.SMALL_HEAVY_CLUSTERS, 3)
+    sun = scenes.spawn_bodies(scenes.ONE_HEAVY_BODY, 4)
+    app = ecs.Application(gpu=gpu_ctx)
+    w = app.world
+    for c, dt, name in ((POS, F3, "Position"), (MASS, np.float32, "Mass"), (VEL, F3, "Velocity"), (ACC, F3, "Acceleration"),
+                        (LIGHT, F3, "PointLight")):
+        w.register_component(c, dt, name)
+    app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+    app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+    app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+    app.add_gpu_system(_lib.SYS_NBODY_COLLISION, [POS], "collision")
+    n = len(planets[1])
+    w.create_entities(n, {POS: planets[0], MASS: planets[1], VEL: planets[2], ACC: planets[3]})
+    w.create_entity({LIGHT: np.array([0.9, 0.8, 0.1], np.float32), POS: sun[0][0], MASS: sun[1][0], VEL: sun[2][0], ACC: sun[3][0]})
+    assert w.archetype_count() == 3
+    pos = np.concatenate([planets[0], sun[0]])
+    mass = np.concatenate([planets[1], sun[1]])
+    vel = np.concatenate([planets[2], sun[2]])
+    alive = np.ones(n + 1, bool)
+    ticks, removed_total = 5, 0
+    for tick in range(ticks):
+        app.run(1)
+        names = [app.system_names[i] for i in app.last_tick_order()[0]]
+        assert names.index("gravity") < names.index("acceleration") < names.index("movement")
+        p = np.ascontiguousarray(pos[alive])
+        m = np.ascontiguousarray(mass[alive])
+        v = np.ascontiguousarray(vel[alive])
+        a = nbody_oracle.gravity(p, m)
+        hit = _collision_mask(p)
+        nbody_oracle.axpy(v, a, nbody_oracle.dt)
+        nbody_oracle.axpy(p, v, nbody_oracle.dt)
+        pos[alive], vel[alive] = p, v
+        assert app.last_playback() == (0, int(hit.sum())), tick
+        removed_total += int(hit.sum())
+        # entities leave by swap_remove: compare as sets of rows keyed by entity id (planet k = entity k, the sun = entity n)
+        idx = np.flatnonzero(alive)
+        alive[idx[hit]] = False
+    app.sync_to_host()
+    got = {}
+    for arch in (1, 2):
+        ents = w.archetype_entities(arch)
+        cp, cv = w.column(arch, POS), w.column(arch, VEL)
+        for row, (eid, gen) in enumerate(ents):
+            got[eid] = (cp[row].copy(), cv[row].copy())
+    assert sorted(got) == list(np.flatnonzero(alive))
+    gp = np.array([got[k][0] for k in sorted(got)])
+    gv = np.array([got[k][1] for k in sorted(got)])
+    assert rel_err_rows(gp, pos[alive], floor=1.0).max() <= 1e-5
+    assert rel_err_rows(gv, vel[alive], floor=1.0).max() <= 1e-4
+    app.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # the complete rain tick: clouds spawn drops (CPU, Commands::create), drops fall (GPU), drops that
 # reach the ground are removed (GPU decides, host plays back)
