@@ -432,6 +432,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         pp.local_flags = c->xchg.flags(c->cfg.rank);
         pp.done_counter = c->xchg.done_counter();
         pp.error = c->dev_error;
+        pp.wait = pp.signal = 1u;
         return pp;
     };
 
@@ -495,35 +496,34 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     // 3. outer iteration: Read<Position>, Write<Acceleration> over the system's archetypes.  Every archetype's
     //    interaction launch comes before any reduce: the fused tail of one archetype moves bodies that the nested
     //    query of the next one still has to see where they were (gravity reads Position, movement writes it).
-    const uint32_t slots = (uint32_t)(c->sm_count * c->grav_ctas_per_sm[variant]);
-    const uint32_t kGravRows = (uint32_t)gravity_variant(variant).rows();
     struct Outer {
         uint32_t arch;
         Column *p, *acc;
         uint64_t row_begin, row_count;
+        int variant;
+        uint32_t iblock_rows;
         GravityWork work;
-        size_t frag_slot_base;
+        size_t frag_base;  // in float4
         uint32_t self_offset;
     };
     std::vector<Outer> outers;
-    size_t frag_slots = 0;
-    for (uint32_t a : sys.archs) {
+    size_t frag_float4 = 0;
+    auto add_outer = [&](uint32_t arch, Column* p, Column* acc, uint64_t row_begin, uint64_t row_count, int v, uint32_t self_offset) -> int32_t {
         Outer o;
-        o.arch = a;
-        if ((st = need_column(c, a, POS, 12, &o.p)) != RECS_OK) return st;
-        if ((st = need_column(c, a, ACC, 12, &o.acc)) != RECS_OK) return st;
-        if ((st = same_count(c, o.p, o.acc)) != RECS_OK) return st;
-        o.row_begin = sharded ? rb : 0;
-        o.row_count = sharded ? re - rb : o.p->count;
-        if (o.row_count == 0 && !sharded) continue;
-        if (o.row_count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
+        o.arch = arch;
+        o.p = p;
+        o.acc = acc;
+        o.row_begin = row_begin;
+        o.row_count = row_count;
+        o.variant = v;
+        o.iblock_rows = (uint32_t)gravity_variant(v).rows();
+        o.self_offset = self_offset;
         GravityWork& w = o.work;
         memset(&w, 0, sizeof w);
-        w.n_iblocks = (uint32_t)((o.row_count + kGravRows - 1) / kGravRows);
+        w.n_iblocks = (uint32_t)((row_count + o.iblock_rows - 1) / o.iblock_rows);
         w.n_tiles_total = n_tiles;
         w.chunk_tiles = K;
-        if ((uint64_t)w.n_iblocks * n_tiles >= (1ull << 32))
-            return fail(c, RECS_ERR_UNSUPPORTED, "work-unit count overflows 32 bits");
+        if ((uint64_t)w.n_iblocks * n_tiles >= (1ull << 32)) return fail(c, RECS_ERR_UNSUPPORTED, "work-unit count overflows 32 bits");
         if (lay_R > 1) {
             // phase 0: the rank's own slice; phase 1: the other ranks' slices, starting behind the own one
             w.n_phases = 2;
@@ -538,53 +538,77 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         }
         uint64_t max_units = 1;
         for (uint32_t ph = 0; ph < w.n_phases; ++ph) max_units = std::max<uint64_t>(max_units, (uint64_t)w.n_iblocks * w.phase[ph].n_vtiles);
-        w.grid = (uint32_t)std::min<uint64_t>(slots, max_units);
+        w.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * c->grav_ctas_per_sm[v], max_units);
         if (c->grav_grid_forced > 0) w.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->grav_grid_forced, max_units);
-        o.frag_slot_base = frag_slots;
-        frag_slots += gravity_assign_frag_slots(w);
+        o.frag_base = frag_float4;
+        frag_float4 += (size_t)gravity_assign_frag_slots(w) * o.iblock_rows;
+        outers.push_back(o);
+        return RECS_OK;
+    };
+    for (uint32_t a : sys.archs) {
+        Column *p, *acc;
+        if ((st = need_column(c, a, POS, 12, &p)) != RECS_OK) return st;
+        if ((st = need_column(c, a, ACC, 12, &acc)) != RECS_OK) return st;
+        if ((st = same_count(c, p, acc)) != RECS_OK) return st;
+        const uint64_t row_begin = sharded ? rb : 0;
+        const uint64_t row_count = sharded ? re - rb : p->count;
+        if (row_count == 0 && !sharded) continue;
+        if (row_count >= (1ull << 31)) return fail(c, RECS_ERR_UNSUPPORTED, "more than 2^31 rows");
         // mirror index of outer row 0 when this archetype is part of the nested query
-        o.self_offset = 0xffffffffu;
+        uint32_t self_offset = 0xffffffffu;
         uint64_t off = 0;
         for (size_t qi = 0; qi < sys.qarchs.size(); ++qi) {
             if (sys.qarchs[qi] == a) {
-                o.self_offset = (uint32_t)off;
+                self_offset = (uint32_t)off;
                 break;
             }
             off += q[qi].first->count;
         }
-        outers.push_back(o);
-    }
-    if ((st = ensure(c, &c->frags, &c->frags_cap, std::max<size_t>(frag_slots, 1) * kGravRows * sizeof(float4))) != RECS_OK) return st;
-
-    for (Outer& o : outers) {
-        GravityArgs ga;
-        memset(&ga, 0, sizeof ga);
-        ga.posm = reinterpret_cast<const float4*>(posm_now);
-        ga.ipos = (const float*)o.p->dev;
-        ga.frags = c->frags + o.frag_slot_base * kGravRows;
-        ga.row_begin = (uint32_t)o.row_begin;
-        ga.row_count = (uint32_t)o.row_count;
-        ga.eps = c->cfg.nbody_epsilon;
-        ga.self_offset = o.self_offset;
-        ga.work = o.work;
-        ga.variant = variant;
-        ga.tiles_per_rank = slice_tiles;
-        ga.own_rank = (uint32_t)lay_r;
-        ga.error = c->dev_error;
-        if (p2p) {
-            ga.flags = c->xchg.flags(c->cfg.rank);
-            ga.wait_gen = c->xchg.gen;
+        // The big shapes work on i-blocks of 1536 rows; a last, partly filled one would cost as much as a full one
+        // (0.8 % of a rank's tick at 1 M bodies on 8 GPUs).  Its rows go to a second, small launch of the 256-row shape
+        // (same arithmetic, same summation tree: not a bit of the result depends on the split).
+        const uint32_t big = (uint32_t)gravity_variant(variant).rows();
+        const uint64_t rest = row_count % big;
+        const bool split_rest = !c->grav_variant_forced && variant == kGravVariantDefault && rest != 0 && row_count >= 4ull * big &&
+                                gravity_variant(kGravVariantMedium).scaled == scaled;
+        if (split_rest) {
+            if ((st = add_outer(a, p, acc, row_begin, row_count - rest, variant, self_offset)) != RECS_OK) return st;
+            if ((st = add_outer(a, p, acc, row_begin + row_count - rest, rest, kGravVariantMedium, self_offset)) != RECS_OK) return st;
+        } else if ((st = add_outer(a, p, acc, row_begin, row_count, variant, self_offset)) != RECS_OK) {
+            return st;
         }
-        // one launch for all phases, except with the NCCL exchange: own tiles, all-gather, the other tiles
-        const bool split = sharded && !p2p;
-        for (uint32_t l = 0; l < (split ? 2u : 1u); ++l) {
+    }
+    if ((st = ensure(c, &c->frags, &c->frags_cap, std::max<size_t>(frag_float4, 1) * sizeof(float4))) != RECS_OK) return st;
+
+    // one launch for all phases, except with the NCCL exchange: own tiles, all-gather, the other tiles
+    const bool split = sharded && !p2p;
+    for (uint32_t l = 0; l < (split ? 2u : 1u); ++l) {
+        if (split && l == 1) {
+            if ((st = enqueue_gather()) != RECS_OK) return st;
+            RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
+        }
+        for (Outer& o : outers) {
+            if (o.row_count == 0) continue;
+            GravityArgs ga;
+            memset(&ga, 0, sizeof ga);
+            ga.posm = reinterpret_cast<const float4*>(posm_now);
+            ga.ipos = (const float*)o.p->dev;
+            ga.frags = c->frags + o.frag_base;
+            ga.row_begin = (uint32_t)o.row_begin;
+            ga.row_count = (uint32_t)o.row_count;
+            ga.eps = c->cfg.nbody_epsilon;
+            ga.self_offset = o.self_offset;
+            ga.work = o.work;
+            ga.variant = o.variant;
+            ga.tiles_per_rank = slice_tiles;
+            ga.own_rank = (uint32_t)lay_r;
+            ga.error = c->dev_error;
+            if (p2p) {
+                ga.flags = c->xchg.flags(c->cfg.rank);
+                ga.wait_gen = c->xchg.gen;
+            }
             ga.phase_begin = split ? l : 0;
             ga.phase_end = split ? l + 1 : o.work.n_phases;
-            if (split && l == 1) {
-                if ((st = enqueue_gather()) != RECS_OK) return st;
-                RECS_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_gather, 0));
-            }
-            if (o.row_count == 0) continue;
             Timed t(c, T_GRAVITY);
             RECS_CUDA(c, launch_gravity(ga, c->stream));
             c->kernel_launches++;
@@ -592,14 +616,16 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         }
     }
     // the tail may be fused when it cannot disturb a later read of this tick: every interaction launch is enqueued
-    for (Outer& o : outers) {
+    uint32_t push_gen = 0;
+    for (size_t oi = 0; oi < outers.size(); ++oi) {
+        Outer& o = outers[oi];
         GravityReduceArgs ra;
         memset(&ra, 0, sizeof ra);
-        ra.frags = c->frags + o.frag_slot_base * kGravRows;
+        ra.frags = c->frags + o.frag_base;
         ra.acc = (float*)o.acc->dev;
         ra.row_begin = (uint32_t)o.row_begin;
         ra.row_count = (uint32_t)o.row_count;
-        ra.iblock_rows = kGravRows;
+        ra.iblock_rows = o.iblock_rows;
         ra.work = o.work;
         Column *tail_pos = nullptr, *tail_vel = nullptr;
         if (movement) {
@@ -618,8 +644,12 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
                 ra.tail.mass = (const float*)mass_col->dev;
                 ra.tail.posm_offset = o.self_offset;
                 if (p2p) {
-                    // the refreshed rows go to every rank's buffer of the next generation
-                    ra.push = peer_push(++c->xchg.gen);
+                    // the refreshed rows go to every rank's buffer of the next generation: ONE generation per tick, the
+                    // first pushing launch waits for the peers, the last one raises the flag
+                    if (!push_gen) push_gen = ++c->xchg.gen;
+                    ra.push = peer_push(push_gen);
+                    ra.push.wait = oi == 0 ? 1u : 0u;
+                    ra.push.signal = oi + 1 == outers.size() ? 1u : 0u;
                     ra.tail.posm = ra.push.posm[c->cfg.rank];
                 } else {
                     ra.tail.posm = c->posm;
@@ -631,8 +661,8 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             RECS_CUDA(c, launch_gravity_reduce(ra, c->stream));
             c->kernel_launches++;
         }
-        o.acc->version++;
-        if (movement) {
+        if (oi + 1 == outers.size() || outers[oi + 1].acc != o.acc) o.acc->version++;
+        if (movement && (oi + 1 == outers.size() || outers[oi + 1].arch != o.arch)) {
             tail_pos->version++;
             tail_vel->version++;
         }

@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
 // Waits until every rank's previous generation has arrived here (nobody still reads the buffer this push overwrites
 // on a peer: a rank that has pushed generation g-1 has finished every kernel that read generation g-2), CTA-wide.
 __device__ __forceinline__ void push_begin(const PeerPush& p) {
-    if (p.n == 0) return;
+    if (p.n == 0 || !p.wait) return;
     if (threadIdx.x < p.n) ptx::wait_generation(p.local_flags + threadIdx.x, p.gen - 1u, p.error);
     __syncthreads();
 }
@@ -484,6 +484,7 @@ __device__ __forceinline__ void push_begin(const PeerPush& p) {
 __device__ __forceinline__ void push_end(const PeerPush& p) {
     if (p.n == 0) return;
     __threadfence_system();
+    if (!p.signal) return;  // a later launch of the same generation raises the flag (stream order)
     __syncthreads();
     __shared__ uint32_t is_last;
     if (threadIdx.x == 0) is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;

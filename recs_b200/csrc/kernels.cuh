@@ -124,6 +124,8 @@ struct PeerPush {
     const uint32_t* local_flags;         // own flags: all must have reached gen - 1 before the push overwrites
     uint32_t* done_counter;              // local: CTAs of the pushing kernel that have stored their rows
     uint32_t* error;
+    uint32_t wait;                       // this launch is the first of its generation: wait for the peers before storing
+    uint32_t signal;                     // this launch is the last of its generation: raise the flag when all CTAs are done
 };
 inline PeerPush no_peer_push() {
     PeerPush p;

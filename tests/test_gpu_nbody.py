@@ -455,14 +455,14 @@ def test_epsilon_boundary_mask_is_bit_exact(monkeypatch, nbody_oracle, variant):
 @pytest.mark.parametrize("n", [3000, 20000, 70000])
 def test_result_does_not_depend_on_grid_or_rank_split(monkeypatch, n):
     """Tile sums are added in a fixed tree (chunks of consecutive tiles, then chunks in ascending order; kernels.cuh),
-    so neither the number of persistent CTAs the (i-block, tile) units are dealt to nor the two-phase walk of a rank of a
-    sharded run (own slice first, then the other ranks' slices in rotated order, mirror padded to R equal slices) may
-    change a bit of any row."""
+    so neither the number of persistent CTAs the (i-block, tile) units are dealt to, nor the two-phase walk of a rank of a
+    sharded run (own slice first, then the other ranks' slices in rotated order, mirror padded to R equal slices), nor
+    which of the i-packed kernel shapes computes a row may change a bit of any row."""
     from recs_b200 import GpuContext
     from recs_b200.nbody import NBodyGpuApp
 
     def run(env):
-        for key in ("RECS_GPU_GRAVITY_GRID", "RECS_GPU_GRAVITY_EMULATE_RANK"):
+        for key in ("RECS_GPU_GRAVITY_GRID", "RECS_GPU_GRAVITY_EMULATE_RANK", "RECS_GPU_GRAVITY_VARIANT"):
             monkeypatch.delenv(key, raising=False)
         for key, value in env.items():
             monkeypatch.setenv(key, value)
@@ -480,7 +480,10 @@ def test_result_does_not_depend_on_grid_or_rank_split(monkeypatch, n):
                 {"RECS_GPU_GRAVITY_GRID": "333"}, {"RECS_GPU_GRAVITY_EMULATE_RANK": "2,0"},
                 {"RECS_GPU_GRAVITY_EMULATE_RANK": "2,1"}, {"RECS_GPU_GRAVITY_EMULATE_RANK": "4,2"},
                 {"RECS_GPU_GRAVITY_EMULATE_RANK": "8,7", "RECS_GPU_GRAVITY_GRID": "61"},
-                {"RECS_GPU_GRAVITY_EMULATE_RANK": "3,1"}):
+                {"RECS_GPU_GRAVITY_EMULATE_RANK": "3,1"},
+                # the default launches the rows of a partly filled last 1536-row i-block with the 256-row shape; a forced
+                # shape does not split: the big shape alone, the small shape alone -- same arithmetic, same tree
+                {"RECS_GPU_GRAVITY_VARIANT": "0"}, {"RECS_GPU_GRAVITY_VARIANT": "3", "RECS_GPU_GRAVITY_GRID": "97"}):
         got = run(env)
         for a, b, what in zip(got, base, ("pos", "vel", "acc")):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{what} differs with {env}"
