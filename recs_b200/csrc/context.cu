@@ -564,19 +564,11 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             }
             off += q[qi].first->count;
         }
-        // The big shapes work on i-blocks of 1536 rows; a last, partly filled one would cost as much as a full one
-        // (0.8 % of a rank's tick at 1 M bodies on 8 GPUs).  Its rows go to a second, small launch of the 256-row shape
-        // (same arithmetic, same summation tree: not a bit of the result depends on the split).
-        const uint32_t big = (uint32_t)gravity_variant(variant).rows();
-        const uint64_t rest = row_count % big;
-        const bool split_rest = !c->grav_variant_forced && variant == kGravVariantDefault && rest != 0 && row_count >= 4ull * big &&
-                                gravity_variant(kGravVariantMedium).scaled == scaled;
-        if (split_rest) {
-            if ((st = add_outer(a, p, acc, row_begin, row_count - rest, variant, self_offset)) != RECS_OK) return st;
-            if ((st = add_outer(a, p, acc, row_begin + row_count - rest, rest, kGravVariantMedium, self_offset)) != RECS_OK) return st;
-        } else if ((st = add_outer(a, p, acc, row_begin, row_count, variant, self_offset)) != RECS_OK) {
-            return st;
-        }
+        // (A partly filled last i-block costs as much as a full one: 0.8 % of a rank's tick at 1 M bodies on 8 GPUs.  Giving
+        // its rows to a second, small launch was measured and dropped: the spans of so few rows are much shorter than a
+        // chunk of the summation tree, nearly every tile sum becomes its own fragment and the reduce of those rows costs more
+        // than the launch saves -- profiles/r02_remainder_launch.txt.)
+        if ((st = add_outer(a, p, acc, row_begin, row_count, variant, self_offset)) != RECS_OK) return st;
     }
     if ((st = ensure(c, &c->frags, &c->frags_cap, std::max<size_t>(frag_float4, 1) * sizeof(float4))) != RECS_OK) return st;
 
