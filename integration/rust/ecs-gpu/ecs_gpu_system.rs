@@ -299,6 +299,16 @@ impl GpuComponent {
             type_name: std::any::type_name::<T>(),
         }
     }
+
+    /// Placeholder for a `Commands` parameter of a generic system (RECS_KPARAM_COMMANDS carries no component; its
+    /// element size / type name describe the record `commands.create(record)` takes, or 0 / "" for remove() only).
+    pub fn commands() -> Self {
+        Self {
+            id: 0,
+            type_id: TypeId::of::<()>(),
+            type_name: "Commands",
+        }
+    }
 }
 
 /// A system whose body runs on the GPU: replaces e.g. `n_body::gravity` (crates/n-body/src/lib.rs:104-135) one for one.

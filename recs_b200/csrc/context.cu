@@ -415,7 +415,10 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             Column* p = find_column(c, a, POS);
             if (p) max_rows = std::max<uint64_t>(max_rows, sharded ? re - rb : p->count);
         }
-        if (max_rows <= kGravSmallRows) variant = kGravVariantSmall;
+        // The j-packed small shape has its own arithmetic (two bodies j per lane pair, exact mask on every pair), the
+        // i-packed shapes share theirs: the small shape is chosen by the size of the nested query alone, so that a rank of
+        // a sharded run uses the arithmetic the single-GPU run uses and results stay bit-identical across rank counts.
+        if (total_j <= kGravSmallRows) variant = kGravVariantSmall;
         else if (max_rows <= kGravMediumRows) variant = kGravVariantMedium;
     }
     const bool scaled = gravity_variant(variant).scaled;

@@ -545,6 +545,7 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
     }
     __syncthreads();
     if (a.tail.posm) push_begin(a.push);
+    float mx = 0.f, my = 0.f, mz = 0.f, mg = 0.f;  // this row's refreshed mirror entry
     if (valid) {
         const uint32_t idx = i - b * rows;
         // `.sum()` of Vector3 starts from zero (crates/n-body/src/lib.rs:129-133).
@@ -601,12 +602,41 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
             v[0] = __fadd_rn(vx, __fmul_rn(sx, a.tail.dt));
             v[1] = __fadd_rn(vy, __fmul_rn(sy, a.tail.dt));
             v[2] = __fadd_rn(vz, __fmul_rn(sz, a.tail.dt));
-            if (a.tail.posm)
-                store_posm(a.push, a.tail.posm, a.tail.posm_offset + row, px * a.tail.pscale, py * a.tail.pscale,
-                           pz * a.tail.pscale, __fmul_rn(a.tail.g, a.tail.mass[row]));
+            if (a.tail.posm) {
+                mx = px * a.tail.pscale;
+                my = py * a.tail.pscale;
+                mz = pz * a.tail.pscale;
+                mg = __fmul_rn(a.tail.g, a.tail.mass[row]);
+            }
         }
     }
-    if (a.tail.posm) push_end(a.push);
+    if (a.tail.posm) {
+        // the refreshed mirror entry.  Two neighbouring rows share one 32-byte pair {x0 x1 y0 y1 | z0 z1 gm0 gm1}: lanes
+        // swap halves so that every lane stores ONE aligned float4 per destination (the even body the first half, the odd
+        // body the second) instead of four scattered 4-byte words -- what matters when the destinations are seven peers
+        // across NVLink.
+        const uint64_t J = a.tail.posm_offset + a.row_begin + i;
+        const bool odd = J & 1;
+        const float ox = __shfl_xor_sync(0xffffffffu, mx, 1), oy = __shfl_xor_sync(0xffffffffu, my, 1);
+        const float oz = __shfl_xor_sync(0xffffffffu, mz, 1), og = __shfl_xor_sync(0xffffffffu, mg, 1);
+        const bool partner_valid = __shfl_xor_sync(0xffffffffu, valid ? 1 : 0, 1) != 0;
+        // the partner lane holds body J ^ 1 iff lane parity == body parity
+        const bool paired = partner_valid && ((threadIdx.x & 1) != 0) == odd;
+        if (valid) {
+            if (paired) {
+                const float4 half = odd ? make_float4(oz, mz, og, mg) : make_float4(mx, ox, my, oy);
+                const size_t o = (J >> 1) * 8 + (odd ? 4 : 0);
+                if (a.push.n == 0) {
+                    *reinterpret_cast<float4*>(a.tail.posm + o) = half;
+                } else {
+                    for (uint32_t q = 0; q < a.push.n; ++q) *reinterpret_cast<float4*>(a.push.posm[q] + o) = half;
+                }
+            } else {
+                store_posm(a.push, a.tail.posm, J, mx, my, mz, mg);
+            }
+        }
+        push_end(a.push);
+    }
 }
 
 __global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict__ pos,
