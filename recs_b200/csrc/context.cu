@@ -934,7 +934,8 @@ int32_t run_kernel_system(recs_gpu_ctx* c, System& sys) {
         ctas = k.n_items;
         cap = (uint64_t)c->sm_count * per_sm;
     } else {
-        ctas = (k.n_items + k.plan.threads - 1) / k.plan.threads;
+        const uint64_t per_cta = k.is_pair ? k.plan.chunk : k.plan.threads;  // pair kernels: several outer entities per thread
+        ctas = (k.n_items + per_cta - 1) / per_cta;
         cap = (uint64_t)c->sm_count * (2048 / k.plan.threads);
     }
     const unsigned grid = (unsigned)std::min<uint64_t>(ctas, cap);

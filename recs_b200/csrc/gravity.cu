@@ -69,7 +69,7 @@ __host__ __device__ inline uint32_t cta_of(uint32_t u, uint32_t grid, uint32_t u
 template <bool MASKED>
 __device__ __forceinline__ void pair_interaction(const f32x2 xj, const f32x2 yj, const f32x2 zj, const f32x2 gm,
                                                  const float nx, const float ny, const float nz, const float eps,
-                                                 f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {
+                                                 f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {  // (both: this row)
     // (x_j0, x_j1) - x_i: written as an add of the negated scalar so ptxas can use FADD2's
     // broadcast-scalar operand form (`-R.F32`): one register read instead of a materialised pair
     const f32x2 dx = ptx::add2(xj, ptx::pack(-nx, -nx));
@@ -108,7 +108,7 @@ __device__ __forceinline__ void pair_interaction(const f32x2 xj, const f32x2 yj,
 template <int RI, int UNROLL, bool MASKED>
 __device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const float (&nxi)[RI], const float (&nyi)[RI],
                                           const float (&nzi)[RI], const float eps, f32x2 (&ax)[RI], f32x2 (&ay)[RI],
-                                          f32x2 (&az)[RI], float& dmin_a, float& dmin_b) {
+                                          f32x2 (&az)[RI], float (&dmin)[RI]) {
 #pragma unroll UNROLL
     for (int p = 0; p < kGravTile / 2; ++p) {
         const float4 lo = t[2 * p];      // x0 x1 y0 y1
@@ -119,7 +119,7 @@ __device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const fl
         const f32x2 gm = ptx::pack(hi.z, hi.w);
 #pragma unroll
         for (int r = 0; r < RI; ++r)
-            pair_interaction<MASKED>(xj, yj, zj, gm, nxi[r], nyi[r], nzi[r], eps, ax[r], ay[r], az[r], dmin_a, dmin_b);
+            pair_interaction<MASKED>(xj, yj, zj, gm, nxi[r], nyi[r], nzi[r], eps, ax[r], ay[r], az[r], dmin[r], dmin[r]);
     }
 }
 
@@ -131,7 +131,7 @@ __device__ __forceinline__ void tile_loop(const float4* __restrict__ t, const fl
 template <bool MASKED, int ABL = 0>
 __device__ __forceinline__ void ipair_interaction(const float xj, const float yj, const float zj, const float gm,
                                                   const f32x2 nx, const f32x2 ny, const f32x2 nz, const float eps,
-                                                  f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {
+                                                  f32x2& ax, f32x2& ay, f32x2& az, float& dmin_a, float& dmin_b) {  // (both: this row)
     const f32x2 dx = ptx::add2(nx, ptx::pack(xj, xj));
     const f32x2 dy = ptx::add2(ny, ptx::pack(yj, yj));
     const f32x2 dz = ptx::add2(nz, ptx::pack(zj, zj));
@@ -180,7 +180,7 @@ __device__ __forceinline__ void ipair_interaction(const float xj, const float yj
 template <int RP, int UNROLL, bool MASKED, int ABL = 0, bool UNSCALE = false>
 __device__ __forceinline__ void itile_loop(const float4* __restrict__ t, const f32x2 (&nx)[RP], const f32x2 (&ny)[RP],
                                            const f32x2 (&nz)[RP], const float eps, f32x2 (&ax)[RP], f32x2 (&ay)[RP],
-                                           f32x2 (&az)[RP], float& dmin_a, float& dmin_b) {
+                                           f32x2 (&az)[RP], float (&dmin)[2 * RP]) {
 #pragma unroll UNROLL
     for (int p = 0; p < kGravTile / 2; ++p) {
         float4 lo = t[2 * p];      // x0 x1 y0 y1
@@ -191,12 +191,12 @@ __device__ __forceinline__ void itile_loop(const float4* __restrict__ t, const f
         }
 #pragma unroll
         for (int q = 0; q < RP; ++q)
-            ipair_interaction<MASKED, ABL>(lo.x, lo.z, hi.x, hi.z, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin_a,
-                                      dmin_b);
+            ipair_interaction<MASKED, ABL>(lo.x, lo.z, hi.x, hi.z, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin[2 * q],
+                                           dmin[2 * q + 1]);
 #pragma unroll
         for (int q = 0; q < RP; ++q)
-            ipair_interaction<MASKED, ABL>(lo.y, lo.w, hi.y, hi.w, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin_a,
-                                      dmin_b);
+            ipair_interaction<MASKED, ABL>(lo.y, lo.w, hi.y, hi.w, nx[q], ny[q], nz[q], eps, ax[q], ay[q], az[q], dmin[2 * q],
+                                           dmin[2 * q + 1]);
     }
 }
 
@@ -310,7 +310,10 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
         // archetype is part of the nested query and the tile belongs to this phase: it goes straight to the exact path
         auto own_tile_of = [&](uint32_t iblock) -> uint32_t {
             if (a.self_offset == 0xffffffffu) return 0xffffffffu;
-            const uint32_t tile = (a.self_offset + a.row_begin + iblock * kGravRows + warp * (32u * RI)) / kGravTile;
+            const uint32_t first = a.self_offset + a.row_begin + iblock * kGravRows + warp * (32u * RI);
+            const uint32_t tile = first / kGravTile;
+            if ((first + 32u * RI - 1) / kGravTile != tile) return 0xffffffffu;  // the warp's rows straddle two tiles: no hint,
+                                                                                 // each row's own tile is found through its poison
             const uint32_t ov = tile >= P.tile_offset ? tile - P.tile_offset : tile + w.n_tiles_total - P.tile_offset;
             return ov < P.n_vtiles ? ov : 0xffffffffu;
         };
@@ -328,8 +331,15 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             ptx::mbar_wait(&full_bar[stage], phase);
             const float4* t = tiles + stage * kGravTile;
 
+            // Which rows take this tile's EXACT result is decided row by row, from data alone: a row's own tile, and any
+            // tile whose fast sum for that row is poisoned (or, for the min-d2 detectors, holds a pair at or below
+            // epsilon).  Not "the thread redoes all its rows": which rows share a thread depends on the kernel shape and
+            // on where a rank's rows begin, and results must not (kernels.cuh).
             float sx[kGravRowsPerThread], sy[kGravRowsPerThread], sz[kGravRowsPerThread];  // this tile's sums per row
-            float dmin_a = 3.0e38f, dmin_b = 3.0e38f;
+            float dmin[kGravRowsPerThread];
+            bool exact[kGravRowsPerThread];
+#pragma unroll
+            for (int r = 0; r < kGravRowsPerThread; ++r) dmin[r] = 3.0e38f, exact[r] = false;
             if constexpr (IPACK) {
                 // lanes = rows (2q, 2q+1) of this thread
                 constexpr int RP = RI / 2;
@@ -341,89 +351,111 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                     nz[q] = ptx::pack(-nzi[2 * q], -nzi[2 * q + 1]);
                     ax[q] = ay[q] = az[q] = 0ull;
                 }
-                if constexpr ((ABL & kAblOverflow) != 0) {
-                    // Range-shifted fast path: tile and row positions are stored times 2^-32 (an exact scaling; G*m is
-                    // stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
-                    // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the tile sums, which come out times 2^64.
-                    // No per-pair detector instruction at all: one finiteness test per tile, then the exact masked
-                    // path on true-scale values.  A tile in which G*m/d^3 of some pair reaches 2^32 s^-2 (a density
-                    // above 1e19 kg/m^3) or whose sums reach 2^64 m/s^2 takes the exact path as well.
+                constexpr bool kShifted = (ABL & kAblOverflow) != 0;
+                bool any_exact = false;
+                if constexpr (kShifted || DETECT) {
+                    // Range-shifted fast path (kShifted): tile and row positions are stored times 2^-32 (an exact scaling;
+                    // G*m is stored as is), so r^-3 of any pair with d2 <= 2^-21.3 -- a superset of the reference's
+                    // `d2 <= f32::EPSILON` -- overflows to +inf and poisons the row's tile sums, which come out times 2^64.
+                    // No per-pair detector instruction at all: one finiteness test per row and tile, then the exact masked
+                    // path on true-scale values.  A row for which G*m/d^3 of some pair of the tile reaches 2^32 s^-2 (a
+                    // density above 1e19 kg/m^3) or whose sums reach 2^64 m/s^2 takes the exact path as well.
                     // The tile that holds the warp's own bodies is known in advance and skips the doomed fast pass.
-                    const bool own_tile = v == own_v;
-                    auto exact_tile = [&]() {
-                        f32x2 ux[RP], uy[RP], uz[RP];
-                        const f32x2 un = ptx::pack(kGravPosUnscale, kGravPosUnscale);
+                    const bool own_tile = kShifted && v == own_v;
+                    if (!own_tile) {
+                        itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin);
+#pragma unroll
+                        for (int q = 0; q < RP; ++q) {
+                            if (kShifted) {
+                                const f32x2 sc = ptx::pack(kGravOutScale, kGravOutScale);
+                                ax[q] = ptx::mul2(ax[q], sc);
+                                ay[q] = ptx::mul2(ay[q], sc);
+                                az[q] = ptx::mul2(az[q], sc);
+                            }
+                            ptx::unpack(ax[q], sx[2 * q], sx[2 * q + 1]);
+                            ptx::unpack(ay[q], sy[2 * q], sy[2 * q + 1]);
+                            ptx::unpack(az[q], sz[2 * q], sz[2 * q + 1]);
+                        }
+#pragma unroll
+                        for (int r = 0; r < RI; ++r) {
+                            // kShifted: inf or NaN in the row's sums; else: the detector sees the FUSED d2, the mask the
+                            // reference's unfused one (an ulp or two apart), so everything within 1 + 1e-6 of epsilon goes too
+                            exact[r] = kShifted ? !(fabsf(sx[r]) + fabsf(sy[r]) + fabsf(sz[r]) < 3.0e38f) : dmin[r] <= eps * 1.000001f;
+                            any_exact = any_exact || exact[r];
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < RI; ++r) exact[r] = true;
+                        any_exact = true;
+                    }
+                    if (any_exact) {
+                        f32x2 ux[RP], uy[RP], uz[RP], ex[RP], ey[RP], ez[RP];
+                        const f32x2 un = ptx::pack(kShifted ? kGravPosUnscale : 1.f, kShifted ? kGravPosUnscale : 1.f);
 #pragma unroll
                         for (int q = 0; q < RP; ++q) {
                             ux[q] = ptx::mul2(nx[q], un);
                             uy[q] = ptx::mul2(ny[q], un);
                             uz[q] = ptx::mul2(nz[q], un);
-                            ax[q] = ay[q] = az[q] = 0ull;
+                            ex[q] = ey[q] = ez[q] = 0ull;
                         }
-                        itile_loop<RP, 2, true, 0, true>(t, ux, uy, uz, eps, ax, ay, az, dmin_a, dmin_b);
-                    };
-                    if (own_tile) {
-                        exact_tile();
-                    } else {
-                        itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-                        float chk = 0.f;
+                        itile_loop<RP, 2, true, 0, kShifted>(t, ux, uy, uz, eps, ex, ey, ez, dmin);
 #pragma unroll
                         for (int q = 0; q < RP; ++q) {
-                            const f32x2 sc = ptx::pack(kGravOutScale, kGravOutScale);
-                            ax[q] = ptx::mul2(ax[q], sc);
-                            ay[q] = ptx::mul2(ay[q], sc);
-                            az[q] = ptx::mul2(az[q], sc);
-                            float u0, u1, v0, v1, w0, w1;
-                            ptx::unpack(ax[q], u0, u1);
-                            ptx::unpack(ay[q], v0, v1);
-                            ptx::unpack(az[q], w0, w1);
-                            chk += fabsf(u0) + fabsf(u1) + fabsf(v0) + fabsf(v1) + fabsf(w0) + fabsf(w1);
+                            float x0, x1, y0, y1, z0, z1;
+                            ptx::unpack(ex[q], x0, x1);
+                            ptx::unpack(ey[q], y0, y1);
+                            ptx::unpack(ez[q], z0, z1);
+                            if (exact[2 * q]) sx[2 * q] = x0, sy[2 * q] = y0, sz[2 * q] = z0;
+                            if (exact[2 * q + 1]) sx[2 * q + 1] = x1, sy[2 * q + 1] = y1, sz[2 * q + 1] = z1;
                         }
-                        if (!(chk < 3.0e38f)) exact_tile();  // inf or NaN somewhere
-                    }
-                } else if (DETECT) {
-                    itile_loop<RP, UNROLL, false, ABL>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-                    // the detector sees the FUSED d2, the mask the reference's unfused one: they differ by an ulp or two,
-                    // so everything within a factor 1 + 2^-20 of epsilon is sent to the exact path as well
-                    if (fminf(dmin_a, dmin_b) <= eps * 1.000001f) {
-#pragma unroll
-                        for (int q = 0; q < RP; ++q) ax[q] = ay[q] = az[q] = 0ull;
-                        itile_loop<RP, 1, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
                     }
                 } else {
-                    itile_loop<RP, UNROLL, true>(t, nx, ny, nz, eps, ax, ay, az, dmin_a, dmin_b);
-                }
+                    itile_loop<RP, UNROLL, true>(t, nx, ny, nz, eps, ax, ay, az, dmin);
 #pragma unroll
-                for (int q = 0; q < RP; ++q) {
-                    ptx::unpack(ax[q], sx[2 * q], sx[2 * q + 1]);
-                    ptx::unpack(ay[q], sy[2 * q], sy[2 * q + 1]);
-                    ptx::unpack(az[q], sz[2 * q], sz[2 * q + 1]);
+                    for (int q = 0; q < RP; ++q) {
+                        ptx::unpack(ax[q], sx[2 * q], sx[2 * q + 1]);
+                        ptx::unpack(ay[q], sy[2 * q], sy[2 * q + 1]);
+                        ptx::unpack(az[q], sz[2 * q], sz[2 * q + 1]);
+                    }
                 }
             } else {
                 f32x2 ax[kGravRowsPerThread], ay[kGravRowsPerThread], az[kGravRowsPerThread];
 #pragma unroll
                 for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
-                if (DETECT) {
-                    tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
-                    if (fminf(dmin_a, dmin_b) <= eps * 1.000001f) {
-                        // some pair of this thread in this tile is at or below epsilon (its own body, or a
-                        // coincident one): the unmasked sums are garbage (inf/NaN) -- redo the tile exactly.
+                auto fold = [&](f32x2 (&bx)[kGravRowsPerThread], f32x2 (&by)[kGravRowsPerThread], f32x2 (&bz)[kGravRowsPerThread], bool only_exact) {
 #pragma unroll
-                        for (int r = 0; r < kGravRowsPerThread; ++r) ax[r] = ay[r] = az[r] = 0ull;
-                        tile_loop<RI, 1, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
+                    for (int r = 0; r < kGravRowsPerThread; ++r) {
+                        if (only_exact && !exact[r]) continue;
+                        float x0, x1, y0, y1, z0, z1;
+                        ptx::unpack(bx[r], x0, x1);
+                        ptx::unpack(by[r], y0, y1);
+                        ptx::unpack(bz[r], z0, z1);
+                        sx[r] = x0 + x1;  // even + odd bodies of the tile
+                        sy[r] = y0 + y1;
+                        sz[r] = z0 + z1;
+                    }
+                };
+                if (DETECT) {
+                    tile_loop<RI, UNROLL, false>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin);
+                    fold(ax, ay, az, false);
+                    bool any_exact = false;
+#pragma unroll
+                    for (int r = 0; r < kGravRowsPerThread; ++r) {
+                        exact[r] = dmin[r] <= eps * 1.000001f;
+                        any_exact = any_exact || exact[r];
+                    }
+                    if (any_exact) {
+                        // some pair of a row in this tile is at or below epsilon (its own body, or a coincident one): the
+                        // unmasked sums of that row are garbage (inf/NaN) -- that row takes the exact result.
+                        f32x2 ex[kGravRowsPerThread], ey[kGravRowsPerThread], ez[kGravRowsPerThread];
+#pragma unroll
+                        for (int r = 0; r < kGravRowsPerThread; ++r) ex[r] = ey[r] = ez[r] = 0ull;
+                        tile_loop<RI, 1, true>(t, nxi, nyi, nzi, eps, ex, ey, ez, dmin);
+                        fold(ex, ey, ez, true);
                     }
                 } else {
-                    tile_loop<RI, UNROLL, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin_a, dmin_b);
-                }
-#pragma unroll
-                for (int r = 0; r < kGravRowsPerThread; ++r) {
-                    float x0, x1, y0, y1, z0, z1;
-                    ptx::unpack(ax[r], x0, x1);
-                    ptx::unpack(ay[r], y0, y1);
-                    ptx::unpack(az[r], z0, z1);
-                    sx[r] = x0 + x1;  // even + odd bodies of the tile
-                    sy[r] = y0 + y1;
-                    sz[r] = z0 + z1;
+                    tile_loop<RI, UNROLL, true>(t, nxi, nyi, nzi, eps, ax, ay, az, dmin);
+                    fold(ax, ay, az, false);
                 }
             }
 

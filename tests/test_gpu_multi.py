@@ -30,6 +30,7 @@ def _torchrun(world, script, args, env=None, timeout=420):
 
 
 @pytest.mark.parametrize("bodies,ticks,mode", [(10000, 1, "full"), (5000, 4, "full"), (300, 2, "full"), (7000, 3, "own"),
+                                               (30000, 2, "own"),   # shards below the small-shape limit of a single GPU
                                                (70000, 2, "own")])
 @pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 def test_sharded_ticks_match_oracle(bodies, ticks, mode, exchange):

@@ -40,6 +40,11 @@ mode = ctx.exchange_mode()
 assert mode == ("nccl-allgather" if exchange == "nccl" else "peer-push"), mode
 rb, re = ctx.shard_rows(n)
 pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 5)
+if n >= 64:  # coincident twins and sub-epsilon neighbours spread over the shards: which rows take a tile's exact result
+    k = n // 16  # must not depend on the rank count either
+    pos[k : 2 * k] = pos[:k]
+    pos[2 * k : 3 * k] = pos[:k] + np.array([1e-4, 0, 0], np.float32)
+    pos = np.ascontiguousarray(pos)
 start = [a.copy() for a in (pos, mass, vel, acc)]
 if own_rows_only:  # poison what this rank does not own: it must never be read
     for a in (pos, mass, vel, acc):
