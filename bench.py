@@ -646,7 +646,10 @@ def run_gpu_arm(args) -> None:
 
     comm = None
     if world > 1:
+        kernel_by_rank = [None] * world
+        dist.all_gather_object(kernel_by_rank, float(roofline["kernel_ms_per_step"]))
         comm = {
+            "kernel_ms_per_step_by_rank": [round(x, 3) for x in kernel_by_rank],
             "exchange": exchange,
             "bytes_per_rank_per_step": int((re - rb) * 16 * (world if exchange == "peer-push" else 1)),
             "bytes_total_per_step": int(n * 16 * (world if exchange == "peer-push" else 1)),
@@ -656,9 +659,10 @@ def run_gpu_arm(args) -> None:
             comm["how"] = ("the integration tail stores every refreshed {position, G*m} entry into all ranks' next mirror buffer "
                            "(P2P stores over NVLink) and raises a generation flag; the next tick is ONE persistent launch that starts on "
                            "its own tiles and acquires a peer's flag before the first tile of that peer's slice")
-            comm["residual"] = ("time a rank's producer warp spends waiting for the slowest peer's flag (inside the interaction kernel), "
-                                "plus the P2P stores of the tail: ms_per_step - kernel time of the fastest rank")
-            comm["residual_ms_per_step"] = total_ms / steps - min(per_rank_ms) if per_rank_ms else None
+            comm["residual"] = ("ms_per_step (slowest rank) minus the mean interaction-kernel time: the reduce + integration tail with its "
+                                "P2P stores, and the skew between ranks (a rank's producer warp waits inside the kernel for the slowest "
+                                "peer's flag, which the kernel time of the waiting rank already contains)")
+            comm["residual_ms_per_step"] = total_ms / steps - float(np.mean(kernel_by_rank))
         else:
             comm["how"] = "ncclAllGather of the mirror, in place, between the own-tile launch and the launch over the other ranks' tiles"
             comm["gather_ms_per_step_incl_peer_wait"] = t["gather_ms"] / k_steps
