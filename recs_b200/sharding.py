@@ -1,13 +1,14 @@
 """Index sharding of the body archetype over R ranks (one process per GPU).
 
-Rank r owns rows [r*S, min((r+1)*S, N)) where S = ceil(N / (256*R)) * 256 (slices are whole j-tiles so
-every rank's slice of the pair-interleaved position mirror is one contiguous, equally sized block:
-the NCCL all-gather needs equal counts and the local-tile launch of gravity needs tile-aligned
-slices).  The partition itself is computed by librecs_gpu.so (recs_gpu_shard_plan); this module only
-wraps it and describes the per-tick protocol for host-side tests:
+Rank r owns rows [r*S, min((r+1)*S, N)).  S is a whole number of CHUNKS of the gravity kernel's summation tree (a chunk
+= K = ceil(tiles / 32) tiles of 256 bodies, a function of N alone): every rank's slice of the pair-interleaved
+position mirror is one contiguous, equally sized run of whole chunks, so a rank's own tiles and the other ranks' tiles
+are two runs of whole chunks and a row's result does not depend on the rank count (recs_b200/csrc/kernels.cuh).  The
+partition is computed by librecs_gpu.so (recs_gpu_shard_plan); this module only wraps it for host-side tests:
 
     tick:  gravity(own rows x all bodies)  ->  movement(own rows)  ->  acceleration(own rows)
-           -> all-gather of the new positions (own slice -> everyone)      [before the next gravity]
+           -> the refreshed positions of the own rows reach every rank (peer push by the integration tail, or the
+              NCCL all-gather) before the next gravity reads them
 """
 from __future__ import annotations
 
