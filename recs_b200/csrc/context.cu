@@ -140,6 +140,7 @@ struct recs_gpu_ctx {
     float4* frags = nullptr;
     size_t frags_cap = 0;
     int grav_grid_forced = 0;           // RECS_GPU_GRAVITY_GRID: test knob (results must not depend on it)
+    bool grav_no_heavy = false;         // RECS_GPU_GRAVITY_NO_LAST_SPLIT: A/B and test knob (ditto)
     int emulate_ranks = 0, emulate_rank = 0;  // RECS_GPU_GRAVITY_EMULATE_RANK="R,r": rank r's phase split on one GPU (test knob)
 
     // sharded runs, peer-pushed mirror: one allocation [mirror buffer 0 | mirror buffer 1 | flags | done counter],
@@ -527,20 +528,39 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         w.n_tiles_total = n_tiles;
         w.chunk_tiles = K;
         if ((uint64_t)w.n_iblocks * n_tiles >= (1ull << 32)) return fail(c, RECS_ERR_UNSUPPORTED, "work-unit count overflows 32 bits");
+        // tile ranges: the rank's own slice first, then the other ranks' slices starting behind it (one range on one GPU)
+        struct TileRange {
+            uint32_t n_vtiles, tile_offset;
+        } ranges[2];
+        uint32_t n_ranges = 1;
         if (lay_R > 1) {
-            // phase 0: the rank's own slice; phase 1: the other ranks' slices, starting behind the own one
-            w.n_phases = 2;
-            w.phase[0].n_vtiles = slice_tiles;
-            w.phase[0].tile_offset = slice_tiles * (uint32_t)lay_r;
-            w.phase[1].n_vtiles = n_tiles - slice_tiles;
-            w.phase[1].tile_offset = (w.phase[0].tile_offset + slice_tiles) % n_tiles;
+            n_ranges = 2;
+            ranges[0] = {slice_tiles, slice_tiles * (uint32_t)lay_r};
+            ranges[1] = {n_tiles - slice_tiles, (slice_tiles * (uint32_t)lay_r + slice_tiles) % n_tiles};
         } else {
-            w.n_phases = 1;
-            w.phase[0].n_vtiles = n_tiles;
-            w.phase[0].tile_offset = 0;
+            ranges[0] = {n_tiles, 0u};
+        }
+        // i-block ranges: a partly filled last i-block of the 1536-row shapes is dealt by itself (its warps without rows
+        // skip the arithmetic: cheaper units, spread evenly over all CTAs).  Worth its extra chunk-sum launch when one
+        // i-block is a visible share of the rank's work: 0.7 % of the tick at 65 536 bodies and on a rank of an 8-GPU run.
+        const uint64_t rest = row_count % o.iblock_rows;
+        const bool own_last = !c->grav_no_heavy && gravity_variant(v).rows_per_thread == 4 && gravity_variant(v).scaled && rest != 0 &&
+                              rest <= (uint64_t)o.iblock_rows * 3 / 4 && w.n_iblocks >= 16 && w.n_iblocks <= 256;
+        w.heavy_iblock = own_last ? w.n_iblocks - 1 : 0xffffffffu;
+        w.n_phases = 0;
+        w.n_own_phases = 0;
+        for (uint32_t tr = 0; tr < n_ranges; ++tr) {
+            for (uint32_t part = 0; part < (own_last ? 2u : 1u); ++part) {
+                GravityPhase& P = w.phase[w.n_phases++];
+                P.n_vtiles = ranges[tr].n_vtiles;
+                P.tile_offset = ranges[tr].tile_offset;
+                P.iblock_begin = part == 0 ? 0 : w.n_iblocks - 1;
+                P.n_iblocks = own_last ? (part == 0 ? w.n_iblocks - 1 : 1) : w.n_iblocks;
+            }
+            if (tr == 0) w.n_own_phases = w.n_phases;
         }
         uint64_t max_units = 1;
-        for (uint32_t ph = 0; ph < w.n_phases; ++ph) max_units = std::max<uint64_t>(max_units, (uint64_t)w.n_iblocks * w.phase[ph].n_vtiles);
+        for (uint32_t ph = 0; ph < w.n_phases; ++ph) max_units = std::max<uint64_t>(max_units, (uint64_t)w.phase[ph].n_iblocks * w.phase[ph].n_vtiles);
         w.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->sm_count * c->grav_ctas_per_sm[v], max_units);
         if (c->grav_grid_forced > 0) w.grid = (uint32_t)std::min<uint64_t>((uint64_t)c->grav_grid_forced, max_units);
         o.frag_base = frag_float4;
@@ -602,8 +622,8 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
                 ga.flags = c->xchg.flags(c->cfg.rank);
                 ga.wait_gen = c->xchg.gen;
             }
-            ga.phase_begin = split ? l : 0;
-            ga.phase_end = split ? l + 1 : o.work.n_phases;
+            ga.phase_begin = split && l == 1 ? o.work.n_own_phases : 0;
+            ga.phase_end = split && l == 0 ? o.work.n_own_phases : o.work.n_phases;
             Timed t(c, T_GRAVITY);
             RECS_CUDA(c, launch_gravity(ga, c->stream));
             c->kernel_launches++;
@@ -653,6 +673,10 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         }
         {
             Timed t(c, T_REDUCE);
+            if (o.work.heavy_iblock != 0xffffffffu && o.row_count) {
+                RECS_CUDA(c, launch_gravity_chunksum(ra, c->stream));
+                c->kernel_launches++;
+            }
             RECS_CUDA(c, launch_gravity_reduce(ra, c->stream));
             c->kernel_launches++;
         }
@@ -1263,6 +1287,7 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
         }
         // test knobs: neither may change a bit of the result (tests/test_gpu_nbody.py)
         if (const char* g = getenv("RECS_GPU_GRAVITY_GRID")) c->grav_grid_forced = atoi(g);
+        c->grav_no_heavy = getenv("RECS_GPU_GRAVITY_NO_LAST_SPLIT") != nullptr;
         if (const char* e = getenv("RECS_GPU_GRAVITY_EMULATE_RANK")) {
             int R = 0, r = 0;
             if (sscanf(e, "%d,%d", &R, &r) == 2 && R > 1 && R <= kGravMaxPeers && r >= 0 && r < R) c->emulate_ranks = R, c->emulate_rank = r;

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             uint32_t ready = 1u << (a.own_rank & 31);  // ranks whose slice of the mirror has been seen complete
             for (uint32_t ph = a.phase_begin; ph < a.phase_end; ++ph) {
                 const GravityPhase& P = w.phase[ph];
-                const Span span = span_of(blockIdx.x, w.grid, w.n_iblocks * P.n_vtiles);
+                const Span span = span_of(blockIdx.x, w.grid, P.n_iblocks * P.n_vtiles);
                 if (span.count == 0) continue;
                 uint32_t v = span.begin % P.n_vtiles;
                 for (uint32_t k = 0; k < span.count; ++k, ++kk) {
@@ -296,10 +296,10 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
     uint32_t kk = 0;
     for (uint32_t ph = a.phase_begin; ph < a.phase_end; ++ph) {
         const GravityPhase& P = w.phase[ph];
-        const Span span = span_of(blockIdx.x, w.grid, w.n_iblocks * P.n_vtiles);
+        const Span span = span_of(blockIdx.x, w.grid, P.n_iblocks * P.n_vtiles);
         if (span.count == 0) continue;
         const uint32_t chunks_per_iblock = P.n_vtiles / K;
-        uint32_t b = span.begin / P.n_vtiles;
+        uint32_t b = P.iblock_begin + span.begin / P.n_vtiles;
         uint32_t v = span.begin % P.n_vtiles;
         uint32_t cv = v / K;        // chunk of the phase the tile belongs to
         uint32_t pic = v - cv * K;  // position of the tile in its chunk
@@ -318,6 +318,12 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             return ov < P.n_vtiles ? ov : 0xffffffffu;
         };
         uint32_t own_v = own_tile_of(b);
+        // a warp of the (partly filled) last i-block that holds no row at all skips the arithmetic and the fragments; it
+        // still takes part in the ring.  (i-packed shapes: a warp's rows are consecutive.)
+        auto warp_has_rows = [&](uint32_t iblock) -> bool {
+            return !IPACK || iblock * kGravRows + warp * (32u * RI) < a.row_count;
+        };
+        bool active = warp_has_rows(b);
         load_rows(b);
 
         for (uint32_t k = 0; k < span.count; ++k, ++kk) {
@@ -330,6 +336,22 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             }
             ptx::mbar_wait(&full_bar[stage], phase);
             const float4* t = tiles + stage * kGravTile;
+            if (!active) {  // (warp-uniform)
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty_bar[stage]);
+                if (++pic == K) pic = 0, ++cv;
+                if (++v == P.n_vtiles) {
+                    v = 0;
+                    cv = 0;
+                    ++b;
+                    if (k + 1 < span.count) {
+                        own_v = own_tile_of(b);
+                        active = warp_has_rows(b);
+                        load_rows(b);
+                    }
+                }
+                continue;
+            }
 
             // Which rows take this tile's EXACT result is decided row by row, from data alone: a row's own tile, and any
             // tile whose fast sum for that row is poisoned (or, for the min-d2 detectors, holds a pair at or below
@@ -466,7 +488,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
             if (prefix) {
                 // level 2: running prefix of the chunk (private shared-memory slots, no synchronisation needed)
                 if (pic + 1 == K || k + 1 == span.count) {
-                    float4* dst = a.frags + static_cast<size_t>(P.frag_base + b * chunks_per_iblock + cv) * kGravRows;
+                    float4* dst = a.frags + static_cast<size_t>(P.frag_base + (b - P.iblock_begin) * chunks_per_iblock + cv) * kGravRows;
 #pragma unroll
                     for (int r = 0; r < kGravRowsPerThread; ++r) {
                         float4 acc = run[r * kGravConsumerThreads + tid];
@@ -498,6 +520,7 @@ __global__ void __launch_bounds__(32 * CW + 32, MIN_CTAS) nbody_gravity_kernel(c
                 ++b;
                 if (k + 1 < span.count) {
                     own_v = own_tile_of(b);
+                    active = warp_has_rows(b);
                     load_rows(b);
                 }
             }
@@ -544,6 +567,92 @@ __device__ __forceinline__ void store_posm(const PeerPush& p, float* local, uint
 __device__ __forceinline__ bool valid_work(const GravityWork& w) { return w.n_iblocks != 0 && w.grid != 0; }
 constexpr uint32_t kGravMaxChunks = 64;  // chunks of the summation tree: kGravTargetChunks plus the padding of up to 16 ranks
 
+// Where the pieces of every chunk sum of i-block b are -- the same for all its rows, worked out once per CTA:
+//   slot[c]            prefix fragment of chunk c
+//   [ext_lo, ext_hi)   units of the chunk beyond the span of the CTA that owns its first tile (tile fragments); empty
+//                      for all but the chunks a span boundary falls into
+struct ChunkTable {
+    uint32_t slot[kGravMaxChunks], ext_lo[kGravMaxChunks], ext_hi[kGravMaxChunks], phase[kGravMaxChunks];
+};
+__device__ __forceinline__ void build_chunk_table(const GravityWork& w, uint32_t b, ChunkTable& t, bool use_chunksums) {
+    const uint32_t K = w.chunk_tiles;
+    const uint32_t n_chunks = w.n_tiles_total / K;
+    if (threadIdx.x < n_chunks && valid_work(w)) {
+        const uint32_t c = threadIdx.x;
+        if (use_chunksums && b == w.heavy_iblock) {
+            // the chunk sums of this i-block were worked out by nbody_gravity_chunksum_kernel
+            t.slot[c] = w.chunksum_base + c;
+            t.ext_lo[c] = t.ext_hi[c] = 0;
+            t.phase[c] = 0;
+            return;
+        }
+        const uint32_t tile0 = c * K;
+        uint32_t ph = 0, v0 = 0;
+        for (; ph < w.n_phases; ++ph) {  // the phase whose i-block range holds b and whose rotated tile range holds the chunk
+            const GravityPhase& Q = w.phase[ph];
+            if (b < Q.iblock_begin || b >= Q.iblock_begin + Q.n_iblocks) continue;
+            v0 = tile0 >= Q.tile_offset ? tile0 - Q.tile_offset : tile0 + w.n_tiles_total - Q.tile_offset;
+            if (v0 < Q.n_vtiles) break;
+        }
+        const GravityPhase& P = w.phase[ph < w.n_phases ? ph : 0];
+        const uint32_t units = P.n_iblocks * P.n_vtiles;
+        const uint32_t u0 = (b - P.iblock_begin) * P.n_vtiles + v0;
+        const Span s0 = span_of(cta_of(u0, w.grid, units), w.grid, units);
+        t.phase[c] = ph;
+        t.slot[c] = P.frag_base + (b - P.iblock_begin) * (P.n_vtiles / K) + v0 / K;
+        t.ext_lo[c] = min(u0 + K, s0.begin + s0.count);
+        t.ext_hi[c] = u0 + K;
+    }
+}
+// One chunk sum of one row: the prefix fragment continued with the tile fragments other CTAs stored one by one, in tile
+// order (fetched eight at a time, added in order).
+__device__ __forceinline__ float4 chunk_sum(const GravityReduceArgs& a, const ChunkTable& t, uint32_t c, uint32_t idx, float4 pre) {
+    const GravityWork& w = a.work;
+    const uint32_t rows = a.iblock_rows, K = w.chunk_tiles;
+    float cx = pre.x, cy = pre.y, cz = pre.z;
+    if (t.ext_lo[c] < t.ext_hi[c]) {
+        const GravityPhase& P = w.phase[t.phase[c]];
+        const uint32_t units = P.n_iblocks * P.n_vtiles;
+        uint32_t u = t.ext_lo[c];
+        uint32_t g = cta_of(u, w.grid, units);
+        Span sg = span_of(g, w.grid, units);
+        while (u < t.ext_hi[c]) {
+            while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
+            const uint32_t n = min(min(t.ext_hi[c], sg.begin + sg.count) - u, 8u);  // consecutive slots of one CTA
+            const float4* src = a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx;
+            float4 f[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                if (j < n) f[j] = __ldcs(src + static_cast<size_t>(j) * rows);
+#pragma unroll
+            for (uint32_t j = 0; j < 8; ++j)
+                if (j < n) cx += f[j].x, cy += f[j].y, cz += f[j].z;
+            u += n;
+        }
+    }
+    return make_float4(cx, cy, cz, 0.f);
+}
+
+// Chunk sums of the rows of the separately dealt last i-block: its spans are a few tiles long, so nearly every tile sum
+// is its own fragment and a row has thousands of pieces.  One warp per row, lane l sums chunks l and l + 32 (in tile
+// order), and the sums land in the fragment workspace where the reduce kernel picks them up like prefix fragments.
+__global__ void __launch_bounds__(256) nbody_gravity_chunksum_kernel(const GravityReduceArgs a) {
+    __shared__ ChunkTable table;
+    const GravityWork& w = a.work;
+    const uint32_t b = w.heavy_iblock;
+    build_chunk_table(w, b, table, false);
+    __syncthreads();
+    const uint32_t rows = a.iblock_rows;
+    const uint32_t idx = blockIdx.x * 8 + (threadIdx.x >> 5);  // row of the i-block
+    if (b * rows + idx >= a.row_count) return;
+    const uint32_t n_chunks = w.n_tiles_total / w.chunk_tiles;
+    float4* out = const_cast<float4*>(a.frags);
+    for (uint32_t c = threadIdx.x & 31; c < n_chunks; c += 32) {
+        const float4 pre = __ldcs(a.frags + static_cast<size_t>(table.slot[c]) * rows + idx);
+        out[static_cast<size_t>(w.chunksum_base + c) * rows + idx] = chunk_sum(a, table, c, idx, pre);
+    }
+}
+
 __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const GravityReduceArgs a) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < a.row_count;
@@ -552,29 +661,8 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
     const uint32_t b = (blockIdx.x * blockDim.x) / rows;
     const uint32_t K = w.chunk_tiles;
     const uint32_t n_chunks = w.n_tiles_total / K;
-    // Where the pieces of every chunk sum of this i-block are: the same for all rows of the CTA, worked out once.
-    //   s_slot[c]            prefix fragment of chunk c
-    //   [s_ext_lo, s_ext_hi) units of the chunk beyond the span of the CTA that owns its first tile (tile fragments);
-    //                        empty for all but the <= grid chunks a span boundary falls into
-    __shared__ uint32_t s_slot[kGravMaxChunks], s_ext_lo[kGravMaxChunks], s_ext_hi[kGravMaxChunks], s_phase[kGravMaxChunks];
-    if (threadIdx.x < n_chunks && valid_work(w)) {
-        const uint32_t c = threadIdx.x;
-        const uint32_t tile0 = c * K;
-        uint32_t ph = 0, v0 = 0;
-        for (; ph < w.n_phases; ++ph) {  // the phase whose rotated tile range holds the chunk
-            v0 = tile0 >= w.phase[ph].tile_offset ? tile0 - w.phase[ph].tile_offset
-                                                  : tile0 + w.n_tiles_total - w.phase[ph].tile_offset;
-            if (v0 < w.phase[ph].n_vtiles) break;
-        }
-        const GravityPhase& P = w.phase[ph < w.n_phases ? ph : 0];
-        const uint32_t units = w.n_iblocks * P.n_vtiles;
-        const uint32_t u0 = b * P.n_vtiles + v0;
-        const Span s0 = span_of(cta_of(u0, w.grid, units), w.grid, units);
-        s_phase[c] = ph;
-        s_slot[c] = P.frag_base + b * (P.n_vtiles / K) + v0 / K;
-        s_ext_lo[c] = min(u0 + K, s0.begin + s0.count);
-        s_ext_hi[c] = u0 + K;
-    }
+    __shared__ ChunkTable table;
+    build_chunk_table(w, b, table, true);
     __syncthreads();
     if (a.tail.posm) push_begin(a.push);
     float mx = 0.f, my = 0.f, mz = 0.f, mg = 0.f;  // this row's refreshed mirror entry
@@ -587,30 +675,15 @@ __global__ void __launch_bounds__(256) nbody_gravity_reduce_kernel(const Gravity
             float4 pre[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                if (c0 + u < n_chunks) pre[u] = __ldcs(a.frags + static_cast<size_t>(s_slot[c0 + u]) * rows + idx);
+                if (c0 + u < n_chunks) pre[u] = __ldcs(a.frags + static_cast<size_t>(table.slot[c0 + u]) * rows + idx);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const uint32_t c = c0 + u;
                 if (c >= n_chunks) break;
-                float cx = pre[u].x, cy = pre[u].y, cz = pre[u].z;
-                if (s_ext_lo[c] < s_ext_hi[c]) {
-                    // continue the prefix with the tile sums other CTAs stored one by one, in tile order
-                    const GravityPhase& P = w.phase[s_phase[c]];
-                    const uint32_t units = w.n_iblocks * P.n_vtiles;
-                    uint32_t u_ = s_ext_lo[c];
-                    uint32_t g = cta_of(u_, w.grid, units);
-                    Span sg = span_of(g, w.grid, units);
-                    for (; u_ < s_ext_hi[c]; ++u_) {
-                        while (u_ >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
-                        const float4 f = __ldcs(a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u_ - sg.begin)) * rows + idx);
-                        cx += f.x;
-                        cy += f.y;
-                        cz += f.z;
-                    }
-                }
-                sx += cx;
-                sy += cy;
-                sz += cz;
+                const float4 cs = chunk_sum(a, table, c, idx, pre[u]);
+                sx += cs.x;
+                sy += cs.y;
+                sz += cs.z;
             }
         }
         const uint64_t row = a.row_begin + i;
@@ -774,6 +847,13 @@ cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s) {
     // a pushing rank always launches (at least one CTA): its peers wait for the generation flag
     const uint32_t grid = std::max<uint32_t>((a.row_count + 255) / 256, 1u);
     nbody_gravity_reduce_kernel<<<grid, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gravity_chunksum(const GravityReduceArgs& a, cudaStream_t s) {
+    if (a.work.heavy_iblock == 0xffffffffu || a.work.heavy_iblock * a.iblock_rows >= a.row_count) return cudaSuccess;
+    const uint32_t heavy_rows = a.row_count - a.work.heavy_iblock * a.iblock_rows;
+    nbody_gravity_chunksum_kernel<<<(heavy_rows + 7) / 8, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

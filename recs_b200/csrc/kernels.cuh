@@ -62,23 +62,33 @@ inline uint32_t gravity_chunk_tiles(uint64_t n_bodies) {
     return (uint32_t)(k ? k : 1);
 }
 
-// One phase: every i-block against tiles [tile_offset, tile_offset + n_vtiles) (mod n_tiles_total).  A single-GPU
-// launch has one phase over all tiles; a rank of a sharded run visits its own slice first (phase 0), then the other
-// ranks' slices in rotated order (phase 1).
+// One phase: i-blocks [iblock_begin, iblock_begin + n_iblocks) against tiles [tile_offset, tile_offset + n_vtiles) (mod
+// n_tiles_total).  A single-GPU launch has one tile range (all tiles); a rank of a sharded run visits its own slice
+// first, then the other ranks' slices in rotated order.  A partly filled LAST i-block gets phases of its own: its warps
+// without rows skip the arithmetic, so its units are cheaper than the others -- dealt evenly over all CTAs by themselves
+// they cannot unbalance the stream-K split, whatever they cost.
 struct GravityPhase {
     uint32_t n_vtiles;        // tiles visited per i-block: whole chunks
     uint32_t tile_offset;     // first tile visited: a chunk boundary
-    uint32_t frag_base;       // prefix fragment of (i-block b, chunk cv of the phase): frag_base + b * (n_vtiles / K) + cv
+    uint32_t iblock_begin;    // first i-block of the phase
+    uint32_t n_iblocks;       // i-blocks of the phase
+    uint32_t frag_base;       // prefix fragment of (i-block b, chunk cv of the phase): frag_base + (b - iblock_begin) * (n_vtiles / K) + cv
     uint32_t tile_frag_base;  // tile fragment of CTA g, unit u: tile_frag_base + g * (K - 1) + (u - span begin of g)
 };
 
+constexpr int kGravMaxPhases = 4;
 struct GravityWork {
     uint32_t grid;            // persistent CTAs (stream-K workers), the same for every phase
     uint32_t n_iblocks;       // ceil(row_count / rows per i-block)
     uint32_t n_tiles_total;   // tiles of the mirror: a multiple of chunk_tiles
     uint32_t chunk_tiles;     // K
     uint32_t n_phases;
-    GravityPhase phase[2];
+    uint32_t n_own_phases;    // phases over the rank's own tiles come first (the NCCL exchange launches them separately)
+    // Chunk sums of the rows of a separately dealt last i-block, worked out by nbody_gravity_chunksum_kernel before the
+    // reduce (slot chunksum_base + c of the fragment workspace); ~0u: no such i-block.
+    uint32_t heavy_iblock;
+    uint32_t chunksum_base;
+    GravityPhase phase[kGravMaxPhases];
 };
 
 // Number of fragment slots (of rows-per-i-block float4 each) a work description needs; assigns the bases.
@@ -86,9 +96,13 @@ inline uint32_t gravity_assign_frag_slots(GravityWork& w) {
     uint32_t next = 0;
     for (uint32_t p = 0; p < w.n_phases; ++p) {
         w.phase[p].frag_base = next;
-        next += w.n_iblocks * (w.phase[p].n_vtiles / w.chunk_tiles);
+        next += w.phase[p].n_iblocks * (w.phase[p].n_vtiles / w.chunk_tiles);
         w.phase[p].tile_frag_base = next;
         next += w.phase[p].n_vtiles ? w.grid * (w.chunk_tiles - 1) : 0;
+    }
+    if (w.heavy_iblock != 0xffffffffu) {
+        w.chunksum_base = next;
+        next += w.n_tiles_total / w.chunk_tiles;
     }
     return next;
 }
@@ -161,6 +175,8 @@ int gravity_max_ctas_per_sm(int variant);  // occupancy of the interaction kerne
 cudaError_t gravity_prepare();  // one-time function attributes
 cudaError_t launch_gravity(const GravityArgs& a, cudaStream_t s);
 cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
+// Chunk sums of the rows of the separately dealt last i-block (a.work.heavy_iblock): one warp per row, lanes = chunks.
+cudaError_t launch_gravity_chunksum(const GravityReduceArgs& a, cudaStream_t s);
 
 // Position(12 B) + Mass(4 B) rows [row_begin, row_begin + n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
 // gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`; bodies [dst_offset + n,
