@@ -546,9 +546,9 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         const uint64_t rest = row_count % o.iblock_rows;
         const bool own_last = !c->grav_no_heavy && gravity_variant(v).rows_per_thread == 4 && gravity_variant(v).scaled && rest != 0 &&
                               rest <= (uint64_t)o.iblock_rows * 3 / 4 && w.n_iblocks >= 16 && w.n_iblocks <= 256;
-        // (its rows have up to K - 1 tile fragments per chunk: beyond a handful the reduce kernel's one-thread-per-row walk
-        // is too serial, and their chunk sums come from nbody_gravity_chunksum_kernel instead)
-        w.heavy_iblock = own_last && K > 16 ? w.n_iblocks - 1 : 0xffffffffu;
+        // (its rows have up to K - 1 tile fragments per chunk; the reduce kernel's one-thread-per-row walk is too serial
+        // for them even at K = 8 -- +48 us at 65 536 bodies -- so their chunk sums come from nbody_gravity_chunksum_kernel)
+        w.heavy_iblock = own_last ? w.n_iblocks - 1 : 0xffffffffu;
         w.n_phases = 0;
         w.n_own_phases = 0;
         for (uint32_t tr = 0; tr < n_ranges; ++tr) {
