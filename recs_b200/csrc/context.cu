@@ -589,10 +589,8 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
             }
             off += q[qi].first->count;
         }
-        // (A partly filled last i-block costs as much as a full one: 0.8 % of a rank's tick at 1 M bodies on 8 GPUs.  Giving
-        // its rows to a second, small launch was measured and dropped: the spans of so few rows are much shorter than a
-        // chunk of the summation tree, nearly every tile sum becomes its own fragment and the reduce of those rows costs more
-        // than the launch saves -- profiles/r02_remainder_launch.txt.)
+        // (A partly filled last i-block is handled inside add_outer: phases of its own.  Giving its rows to a second, small
+        // launch of the 256-row shape was measured first and dropped -- profiles/r02_remainder_launch.txt.)
         if ((st = add_outer(a, p, acc, row_begin, row_count, variant, self_offset)) != RECS_OK) return st;
     }
     if ((st = ensure(c, &c->frags, &c->frags_cap, std::max<size_t>(frag_float4, 1) * sizeof(float4))) != RECS_OK) return st;

@@ -2,7 +2,7 @@
 wait on one another, so they must never share a device).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node R --master-addr 127.0.0.1 --master-port P \
-        tests/tools/multi_gpu_check.py [bodies] [ticks] [full|own] [p2p|nccl]
+        tests/tools/multi_gpu_check.py [bodies] [ticks] [full|own] [p2p|nccl] [noref]
 
 Checks, per rank, on the rows it owns: the oracle tolerances (positions bit-exact after one tick), and that the
 sharded result equals the SINGLE-GPU result of the same library bit for bit (the summation tree does not depend on
@@ -24,6 +24,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
 ticks = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 own_rows_only = len(sys.argv) > 3 and sys.argv[3] == "own"  # every rank's host holds (and moves) only its own rows
 exchange = sys.argv[4] if len(sys.argv) > 4 else "p2p"
+skip_oracle = len(sys.argv) > 5 and sys.argv[5] == "noref"  # sizes the CPU oracle takes minutes for: bit-identity with the single-GPU run only
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 device = local
 dist.init_process_group("gloo")
@@ -67,9 +68,10 @@ with GpuContext(device=device, use_cuda_graph=False) as one:
 same_as_single_gpu = all(
     np.array_equal(a[rb:re].view(np.uint32), b[rb:re].view(np.uint32)) for a, b in ((pos, single[0]), (vel, single[2]), (acc, single[3])))
 
-ref = [a.copy() for a in start]
-orc = oracle.load_nbody()
-orc.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks)
+ref = [a.copy() for a in (single if skip_oracle else start)]
+if not skip_oracle:
+    orc = oracle.load_nbody()
+    orc.run_sequential(ref[0], ref[1], ref[2], ref[3], ticks)
 
 
 def rel(got, want, floor=0.0):
