@@ -12,17 +12,26 @@
 //     "j-packed" form (lanes = two bodies j) is kept as an A/B variant.
 //   * the reference's `d2 <= f32::EPSILON => zero` costs no instruction per pair: positions are stored
 //     scaled by 2^-32 (exact), so r^-3 overflows to +inf for every pair the reference masks (and a few
-//     more); one finiteness test per tile sends the thread to an exact masked redo of that tile.
+//     more); one finiteness test per row and tile sends that row to an exact masked redo of the tile.
 //   * j tiles live in HBM pair-interleaved ({x0 x1 y0 y1 | z0 z1 gm0 gm1}, 32 B per pair), so a tile is one
 //     contiguous 4 KiB block: a single elected thread of a producer warp moves it with a 1-D TMA bulk copy
 //     (cp.async.bulk -> UBLKCP) into a 4-stage shared-memory ring guarded by full/empty mbarriers.
 //     Consumers read tiles with uniform (broadcast) LDS.128.
 //   * register blocking: 4 bodies i per thread (2 row pairs), so one LDS.128 pair feeds 4 pair-interactions;
-//     a warp owns 128 consecutive rows, i.e. its own bodies sit in one j tile.
-//   * stream-K work split: the (i-block, j-tile) units of a launch are cut into equal contiguous spans, one
-//     per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies load all 148 SMs as evenly as 1 M
-//     bodies do.  A CTA writes one partial ("fragment") per i-block it touched; a second kernel adds the
-//     fragments of each i-block in ascending j order -- deterministic, no float atomics -- and integrates.
+//     a warp owns 128 consecutive rows, i.e. its own bodies sit in one j tile, which goes straight to the exact path.
+//     Which rows take a tile's exact result is decided row by row from data alone (own tile, or the row's fast sum
+//     poisoned), never by which rows happen to share a thread.
+//   * stream-K work split over a FIXED SUMMATION TREE (kernels.cuh): the (i-block, j-tile) units of a phase are cut
+//     into equal contiguous spans, one per persistent CTA (grid = SMs x resident CTAs), so 65 536 bodies load all 148
+//     SMs as evenly as 1 M bodies do.  Tile sums are added into chunk sums (K consecutive tiles) and chunk sums into
+//     the row total, both in ascending order from zero: a CTA that enters a chunk at its first tile stores the chunk's
+//     running prefix once, a CTA whose span begins inside a chunk stores the remaining tile sums one by one, and the
+//     reduce kernel continues the prefix with them in tile order -- deterministic, no float atomics, and not a bit of
+//     a row depends on the grid, on the launch split or on the number of GPUs.  The reduce kernel then integrates.
+//   * phases: a tile range (a rank of a sharded run walks its own slice first, then the other ranks' slices, whose
+//     tiles it loads only after acquiring that rank's generation flag -- the peers push their refreshed positions
+//     into this GPU's memory over NVLink) times an i-block range (a partly filled last i-block is dealt by itself, its
+//     warps without rows skip the arithmetic).  One persistent launch runs all phases.
 #include <algorithm>
 
 #include "kernels.cuh"
