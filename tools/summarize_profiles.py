@@ -31,10 +31,11 @@ def launch_list(n, path, extra=""):
     agg = collections.OrderedDict()
     for k, us in seq:
         agg.setdefault(k, []).append(us)
-    g = sum(agg["nbody_gravity_kernel"]) / len(agg["nbody_gravity_kernel"])
-    r = sum(agg["nbody_gravity_reduce_kernel"]) / len(agg["nbody_gravity_reduce_kernel"])
-    lines.append(f"# per tick: nbody_gravity_kernel {g:.2f} us + nbody_gravity_reduce_kernel (fragment sum + movement + acceleration + "
-                 f"mirror refresh) {r:.2f} us -> interaction kernel share of the tick {g / (g + r):.4f}")
+    mean = lambda k: sum(agg[k]) / len(agg[k]) if k in agg else 0.0
+    g, r, cs = mean("nbody_gravity_kernel"), mean("nbody_gravity_reduce_kernel"), mean("nbody_gravity_chunksum_kernel")
+    lines.append(f"# per tick: nbody_gravity_kernel {g:.2f} us + nbody_gravity_chunksum_kernel (chunk sums of a separately dealt last i-block) "
+                 f"{cs:.2f} us + nbody_gravity_reduce_kernel (fragment sum + movement + acceleration + mirror refresh) {r:.2f} us "
+                 f"-> interaction kernel share of the tick {g / (g + r + cs):.4f}")
     lines.append("# (recs_generic_system = the reference-order generic gravity of the parity block; fp32_peak_kernel = the live FFMA2 probe; "
                  "fill / read_sweep = L2 flush; pack_posm_kernel = mirror pack after an upload)")
     open(os.path.join(P, f"r02_launch_list_{n}.txt"), "w").write("\n".join(lines) + "\n")
