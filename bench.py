@@ -358,6 +358,16 @@ def kernel_roofline(ctx, app, n, rows_here, k_steps, traffic):
     }, t
 
 
+def energy_drift(orc, initial, finals: dict) -> dict:
+    """|E_end - E_0| / |E_0| with E = kinetic + potential in f64 (oracle.total_energy) for each named final state."""
+    k0, u0 = orc.total_energy(initial[0], initial[1], initial[2])
+    out = {"e0": k0 + u0, "kinetic0": k0, "potential0": u0, "norm": "|E_end - E_0| / |E_0|, E in f64 from the columns"}
+    for name, (p, v) in finals.items():
+        k, u = orc.total_energy(p, initial[1], v)
+        out[name] = abs((k + u) - (k0 + u0)) / abs(k0 + u0)
+    return out
+
+
 def config_subrecord(n, ticks_per_step, steps, device, traffic, scenes, cpu_orc, cpu_note):
     """One secondary config on a fresh single-GPU context: value, roofline, parity, clocks, cpu_baseline."""
     import oracle
@@ -397,6 +407,24 @@ def config_subrecord(n, ticks_per_step, steps, device, traffic, scenes, cpu_orc,
                 "bound": 1e-4,
                 "norm": "max_i |x_gpu - x_ref| / max(|x_ref|, 1)",
             }
+            # relative total-energy drift, reported beside the f64 run of the same integration
+            p64, v64, a64 = pos0.astype(np.float64), vel0.astype(np.float64), acc0.astype(np.float64)
+            orc.run_f64(p64, mass0, v64, a64, ticks_per_step)
+            parity[f"energy_drift_after_{ticks_per_step}_ticks"] = energy_drift(
+                orc, (pos0, mass0, vel0), {"gpu": (app.pos, app.vel), "reference_order_f32": (ref[0], ref[2]), "f64_oracle": (p64, v64)})
+        elif n <= 65536:
+            # configs[1]: the north star's 100 steps; the energy of the GPU run alone (the f64 run of 100 ticks at this
+            # size is minutes of host time; tests/test_gpu_nbody.py compares the columns with the reference order)
+            for dst, src in zip(cols, (pos0, mass0, vel0, acc0)):
+                dst[...] = src
+            app.upload()
+            app.tick(100)
+            app.download()
+            parity["energy_drift_after_100_ticks"] = energy_drift(orc, (pos0, mass0, vel0), {"gpu": (app.pos, app.vel)})
+            parity["energy_drift_after_100_ticks"]["note"] = (
+                "the integrator's own drift (semi-implicit Euler at dt = 1/20000 through close encounters), not arithmetic: "
+                "tests/test_gpu_nbody.py::test_drift_65536_bodies_100_ticks runs the reference summation order beside it and "
+                "asserts the two energies agree to 1e-6 of E_0")
         for _ in range(3):
             app.tick(ticks_per_step)
         ctx.synchronize()
@@ -752,6 +780,30 @@ def hbm_roofline(kernel, gbs, peak, ms, traffic):
             "traffic_unit": "bytes of DRAM traffic per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r02_traffic.json)"}
 
 
+def rain_parity(ctx, arch, vel_id, pos_id, vel, pos, ticks, rows=1 << 20) -> dict:
+    """The fused rain tick against the oracle's three systems in schedule order (wind -> gravity -> movement) on the first
+    and last `rows` drops (drops are independent of each other), after the `ticks` ticks this section ran: bit for bit."""
+    import oracle
+
+    orc = oracle.load_nbody()
+    n = vel.shape[0]
+    v0, p0 = vel.copy(), pos.copy()  # bound host arrays still hold the initial state: nothing was downloaded yet
+    vel = ctx.download(arch, vel_id)
+    pos = ctx.download(arch, pos_id)
+    direction = np.ascontiguousarray(ctx.get_wind_direction(), dtype=np.float32)
+    ok, checked = True, 0
+    for b, e in ((0, min(rows, n)), (max(n - rows, 0), n)):
+        rv, rp = np.ascontiguousarray(v0[b:e]), np.ascontiguousarray(p0[b:e])
+        for _ in range(ticks):
+            orc.rain_wind(rv, direction)
+            orc.rain_gravity(rv)
+            orc.rain_movement(rp, rv)
+        ok = ok and np.array_equal(rv.view(np.uint32), vel[b:e].view(np.uint32)) and np.array_equal(rp.view(np.uint32), pos[b:e].view(np.uint32))
+        checked += e - b
+    return {"bit_exact": bool(ok), "rows_checked": int(checked), "ticks": int(ticks),
+            "how": "velocity and position columns against the oracle's wind, gravity, movement run in schedule order"}
+
+
 def streaming_extras(ctx, traffic) -> dict:
     """HBM-bound systems of configs[3] / configs[4]: achieved GB/s on algorithmic bytes, each with its own roofline block."""
     from recs_b200 import _lib, scenes
@@ -825,6 +877,12 @@ def streaming_extras(ctx, traffic) -> dict:
         "how": "same 20-pass bracket; NVRTC-compiled body in the generated TMA-pipelined kernel",
         "roofline": hbm_roofline("recs_generic_system (generated)", ggbs, peak, float(generic_ms), traffic.get("recs_generic_system_simple_iter_10M")),
     }
+    # parity of both simple_iter systems: every pass adds (1, 1, 1) to a position that started at (1, 1, 1), exactly
+    got = ctx.download(ARCH, A)
+    n_passes = (3 + passes + 20) + (3 + passes)
+    ok = bool(np.all(got == np.float32(1 + n_passes)))
+    for key in ("simple_iter_10M", "simple_iter_10M_generic_system"):
+        out[key]["parity"] = {"bit_exact": ok, "rows_checked": n, "how": f"all rows after the {n_passes} passes of this section (both systems), against 1 + passes"}
     # rain: 4 Mi drops, fused wind -> gravity -> movement, 48 B / entity / tick
     n = 4 * 1024 * 1024
     VEL, POS, ARCH2 = 201, 202, 8
@@ -865,6 +923,7 @@ def streaming_extras(ctx, traffic) -> dict:
         "roofline": dict(hbm_roofline("rain_tma_kernel<2>", gbs, peak, float(np.median(ms)), traffic.get("rain_tma_kernel_4Mi")),
                          note="NOT an HBM figure: at this size the written half of the columns stays in L2 (traffic < algorithmic bytes)"),
     }
+    out["rain_4Mi_fused"]["parity"] = rain_parity(ctx, ARCH2, VEL, POS, vel, pos, 3 + 20 + 20)
     # the same tick HBM-bound: 16 Mi drops (2 x 200 MB columns, larger than L2), 20 ticks back to back
     n = 16 * 1024 * 1024
     vel, mass, pos = scenes.rain_drops(n, 1)
@@ -889,6 +948,7 @@ def streaming_extras(ctx, traffic) -> dict:
         "roofline": hbm_roofline("rain_tma_kernel<2>", bgbs, peak, float(big_ms), traffic.get("rain_tma_kernel_16Mi")),
     }
     out["clocks"] = sampler.stop()
+    out["rain_16Mi_fused"]["parity"] = rain_parity(ctx, ARCH2, VEL, POS, vel, pos, 3 + 20)
     out["hbm_peak_GBps"] = peak
     return out
 

@@ -38,6 +38,8 @@ class NBodyOracle:
         lib.oracle_gravity_sample.restype = None
         lib.oracle_gravity_sample_mt.argtypes = [_f32p, _u64p, z, _f32p, _f32p, z, C.c_void_p, C.c_void_p, C.c_int]
         lib.oracle_gravity_sample_mt.restype = None
+        lib.oracle_total_energy_mt.argtypes = [_f64p, _f32p, _f64p, z, C.c_int, _f64p]
+        lib.oracle_total_energy_mt.restype = None
         lib.oracle_axpy_rows.argtypes = [_f32p, _f32p, C.c_float, z, z]
         lib.oracle_axpy_rows.restype = None
         lib.oracle_add_rows.argtypes = [_f32p, _f32p, z, z]
@@ -88,6 +90,17 @@ class NBodyOracle:
             pos, rows, rows.size, pos, mass, pos.shape[0], out32.ctypes.data, out64.ctypes.data if f64 else None, int(threads)
         )
         return out32, out64
+
+    def total_energy(self, pos, mass, vel, threads=None):
+        """(kinetic, potential) of the whole set in f64 (SURVEY 8d's energy-drift diagnostic); f32 columns are widened."""
+        pos64 = np.ascontiguousarray(pos, dtype=np.float64)
+        vel64 = np.ascontiguousarray(vel, dtype=np.float64)
+        mass = np.ascontiguousarray(mass, dtype=np.float32).reshape(-1)
+        if threads is None:
+            threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        out = np.zeros(2, dtype=np.float64)
+        self.lib.oracle_total_energy_mt(pos64, mass, vel64, pos64.shape[0], int(min(threads, 256)), out)
+        return float(out[0]), float(out[1])
 
     def axpy(self, y, x, a, rows=None):
         b, e = (0, y.shape[0]) if rows is None else rows

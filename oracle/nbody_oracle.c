@@ -151,6 +151,57 @@ ORACLE_API void oracle_gravity_sample_mt(const float* pos, const uint64_t* rows,
     free(th);
 }
 
+/* ---- total energy (relative total-energy drift over 100 ticks, reported) ------------------------------
+ * E = sum_i 1/2 m_i |v_i|^2  -  sum_{i<j} G m_i m_j / |p_j - p_i|, all in f64 from f64 state (f32 columns are widened by
+ * the caller).  Pairs the force law masks (d2 <= f32::EPSILON, lib.rs:118-120) carry no force and so no potential
+ * here either.  Not part of the reference (it never computes an energy); a diagnostic of the integration. */
+typedef struct {
+    const double *pos, *vel;
+    const float* mass;
+    size_t n;
+    int t, n_threads;
+    double kinetic, potential;
+} energy_job_t;
+static void* energy_worker(void* arg) {
+    energy_job_t* j = (energy_job_t*)arg;
+    double k = 0.0, u = 0.0;
+    for (size_t i = (size_t)j->t; i < j->n; i += (size_t)j->n_threads) { /* interleaved rows: even pair counts */
+        const double px = j->pos[3 * i], py = j->pos[3 * i + 1], pz = j->pos[3 * i + 2];
+        const double vx = j->vel[3 * i], vy = j->vel[3 * i + 1], vz = j->vel[3 * i + 2];
+        const double mi = (double)j->mass[i];
+        k += 0.5 * mi * ((vx * vx + vy * vy) + vz * vz);
+        double ui = 0.0;
+        for (size_t q = i + 1; q < j->n; ++q) {
+            const double tx = j->pos[3 * q] - px, ty = j->pos[3 * q + 1] - py, tz = j->pos[3 * q + 2] - pz;
+            const double d2 = (tx * tx + ty * ty) + tz * tz;
+            if (!(d2 <= (double)F32_EPSILON)) ui += (double)j->mass[q] / sqrt(d2);
+        }
+        u -= (double)GRAVITATIONAL_CONSTANT * mi * ui;
+    }
+    j->kinetic = k;
+    j->potential = u;
+    return NULL;
+}
+/* out[0] = kinetic, out[1] = potential (negative). */
+ORACLE_API void oracle_total_energy_mt(const double* pos, const float* mass, const double* vel, size_t n, int n_threads,
+                                       double* out) {
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > 256) n_threads = 256;
+    pthread_t th[256];
+    energy_job_t jobs[256];
+    for (int t = 0; t < n_threads; ++t) {
+        energy_job_t j = {pos, vel, mass, n, t, n_threads, 0.0, 0.0};
+        jobs[t] = j;
+        pthread_create(&th[t], NULL, energy_worker, &jobs[t]);
+    }
+    out[0] = out[1] = 0.0;
+    for (int t = 0; t < n_threads; ++t) {
+        pthread_join(th[t], NULL);
+        out[0] += jobs[t].kinetic; /* fixed thread order: the sum does not depend on timing */
+        out[1] += jobs[t].potential;
+    }
+}
+
 /* ---- movement / acceleration: crates/n-body/src/lib.rs:87-102 ---------------------------- */
 /* position.point += velocity * FIXED_TIME_STEP  (mul, then add; componentwise) */
 ORACLE_API void oracle_axpy_rows(float* y, const float* x, float a, size_t row_begin, size_t row_end) {

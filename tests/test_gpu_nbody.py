@@ -135,10 +135,21 @@ def test_100_ticks_config0_drift(nbody_oracle, use_graph):
         app, (pos, mass, vel, acc) = _app(ctx, 1000, seed=1, scene=scenes.EVERYTHING_HEAVY)
         app.tick(100)
         app.download()
+    start = [a.copy() for a in (pos, mass, vel, acc)]
     nbody_oracle.run_sequential(pos, mass, vel, acc, 100)
     assert rel_err_rows(app.pos, pos, floor=1.0).max() <= 1e-4
     assert rel_err_rows(app.vel, vel, floor=1.0).max() <= 1e-4
     assert rel_err_rows(app.acc, acc).max() <= 1e-3  # accelerations of drifted positions
+    # relative total-energy drift, beside the f64 run of the same integration.  The integrator (semi-implicit
+    # Euler at dt = 1/20000) does not conserve energy exactly; what is asserted is that f32 on the GPU adds nothing visible
+    # to what the f64 run and the reference-order f32 run show.
+    e0 = sum(nbody_oracle.total_energy(start[0], start[1], start[2]))
+    p64, v64, a64 = (start[i].astype(np.float64) for i in (0, 2, 3))
+    nbody_oracle.run_f64(p64, start[1], v64, a64, 100)
+    drift = {name: abs(sum(nbody_oracle.total_energy(p, start[1], v)) - e0) / abs(e0)
+             for name, (p, v) in {"gpu": (app.pos, app.vel), "ref32": (pos, vel), "f64": (p64, v64)}.items()}
+    print("energy drift 1000 x 100:", drift)
+    assert abs(drift["gpu"] - drift["f64"]) <= 1e-6 + 2.0 * abs(drift["ref32"] - drift["f64"])
 
 
 def test_graph_and_eager_ticks_agree_bitwise():
@@ -659,3 +670,9 @@ def test_drift_65536_bodies_100_ticks(nbody_oracle):
     assert vel_err <= max(1e-4, 2.0 * ref_vel_sens), f"velocity drift {vel_err:.3e}, reference's own order sensitivity {ref_vel_sens:.3e}"
     # the bulk of the bodies is nowhere near the bound
     assert np.quantile(rel_err_rows(gpu[2], ref[2], floor=1.0), 0.999) <= 1e-5
+    # relative total-energy drift over the 100 ticks (f64 from the columns), beside the reference-order run's
+    e0 = sum(nbody_oracle.total_energy(start[0], start[1], start[2]))
+    e_gpu = sum(nbody_oracle.total_energy(gpu[0], start[1], gpu[2]))
+    e_ref = sum(nbody_oracle.total_energy(ref[0], start[1], ref[2]))
+    print(f"energy drift 65536 x 100: gpu {abs(e_gpu - e0) / abs(e0):.3e}  reference order {abs(e_ref - e0) / abs(e0):.3e}")
+    assert abs(e_gpu - e_ref) / abs(e0) <= 1e-6

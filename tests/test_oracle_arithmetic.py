@@ -157,3 +157,25 @@ def test_f64_oracle_bounds_the_f32_reference_order_sum(nbody_oracle):
     a64 = nbody_oracle.gravity_f64(pos, mass)
     err = np.linalg.norm(a32 - a64, axis=1) / np.linalg.norm(a64, axis=1)
     assert err.max() < 2e-5  # the reference's own sequential f32 sum at 2 000 bodies
+
+
+def test_total_energy_equals_numpy_f64_and_is_thread_independent(nbody_oracle):
+    """SURVEY 8d's energy-drift diagnostic: E = sum 1/2 m v^2 - sum_{i<j} G m_i m_j / r, pairs the force law masks left out."""
+    from recs_b200 import scenes
+
+    n = 700
+    pos, mass, vel, _ = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 4)
+    pos[11] = pos[10]  # a coincident pair: no force in the reference (lib.rs:118-120), no potential here
+    k, u = nbody_oracle.total_energy(pos, mass, vel, threads=3)
+    p, m = pos.astype(np.float64), mass.reshape(-1).astype(np.float64)
+    d = p[None, :, :] - p[:, None, :]
+    d2 = (d * d).sum(-1)
+    i, j = np.triu_indices(n, 1)
+    keep = d2[i, j] > np.float64(np.finfo(np.float32).eps)
+    assert keep.sum() == i.size - 1
+    g = np.float64(np.float32(6.67e-11))
+    want_u = -(g * m[i[keep]] * m[j[keep]] / np.sqrt(d2[i, j][keep])).sum()
+    want_k = (0.5 * m * (vel.astype(np.float64) ** 2).sum(-1)).sum()
+    assert abs(k - want_k) <= 1e-12 * abs(want_k) and abs(u - want_u) <= 1e-12 * abs(want_u)
+    k1, u1 = nbody_oracle.total_energy(pos, mass, vel, threads=1)
+    assert abs(k1 - k) <= 1e-13 * abs(k) and abs(u1 - u) <= 1e-13 * abs(u)
