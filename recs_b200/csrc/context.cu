@@ -135,6 +135,12 @@ struct recs_gpu_ctx {
     // gravity workspace
     float* posm = nullptr;
     size_t posm_cap = 0;
+    // second mirror buffer + grid-barrier word of the many-ticks-in-one-launch path (small single-archetype worlds)
+    float* posm_alt = nullptr;
+    size_t posm_alt_cap = 0;
+    uint32_t* resident_barrier = nullptr;
+    uint64_t resident_max_rows = 4096;  // RECS_GPU_RESIDENT_MAX_ROWS (0 switches the path off)
+    uint64_t resident_launches = 0;
     uint64_t posm_bodies = 0;  // padded body count currently laid out
     std::vector<std::pair<ColKey, uint64_t>> posm_sources;  // (column, version) the mirror was packed from
     float4* frags = nullptr;
@@ -1132,7 +1138,9 @@ bool posm_is_current(recs_gpu_ctx* c) {
 int32_t check_device_error(recs_gpu_ctx* c) {
     if (c->dev_error_host && *reinterpret_cast<volatile uint32_t*>(c->dev_error_host)) {
         *c->dev_error_host = 0;
-        return fail(c, RECS_ERR_NCCL, "peer exchange timed out: a rank did not push its slice of the position mirror (ranks must run the same ticks)");
+        return fail(c, RECS_ERR_NCCL, c->cfg.world_size > 1
+                                          ? "peer exchange timed out: a rank did not push its slice of the position mirror (ranks must run the same ticks)"
+                                          : "a device-side wait timed out (grid barrier of the resident n-body ticks)");
     }
     return RECS_OK;
 }
@@ -1288,6 +1296,8 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
         // test knobs: neither may change a bit of the result (tests/test_gpu_nbody.py)
         if (const char* g = getenv("RECS_GPU_GRAVITY_GRID")) c->grav_grid_forced = atoi(g);
         c->grav_no_heavy = getenv("RECS_GPU_GRAVITY_NO_LAST_SPLIT") != nullptr;
+        if (const char* r = getenv("RECS_GPU_RESIDENT_MAX_ROWS")) c->resident_max_rows = (uint64_t)atoll(r);
+        if (c->resident_max_rows > (uint64_t)kResidentMaxTiles * kGravTile) c->resident_max_rows = (uint64_t)kResidentMaxTiles * kGravTile;
         if (const char* e = getenv("RECS_GPU_GRAVITY_EMULATE_RANK")) {
             int R = 0, r = 0;
             if (sscanf(e, "%d,%d", &R, &r) == 2 && R > 1 && R <= kGravMaxPeers && r >= 0 && r < R) c->emulate_ranks = R, c->emulate_rank = r;
@@ -1325,6 +1335,8 @@ int32_t recs_gpu_destroy(recs_gpu_ctx* c) {
                 if (kv.second.counter) cudaFree(kv.second.counter);
             }
         if (c->posm) cudaFree(c->posm);
+        if (c->posm_alt) cudaFree(c->posm_alt);
+        if (c->resident_barrier) cudaFree(c->resident_barrier);
         if (c->frags) cudaFree(c->frags);
         for (int r = 0; r < kGravMaxPeers; ++r)
             if (c->xchg.peer[r] && c->xchg.peer[r] != c->xchg.base) cudaIpcCloseMemHandle(c->xchg.peer[r]);
@@ -1857,9 +1869,78 @@ int32_t recs_gpu_set_tick_order(recs_gpu_ctx* c, const uint32_t* ids, uint32_t n
     return RECS_OK;
 }
 
+// The tick is exactly gravity -> movement -> acceleration over one small body archetype (the reference's benchmark at its
+// own size): `n_ticks` further ticks in one cooperative launch.  The mirror must be current (a tick of the ordinary chain
+// just ran).  Bit-identical to running the chain tick by tick.
+bool resident_ticks_apply(recs_gpu_ctx* c) {
+    if (c->order.size() != 3 || c->cfg.world_size != 1 || c->emulate_ranks > 1 || c->grav_variant_forced || c->timing) return false;
+    System& g = c->systems[c->order[0]];
+    System& m = c->systems[c->order[1]];
+    System& a = c->systems[c->order[2]];
+    if (g.kind != RECS_SYS_NBODY_GRAVITY || m.kind != RECS_SYS_NBODY_MOVEMENT || a.kind != RECS_SYS_NBODY_ACCELERATION) return false;
+    if (g.archs.size() != 1 || g.archs != g.qarchs || g.archs != m.archs || g.archs != a.archs) return false;
+    if (m.comp[0] != g.comp[0] || a.comp[0] != m.comp[1] || a.comp[1] != g.comp[1]) return false;
+    const Column* p = find_column(c, g.archs[0], g.comp[0]);
+    return p && p->count >= 1 && p->count <= c->resident_max_rows && p->count <= kGravSmallRows;
+}
+
+int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks) {
+    System& g = c->systems[c->order[0]];
+    const uint32_t arch = g.archs[0];
+    Column *pos, *vel, *acc, *mass;
+    int32_t st;
+    if ((st = need_column(c, arch, g.comp[0], 12, &pos)) != RECS_OK) return st;
+    if ((st = need_column(c, arch, c->systems[c->order[1]].comp[1], 12, &vel)) != RECS_OK) return st;
+    if ((st = need_column(c, arch, g.comp[1], 12, &acc)) != RECS_OK) return st;
+    if ((st = need_column(c, arch, g.comp[2], 4, &mass)) != RECS_OK) return st;
+    if ((st = same_count(c, pos, vel)) != RECS_OK || (st = same_count(c, pos, acc)) != RECS_OK) return st;
+    const uint64_t n = pos->count;
+    const uint64_t n_pad = (n + kGravTile - 1) / kGravTile * kGravTile;
+    if (c->posm_bodies != n_pad || c->posm_scaled || !posm_is_current(c))
+        return fail(c, RECS_ERR_UNSUPPORTED, "resident ticks need the current unscaled mirror of the archetype");
+    if ((st = ensure(c, &c->posm_alt, &c->posm_alt_cap, n_pad * 16)) != RECS_OK) return st;
+    if (!c->resident_barrier) RECS_CUDA(c, cudaMalloc((void**)&c->resident_barrier, 256));
+    RECS_CUDA(c, cudaMemsetAsync(c->resident_barrier, 0, 4, c->stream));
+    RECS_CUDA(c, cudaMemcpyAsync(c->posm_alt, c->posm, n_pad * 16, cudaMemcpyDeviceToDevice, c->stream));  // G*m and the null bodies
+    ResidentTicksArgs ra;
+    memset(&ra, 0, sizeof ra);
+    ra.posm[0] = c->posm;
+    ra.posm[1] = c->posm_alt;
+    ra.pos = (float*)pos->dev;
+    ra.vel = (float*)vel->dev;
+    ra.acc = (float*)acc->dev;
+    ra.n_rows = (uint32_t)n;
+    ra.n_tiles = (uint32_t)(n_pad / kGravTile);
+    ra.n_ticks = n_ticks;
+    ra.dt = c->cfg.nbody_dt;
+    ra.eps = c->cfg.nbody_epsilon;
+    ra.barrier = c->resident_barrier;
+    ra.error = c->dev_error;
+    {
+        NvtxRange range("resident ticks");
+        RECS_CUDA(c, launch_resident_ticks(ra, c->stream));
+    }
+    c->kernel_launches++;
+    c->gravity_launches++;
+    c->resident_launches++;
+    if (n_ticks & 1)  // the last tick refreshed the second buffer
+        RECS_CUDA(c, cudaMemcpyAsync(c->posm, c->posm_alt, n_pad * 16, cudaMemcpyDeviceToDevice, c->stream));
+    pos->version += n_ticks;
+    vel->version += n_ticks;
+    acc->version += n_ticks;
+    for (auto& src : c->posm_sources) src.second = find_column(c, src.first.first, src.first.second)->version;
+    return RECS_OK;
+}
+
 int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
     RECS_ENTER(c);
     if (n_ticks == 0 || c->order.empty()) return RECS_OK;
+    if (n_ticks >= 3 && !c->capturing && resident_ticks_apply(c)) {
+        // the first tick through the ordinary chain (binds, sizes, packs the mirror if a column changed), the rest in one launch
+        int32_t st = run_tick_once(c);
+        if (st != RECS_OK) return st;
+        return run_resident_ticks(c, n_ticks - 1);
+    }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {
         e0 = get_event(c);

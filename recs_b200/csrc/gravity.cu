@@ -770,6 +770,102 @@ __global__ void __launch_bounds__(256) pack_posm_kernel(const float* __restrict_
     push_end(push);
 }
 
+// ---- small worlds: many ticks in ONE launch ------------------------------------------------------------------------------
+// At the reference's own benchmark size (1 000 bodies x 100 ticks, crates/ecs_bench_suite/benches/n_body.rs:4) a tick is a
+// microsecond of arithmetic behind two kernel launches.  This kernel runs the whole fused tick (gravity -> movement ->
+// acceleration, one body archetype) for n_ticks ticks: a cooperative grid of one CTA per 32 rows, warp = j tile, lane = row;
+// every CTA bulk-copies the whole mirror (<= 64 KiB) into shared memory once per tick, a row's tile sums meet in shared
+// memory and warp 0 adds them in tile order, integrates the row in registers (position and velocity never leave them
+// between ticks) and stores the refreshed mirror entry into the OTHER mirror buffer (tick k reads buffer k & 1: a CTA may
+// still be loading the current one); one grid-wide barrier per tick.
+// Same arithmetic, same summation tree (tile sum from zero, K = 1 chunk = 0 + tile sum, row total from zero in tile order)
+// and same roundings as nbody_gravity_kernel<2, 3, 8, false, 4> + nbody_gravity_reduce_kernel, which is what the same
+// sizes run tick by tick: results are bit-identical (tests/test_gpu_nbody.py::test_resident_ticks_equal_single_ticks).
+__global__ void __launch_bounds__(512, 1) nbody_resident_ticks_kernel(const ResidentTicksArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4* mirror = reinterpret_cast<float4*>(smem_raw);  // n_tiles x 256 bodies, pair-interleaved
+    float4* sums = mirror + static_cast<size_t>(a.n_tiles) * kGravTile;  // [tile][row of the CTA]
+    __shared__ __align__(8) uint64_t full_bar;
+    __shared__ uint32_t stop;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row = blockIdx.x * 32u + lane;
+    const bool valid = row < a.n_rows;
+    const size_t o = static_cast<size_t>(row >> 1) * 8 + (row & 1);  // float index of x in the mirror; y, z, gm at +2, +4, +6
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(&full_bar, 1);
+        ptx::mbar_fence_init();
+        stop = 0;
+    }
+    __syncthreads();
+    float px = 0.f, py = 0.f, pz = 0.f, vx = 0.f, vy = 0.f, vz = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+    if (warp == 0 && valid) {
+        px = a.pos[3ull * row], py = a.pos[3ull * row + 1], pz = a.pos[3ull * row + 2];
+        vx = a.vel[3ull * row], vy = a.vel[3ull * row + 1], vz = a.vel[3ull * row + 2];
+    }
+    const uint32_t bytes = a.n_tiles * kGravTileBytes;
+    for (uint32_t k = 0; k < a.n_ticks; ++k) {
+        const float* src = (k & 1u) ? a.posm[1] : a.posm[0];
+        float* dst = (k & 1u) ? a.posm[0] : a.posm[1];
+        if (threadIdx.x == 0) {
+            // the other CTAs' stores of the previous tick (generic proxy, acquired at the barrier) before the bulk read
+            ptx::fence_proxy_async_global();
+            ptx::mbar_arrive_expect_tx(&full_bar, bytes);
+            ptx::bulk_g2s(mirror, src, bytes, &full_bar);
+        }
+        ptx::mbar_wait(&full_bar, k & 1u);
+        const float* mf = reinterpret_cast<const float*>(mirror);
+        float fx = 0.f, fy = 0.f, fz = 0.f;
+        if (valid) {
+            const float nxi[1] = {mf[o]}, nyi[1] = {mf[o + 2]}, nzi[1] = {mf[o + 4]};
+            f32x2 ax[1] = {0ull}, ay[1] = {0ull}, az[1] = {0ull};
+            float dmin[1] = {3.0e38f};
+            tile_loop<1, 8, true>(mirror + static_cast<size_t>(warp) * kGravTile, nxi, nyi, nzi, a.eps, ax, ay, az, dmin);
+            float x0, x1, y0, y1, z0, z1;
+            ptx::unpack(ax[0], x0, x1);
+            ptx::unpack(ay[0], y0, y1);
+            ptx::unpack(az[0], z0, z1);
+            // even + odd bodies of the tile, then the chunk of one tile: its running prefix starts from zero
+            fx = 0.f + (x0 + x1);
+            fy = 0.f + (y0 + y1);
+            fz = 0.f + (z0 + z1);
+        }
+        sums[warp * 32u + lane] = make_float4(fx, fy, fz, 0.f);
+        __syncthreads();
+        if (warp == 0 && valid) {
+            sx = sy = sz = 0.f;  // `.sum()` starts from zero (crates/n-body/src/lib.rs:129-133)
+            for (uint32_t t = 0; t < a.n_tiles; ++t) {
+                const float4 f = sums[t * 32u + lane];
+                sx += f.x, sy += f.y, sz += f.z;
+            }
+            // movement (:92), then acceleration (:101): separate roundings like the Rust code
+            px = __fadd_rn(px, __fmul_rn(vx, a.dt));
+            py = __fadd_rn(py, __fmul_rn(vy, a.dt));
+            pz = __fadd_rn(pz, __fmul_rn(vz, a.dt));
+            vx = __fadd_rn(vx, __fmul_rn(sx, a.dt));
+            vy = __fadd_rn(vy, __fmul_rn(sy, a.dt));
+            vz = __fadd_rn(vz, __fmul_rn(sz, a.dt));
+            dst[o] = px, dst[o + 2] = py, dst[o + 4] = pz;  // (G*m is in both buffers and does not change)
+        }
+        __syncthreads();  // the mirror and the sums are free; this CTA's stores are issued
+        if (k + 1 < a.n_ticks) {
+            if (threadIdx.x == 0) {
+                __threadfence();
+                atomicAdd(a.barrier, 1u);
+                // bounded: a grid that is not co-resident (never the case for a cooperative launch) ends in an error, not a hang
+                // (every CTA waits for the same count, so all of them give up at the same tick)
+                if (!ptx::wait_generation(a.barrier, (k + 1u) * gridDim.x, a.error, 2000000000ull)) stop = 1;
+            }
+            __syncthreads();
+            if (stop) break;
+        }
+    }
+    if (warp == 0 && valid) {
+        a.pos[3ull * row] = px, a.pos[3ull * row + 1] = py, a.pos[3ull * row + 2] = pz;
+        a.vel[3ull * row] = vx, a.vel[3ull * row + 1] = vy, a.vel[3ull * row + 2] = vz;
+        a.acc[3ull * row] = sx, a.acc[3ull * row + 1] = sy, a.acc[3ull * row + 2] = sz;
+    }
+}
+
 }  // namespace
 
 namespace {
@@ -864,6 +960,25 @@ cudaError_t launch_gravity_chunksum(const GravityReduceArgs& a, cudaStream_t s) 
     const uint32_t heavy_rows = a.row_count - a.work.heavy_iblock * a.iblock_rows;
     nbody_gravity_chunksum_kernel<<<(heavy_rows + 7) / 8, 256, 0, s>>>(a);
     return cudaGetLastError();
+}
+
+static size_t resident_smem_bytes(uint32_t n_tiles) { return (size_t)n_tiles * (kGravTileBytes + 32 * sizeof(float4)); }
+
+cudaError_t launch_resident_ticks(const ResidentTicksArgs& a, cudaStream_t s) {
+    if (a.n_ticks == 0 || a.n_rows == 0) return cudaSuccess;
+    if (a.n_tiles == 0 || a.n_tiles > kResidentMaxTiles) return cudaErrorInvalidValue;
+    static bool prepared = false;
+    if (!prepared) {
+        cudaError_t e = cudaFuncSetAttribute(nbody_resident_ticks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)resident_smem_bytes(kResidentMaxTiles));
+        if (e != cudaSuccess) return e;
+        prepared = true;
+    }
+    ResidentTicksArgs args = a;
+    void* params[1] = {&args};
+    // cooperative: all CTAs resident at once, or the launch fails -- the grid barrier cannot wait for a CTA that never starts
+    return cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(nbody_resident_ticks_kernel), dim3((a.n_rows + 31) / 32),
+                                       dim3(32 * a.n_tiles), params, resident_smem_bytes(a.n_tiles), s);
 }
 
 cudaError_t launch_pack_posm(const float* pos, const float* mass, float g, float* posm,

@@ -178,6 +178,23 @@ cudaError_t launch_gravity_reduce(const GravityReduceArgs& a, cudaStream_t s);
 // Chunk sums of the rows of the separately dealt last i-block (a.work.heavy_iblock): one warp per row, lanes = chunks.
 cudaError_t launch_gravity_chunksum(const GravityReduceArgs& a, cudaStream_t s);
 
+// Many fused n-body ticks of a small single-archetype world in one cooperative launch (gravity.cu).
+constexpr uint32_t kResidentMaxTiles = 16;  // mirror of up to 4 096 bodies in shared memory, 32 x tiles threads per CTA
+struct ResidentTicksArgs {
+    float* posm[2];    // two pair-interleaved mirror buffers holding the same G*m; tick k reads [k & 1] and refreshes the other
+    float* pos;        // Position, Velocity, Acceleration columns of the archetype (row 0 = mirror body 0)
+    float* vel;
+    float* acc;
+    uint32_t n_rows;
+    uint32_t n_tiles;  // mirror size / 256
+    uint32_t n_ticks;
+    float dt;
+    float eps;
+    uint32_t* barrier; // zero before the launch
+    uint32_t* error;   // raised if the grid barrier times out
+};
+cudaError_t launch_resident_ticks(const ResidentTicksArgs& a, cudaStream_t s);
+
 // Position(12 B) + Mass(4 B) rows [row_begin, row_begin + n) -> pair-interleaved posm bodies [dst_offset, dst_offset+n),
 // gm = G * m rounded once like the reference's `GRAVITATIONAL_CONSTANT * body_mass`; bodies [dst_offset + n,
 // dst_offset + n + n_pad) become null bodies (gm = 0) so partially filled tiles contribute nothing.  With

@@ -152,6 +152,35 @@ def test_100_ticks_config0_drift(nbody_oracle, use_graph):
     assert abs(drift["gpu"] - drift["f64"]) <= 1e-6 + 2.0 * abs(drift["ref32"] - drift["f64"])
 
 
+@pytest.mark.parametrize("n,ticks", [(1, 3), (2, 4), (31, 5), (33, 3), (255, 4), (257, 7), (1000, 100), (1000, 101), (1536, 6), (2048, 9), (3000, 5), (4096, 4)])
+def test_resident_ticks_equal_single_ticks(monkeypatch, n, ticks):
+    """Small single-archetype worlds run `recs_gpu_tick(n)` as one cooperative launch (nbody_resident_ticks_kernel) after
+    the first tick.  Same arithmetic, same summation tree: every column must equal the tick-by-tick chain bit for bit,
+    and the mirror it leaves behind must be the one the next ordinary tick needs."""
+    from recs_b200 import GpuContext
+
+    outs, launches = [], []
+    for resident in (True, False):
+        if not resident:
+            monkeypatch.setenv("RECS_GPU_RESIDENT_MAX_ROWS", "0")
+        with GpuContext(device=0, use_cuda_graph=False) as ctx:
+            app, host = _app(ctx, n, seed=9)
+            if n >= 4:  # a coincident pair and a sub-epsilon neighbour: the masked pairs of the reference
+                app.pos[1] = app.pos[0]
+                app.pos[3] = app.pos[2] + np.float32(1e-5)
+                app.upload()
+            app.tick(ticks)
+            launches.append(ctx.timing()["kernel_launches"])
+            assert resident or launches[-1] >= 2 * ticks
+            app.tick(1)       # an ordinary tick on the mirror the resident launch left
+            app.tick(ticks)   # and a resident launch on a mirror that needs no pack
+            app.download()
+            outs.append((app.pos.copy(), app.vel.copy(), app.acc.copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert launches[0] <= 4, launches  # pack + tick 1 (2 launches) + ONE launch for the rest
+
+
 def test_graph_and_eager_ticks_agree_bitwise():
     from recs_b200 import GpuContext
 
