@@ -849,11 +849,9 @@ __global__ void __launch_bounds__(512, 1) nbody_resident_ticks_kernel(const Resi
         __syncthreads();  // the mirror and the sums are free; this CTA's stores are issued
         if (k + 1 < a.n_ticks) {
             if (threadIdx.x == 0) {
-                __threadfence();
-                atomicAdd(a.barrier, 1u);
                 // bounded: a grid that is not co-resident (never the case for a cooperative launch) ends in an error, not a hang
                 // (every CTA waits for the same count, so all of them give up at the same tick)
-                if (!ptx::wait_generation(a.barrier, (k + 1u) * gridDim.x, a.error, 2000000000ull)) stop = 1;
+                if (!ptx::grid_barrier(a.barrier, (k + 1u) * gridDim.x, a.error)) stop = 1;
             }
             __syncthreads();
             if (stop) break;

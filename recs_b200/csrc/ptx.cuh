@@ -148,5 +148,28 @@ __device__ __forceinline__ bool wait_generation(const uint32_t* flag, uint32_t g
     return true;
 }
 
+// ---- grid-wide barrier of a cooperative launch (one GPU) ---------------------------------------------------------
+// One thread per CTA: arrive (release, gpu scope: this CTA's earlier stores, ordered before by the CTA barrier, become
+// visible with it) and spin until `target` arrivals have been counted since the launch.  Tight spin -- the wait is a
+// microsecond -- but bounded like wait_generation.
+__device__ __forceinline__ bool grid_barrier(uint32_t* counter, uint32_t target, uint32_t* error,
+                                             unsigned long long timeout_ns = 2000000000ull) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    uint32_t v, spins = 0;
+    unsigned long long t0 = 0;
+    for (;;) {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (static_cast<int32_t>(v - target) >= 0) return true;
+        if ((++spins & 4095u) == 0) {
+            if (t0 == 0) {
+                t0 = globaltimer_ns();
+            } else if (globaltimer_ns() - t0 > timeout_ns) {
+                if (error) *reinterpret_cast<volatile uint32_t*>(error) = 1u;
+                return false;
+            }
+        }
+    }
+}
+
 }  // namespace ptx
 }  // namespace recs
