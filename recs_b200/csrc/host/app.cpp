@@ -185,6 +185,8 @@ struct recs_app {
     // context as ONE chain (recs_gpu_set_tick_order + recs_gpu_tick), so its fusions apply through the Application too
     // (gravity -> movement -> acceleration in the reduce tail, wind -> gravity -> movement in one pass).
     std::vector<uint32_t> gpu_chain;
+    uint32_t chains_flushed = 0;  // in the current tick
+    uint32_t last_chain_len = 0;
     std::mutex command_mu;             // Commands may be recorded from several worker threads at once
     std::string error;
 
@@ -253,6 +255,8 @@ int32_t flush_gpu_chain(recs_app* app) {
     if (app->gpu_chain.empty()) return RECS_OK;
     int32_t st = recs_gpu_set_tick_order(app->gpu, app->gpu_chain.data(), (uint32_t)app->gpu_chain.size());
     if (st == RECS_OK) st = recs_gpu_tick(app->gpu, 1);
+    app->chains_flushed++;
+    app->last_chain_len = (uint32_t)app->gpu_chain.size();
     app->gpu_chain.clear();
     return st == RECS_OK ? RECS_OK : gpu_fail(app, st);
 }
@@ -855,6 +859,19 @@ int32_t recs_app_set_executor(recs_app* app, uint32_t worker_threads) {
     return RECS_OK;
 }
 
+namespace {
+bool whole_tick_is_one_gpu_chain(recs_app* app) {
+    if (!app->gpu || app->systems.empty() || app->chains_flushed != 1 || app->last_chain_len != app->systems.size()) return false;
+    for (const AppSystem& s : app->systems) {
+        if (!s.gpu || s.decides_removals || !s.create_comps.empty()) return false;
+        if (s.kind == RECS_SYS_NBODY_COLLISION || s.kind == RECS_SYS_RAIN_GROUND_COLLISION) return false;
+        if (s.kind == RECS_SYS_RAIN_WIND_DIRECTION) return false;  // a host-side per-tick value
+    }
+    std::lock_guard<std::mutex> lock(app->command_mu);
+    return app->creates.empty() && app->removes.empty();
+}
+}  // namespace
+
 int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
     int32_t st = ensure_schedule(app, ordered ? 1 : 0);
@@ -862,6 +879,7 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
     std::vector<uint32_t> batch(app->systems.size() + 1);
     for (uint32_t tick = 0; tick < n_ticks; ++tick) {
         app->gpu_chain.clear();  // nothing survives a tick (or an error return)
+        app->chains_flushed = 0;
         app->gpu_create_sources.clear();
         app->last_order.clear();
         app->last_batch.clear();
@@ -913,6 +931,14 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
         if ((st = flush_gpu_chain(app)) != RECS_OK) return st;
         // loop { runner.tick(); runner.playback_commands(); } (lib.rs:321-323)
         if ((st = playback_commands(app)) != RECS_OK) return st;
+        // A tick that was ONE chain of GPU systems holding every system of the application, none of which can record a
+        // command: nothing on the host changes from tick to tick (same batches, same archetypes, no playback), so the
+        // remaining ticks are the same chain again -- handed to the context in one call, which captures it in a CUDA graph
+        // or, for a small n-body world, runs all of them in one cooperative launch (recs_gpu_tick).
+        if (tick + 1 < n_ticks && whole_tick_is_one_gpu_chain(app)) {
+            st = recs_gpu_tick(app->gpu, n_ticks - tick - 1);  // (the tick order is the one flush_gpu_chain just set)
+            return st == RECS_OK ? RECS_OK : gpu_fail(app, st);
+        }
     }
     return RECS_OK;
 }

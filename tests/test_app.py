@@ -289,3 +289,40 @@ def test_application_hands_gpu_chains_to_the_context_as_one(gpu_ctx, nbody_oracl
         assert rel_err_rows(w.column(1, VEL)[:n], ref[2], floor=1.0).max() <= 1e-4, names
         assert rel_err_rows(w.column(1, ACC)[:n], ref[3]).max() <= 1e-3, names
         app.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1000, 6000])
+def test_application_of_gpu_systems_only_hands_the_remaining_ticks_over_in_one_call(gpu_ctx, nbody_oracle, n):
+    """An application whose every system is a GPU system of one chain and cannot record commands repeats the same chain
+    every tick: recs_app_run gives ticks 2..n to the context in one recs_gpu_tick call (CUDA graph, or for a small n-body
+    world ONE cooperative launch).  Columns equal the tick-by-tick run bit for bit."""
+    ticks = 12
+    outs, launches = [], []
+    for one_by_one in (False, True):
+        gpu_ctx.reset_timing()
+        app = ecs.Application(gpu=gpu_ctx)
+        w = app.world
+        for c, dt, name in ((POS, F3, "Position"), (MASS, np.float32, "Mass"), (VEL, F3, "Velocity"), (ACC, F3, "Acceleration")):
+            w.register_component(c, dt, name)
+        pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 5)
+        app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+        app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+        app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+        w.create_entities(n, {POS: pos, MASS: mass, VEL: vel, ACC: acc})
+        if one_by_one:
+            for _ in range(ticks):
+                app.run(1)
+        else:
+            app.run(ticks)
+        launches.append(gpu_ctx.timing()["kernel_launches"])
+        order, _ = app.last_tick_order()
+        assert [app.system_names[i] for i in order] == ["gravity", "movement", "acceleration"]
+        app.sync_to_host()
+        outs.append([w.column(1, c)[:n].copy() for c in (POS, VEL, ACC)])
+        app.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert launches[1] >= 2 * ticks
+    if n <= 4096:
+        assert launches[0] <= 6, launches  # pack, tick 1, tick 2 (first of the handed-over call), one launch for the rest
