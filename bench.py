@@ -444,7 +444,9 @@ def config_subrecord(n, ticks_per_step, steps, device, traffic, scenes, cpu_orc,
         value = n * n * ticks_per_step / (ms_step * 1e-3) / 1e9
         roof, _ = kernel_roofline(ctx, app, n, n, 10, traffic)
         if ticks_per_step > 1:
-            roof["note"] = "launch-bound at this size: the tick is two small launches inside a CUDA graph (interaction kernel, reduce + integration tail)"
+            roof["note"] = ("latency-bound at this size: ticks 2..n of a recs_gpu_tick(n) call run in ONE cooperative launch "
+                            "(nbody_resident_ticks_kernel, one grid barrier per tick; bit-identical to the chain); this block times "
+                            "the interaction kernel of the tick-by-tick chain (two launches per tick), which is what timing mode runs")
         # end to end at this size: upload inputs, tick(s), download results
         e0 = time.perf_counter()
         e_steps = max(3, min(steps, 20))
