@@ -1884,7 +1884,8 @@ bool resident_ticks_apply(recs_gpu_ctx* c) {
     return p && p->count >= 1 && p->count <= c->resident_max_rows && p->count <= kGravSmallRows;
 }
 
-int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks) {
+int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
+    *launched = true;
     System& g = c->systems[c->order[0]];
     const uint32_t arch = g.archs[0];
     Column *pos, *vel, *acc, *mass;
@@ -1918,7 +1919,14 @@ int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks) {
     ra.error = c->dev_error;
     {
         NvtxRange range("resident ticks");
-        RECS_CUDA(c, launch_resident_ticks(ra, c->stream));
+        const cudaError_t e = launch_resident_ticks(ra, c->stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge) {
+            // the grid cannot be co-resident on this device (fewer SMs than CTAs): the ordinary chain runs the ticks
+            cudaGetLastError();
+            *launched = false;
+            return RECS_OK;
+        }
+        RECS_CUDA(c, e);
     }
     c->kernel_launches++;
     c->gravity_launches++;
@@ -1939,7 +1947,11 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
         // the first tick through the ordinary chain (binds, sizes, packs the mirror if a column changed), the rest in one launch
         int32_t st = run_tick_once(c);
         if (st != RECS_OK) return st;
-        return run_resident_ticks(c, n_ticks - 1);
+        bool launched = false;
+        st = run_resident_ticks(c, n_ticks - 1, &launched);
+        if (st != RECS_OK || launched) return st;
+        c->resident_max_rows = 0;  // not on this device: the chain below, now and from here on
+        --n_ticks;
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {

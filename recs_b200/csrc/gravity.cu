@@ -928,7 +928,8 @@ cudaError_t gravity_prepare() {
                                              gravity_smem_bytes(v));
         if (e != cudaSuccess) return e;
     }
-    return cudaSuccess;
+    return cudaFuncSetAttribute(nbody_resident_ticks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)((size_t)kResidentMaxTiles * (kGravTileBytes + 32 * sizeof(float4))));
 }
 
 int gravity_max_ctas_per_sm(int variant) {
@@ -965,13 +966,6 @@ static size_t resident_smem_bytes(uint32_t n_tiles) { return (size_t)n_tiles * (
 cudaError_t launch_resident_ticks(const ResidentTicksArgs& a, cudaStream_t s) {
     if (a.n_ticks == 0 || a.n_rows == 0) return cudaSuccess;
     if (a.n_tiles == 0 || a.n_tiles > kResidentMaxTiles) return cudaErrorInvalidValue;
-    static bool prepared = false;
-    if (!prepared) {
-        cudaError_t e = cudaFuncSetAttribute(nbody_resident_ticks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)resident_smem_bytes(kResidentMaxTiles));
-        if (e != cudaSuccess) return e;
-        prepared = true;
-    }
     ResidentTicksArgs args = a;
     void* params[1] = {&args};
     // cooperative: all CTAs resident at once, or the launch fails -- the grid barrier cannot wait for a CTA that never starts
