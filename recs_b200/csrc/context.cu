@@ -413,7 +413,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
     }
 
     // kernel shape by outer-row count (profiles/r01_gravity_small_n_sweep.txt, r01_gravity_variant_sweep5.txt):
-    // small i-blocks give the stream-K split more units, and below 16 384 rows the redo of the tile that holds a
+    // small i-blocks give the stream-K split more units, and below 5 120 bodies the redo of the tile that holds a
     // warp's own bodies is a large enough share that masking every pair exactly is cheaper
     int variant = c->grav_variant;
     if (!c->grav_variant_forced) {

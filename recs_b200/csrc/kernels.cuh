@@ -33,8 +33,8 @@ constexpr int kGravVariantCount = 9;
 constexpr int kGravVariantDefault = 0;
 constexpr int kGravVariantSmall = 2;    // up to kGravSmallRows outer rows
 constexpr int kGravVariantMedium = 3;   // up to kGravMediumRows outer rows
-constexpr uint64_t kGravSmallRows = 16384;
-constexpr uint64_t kGravMediumRows = 49152;
+constexpr uint64_t kGravSmallRows = 5120;    // (profiles/r02_shape_thresholds.txt)
+constexpr uint64_t kGravMediumRows = 22528;
 GravityVariant gravity_variant(int index);
 
 // Range shift of the overflow-detector variants: positions x 2^-32 (exact power-of-two scaling, G*m unscaled);

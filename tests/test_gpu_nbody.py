@@ -280,7 +280,7 @@ def test_other_tick_orders_follow_the_oracle(gpu_ctx, nbody_oracle, order):
     assert rel_err_rows(app.acc, acc).max() <= 1e-4
 
 
-@pytest.mark.parametrize("n", [16384, 16385, 49152, 49153])
+@pytest.mark.parametrize("n", [5120, 5121, 16384, 22528, 22529, 49153])
 def test_kernel_shape_switch_sizes(gpu_ctx, nbody_oracle, n):
     """Sizes on both sides of the small / medium / default kernel-shape switches."""
     app, (pos, mass, vel, acc) = _app(gpu_ctx, n, seed=3)
@@ -527,7 +527,7 @@ def test_result_does_not_depend_on_grid_or_rank_split(monkeypatch, n):
                  # at 70 000 rows the partly filled last i-block is dealt by itself (phases of its own, chunk sums in a
                  # separate launch); switching that off, alone and inside an emulated rank, must change nothing
                  {"RECS_GPU_GRAVITY_NO_LAST_SPLIT": "1"}, {"RECS_GPU_GRAVITY_NO_LAST_SPLIT": "1", "RECS_GPU_GRAVITY_EMULATE_RANK": "4,1"})
-                if n > 16384 else ()):
+                if n > 5120 else ()):
         got = run(env)
         for a, b, what in zip(got, base, ("pos", "vel", "acc")):
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{what} differs with {env}"
