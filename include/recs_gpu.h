@@ -283,7 +283,15 @@ int32_t recs_gpu_system_set_uniform(recs_gpu_ctx* ctx, uint32_t system_id, const
  * row order); finish(...).  One thread per outer entity, query entities staged through shared memory in tiles, so a
  * body that accumulates in call order reproduces the reference's sequential fold bit for bit (--fmad=false, IEEE
  * division and square root).  In a sharded context every rank folds the whole query for the outer rows it owns; the
- * query's columns must be complete on every rank (recs_gpu_column_allgather after a sharded write). */
+ * query's columns must be complete on every rank (recs_gpu_column_allgather after a sharded write).
+ * Optional speculative fast fold: if `source` also defines
+ *     bool <pair_fn>_fast(<the parameters of pair>);
+ * -- a body that does to `acc` exactly what pair does whenever it returns true -- every tile of the nested query is
+ * folded with it first and, only if some call returned false, folded again from the tile's starting accumulator with
+ * pair.  The bodies see helper functions for the purpose: recs_div_rn_seq(a, b) / recs_sqrt_rn_seq(x) are `a / b` and
+ * sqrtf(x) as the branch-free in-range instruction sequences, bit-identical to the operators while
+ * recs_div_in_range(a) & recs_div_in_range(b) / recs_sqrt_in_range(x) hold (operands within 2^-63 .. 2^63 /
+ * 2^-101 .. 2^127).  Results never depend on whether the fast body exists. */
 #define RECS_KPARAM_QUERY_READ 4u
 #define RECS_KPARAM_QUERY_ENTITY 5u
 int32_t recs_gpu_system_create_pair_kernel(recs_gpu_ctx* ctx, const char* name, const char* source,

@@ -72,6 +72,106 @@ def test_generic_gravity_reproduces_the_reference_order_sum_bitwise(gpu_ctx, nbo
     assert np.array_equal(acc.view(np.uint32), want.view(np.uint32))
 
 
+def _strip_fast(source: str) -> str:
+    """The same system without its `pair_fast` body: the generated kernel then folds with the exact body only."""
+    i = source.index("bool pair_fast(")
+    j = source.index("void finish(")
+    return source[:i] + source[j:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("what", ["denormal_gm", "huge_distances", "tiny_distances", "mixed", "nan_and_inf"])
+def test_fast_fold_redoes_tiles_with_out_of_range_pairs(gpu_ctx, nbody_oracle, what):
+    """The speculative fast fold (pair_fast: branch-free division / square-root sequences, valid for operands within
+    2^-63 .. 2^63) must hand every tile holding an out-of-range pair to the exact body: denormal G*m, distances beyond
+    2^31.5 m (d2 > 2^63), d2 below 2^-63 but above zero is masked anyway, quotients that leave the range, NaN / inf
+    positions.  Bit for bit against the CPU oracle AND against the kernel generated without the fast body."""
+    ctx = gpu_ctx
+    n = 1300
+    rng = np.random.default_rng(21)
+    pos, mass, vel, acc = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(n), 17)
+    if what in ("denormal_gm", "mixed"):
+        mass[rng.choice(n, 40, replace=False)] = np.float32(1e-30)   # G*m = 6.67e-41: denormal
+        mass[rng.choice(n, 5, replace=False)] = np.float32(0.0)
+    if what in ("huge_distances", "mixed"):
+        pos[rng.choice(n, 30, replace=False)] *= np.float32(3e7)     # d2 ~ 1e21..1e25 > 2^63
+        pos[rng.choice(n, 3, replace=False)] = np.float32(1e19)      # d2 overflows to inf
+    if what in ("tiny_distances", "mixed"):
+        k = rng.choice(n - 1, 30, replace=False)
+        pos[k + 1] = pos[k] + rng.uniform(-4e-4, 4e-4, (30, 3)).astype(np.float32)  # around epsilon: some masked, some huge quotients
+        mass[k] = np.float32(3e33)                                   # acceleration beyond 2^63
+    if what == "nan_and_inf":
+        pos[5, 1] = np.float32(np.nan)
+        pos[700] = np.float32(np.inf)
+    got = {}
+    for name, src in (("fast", GRAVITY), ("exact", _strip_fast(GRAVITY))):
+        out = np.zeros_like(acc)
+        for comp, arr in ((POS, pos), (MASS, mass), (ACC, out)):
+            _bind(ctx, 1, comp, arr)
+        sid = ctx.create_pair_kernel_system("gravity_" + name, src, "Total", "pair", "finish", GRAVITY_PARAMS)
+        ctx.set_archetypes(sid, [1])
+        ctx.set_query_archetypes(sid, [1])
+        ctx.run_system(sid)
+        ctx.download(1, ACC)
+        got[name] = out
+    with np.errstate(all="ignore"):
+        want = nbody_oracle.gravity(pos, mass)
+    same = lambda a, b: np.array_equal(a.view(np.uint32), b.view(np.uint32)) or np.array_equal(  # NaN payloads may differ
+        np.where(np.isnan(a), np.float32(0), a).view(np.uint32), np.where(np.isnan(b), np.float32(0), b).view(np.uint32)) and np.array_equal(np.isnan(a), np.isnan(b))
+    assert same(got["fast"], got["exact"])
+    assert same(got["fast"], want)
+
+
+DIV_SQRT_PROBE = """
+struct Pair { float a, b; };
+struct Out { float q, s; int in_range; };
+void probe(const Pair& p, Out& o) {
+    o.q = recs_div_rn_seq(p.a, p.b);
+    o.s = recs_sqrt_rn_seq(p.b);
+    o.in_range = (recs_div_in_range(p.a) & recs_div_in_range(p.b) ? 1 : 0) | (recs_sqrt_in_range(p.b) ? 2 : 0);
+}
+"""
+
+
+@pytest.mark.gpu
+def test_division_and_square_root_sequences_are_ieee_in_range(gpu_ctx):
+    """recs_div_rn_seq / recs_sqrt_rn_seq (the generated kernels' branch-free helpers) against numpy's correctly rounded
+    float32 division and square root: bit for bit on every operand pair their range tests admit, over four million pairs
+    with exponents drawn across (and beyond) the admitted ranges, mantissas random and special (powers of two, all-ones)."""
+    ctx = gpu_ctx
+    n = 1 << 22
+    rng = np.random.default_rng(5)
+
+    def floats(lo_exp, hi_exp):
+        e = rng.integers(lo_exp + 127, hi_exp + 128, n).astype(np.uint32)
+        m = rng.integers(0, 1 << 23, n).astype(np.uint32)
+        special = rng.integers(0, 16, n)
+        m = np.where(special == 0, 0, np.where(special == 1, (1 << 23) - 1, np.where(special == 2, 1, m))).astype(np.uint32)
+        sign = (rng.integers(0, 2, n).astype(np.uint32) << 31)
+        return ((e << 23) | m | sign).view(np.float32)
+
+    pairs = np.zeros((n, 2), np.float32)
+    pairs[:, 0] = floats(-70, 70)
+    pairs[:, 1] = np.abs(floats(-110, 127))
+    out = np.zeros(n, dtype=np.dtype([("q", np.float32), ("s", np.float32), ("in_range", np.int32)]))
+    _bind(ctx, 3, 31, pairs)
+    _bind(ctx, 3, 32, out)
+    sid = ctx.create_kernel_system("probe", DIV_SQRT_PROBE, "probe", [(31, 8, "read", "Pair"), (32, 12, "write", "Out")])
+    ctx.set_archetypes(sid, [3])
+    ctx.run_system(sid)
+    ctx.download(3, 32)
+    with np.errstate(all="ignore"):
+        q = pairs[:, 0] / pairs[:, 1]
+        s = np.sqrt(pairs[:, 1])
+    div_ok = (out["in_range"] & 1) != 0
+    sqrt_ok = (out["in_range"] & 2) != 0
+    assert div_ok.sum() > n // 4 and sqrt_ok.sum() > n // 2
+    a, b = np.abs(pairs[:, 0]), pairs[:, 1]
+    assert np.array_equal(div_ok, (a >= 2.0 ** -63) & (a <= 2.0 ** 63) & (b >= 2.0 ** -63) & (b <= 2.0 ** 63))
+    assert np.array_equal(out["q"][div_ok].view(np.uint32), q[div_ok].view(np.uint32))
+    assert np.array_equal(out["s"][sqrt_ok].view(np.uint32), s[sqrt_ok].view(np.uint32))
+
+
 @pytest.mark.gpu
 def test_generic_gravity_over_several_archetypes_follows_query_order(gpu_ctx, nbody_oracle):
     """Outer rows in two archetypes, nested query over three (one of them not an outer archetype, one empty): every outer
