@@ -172,6 +172,8 @@ struct recs_gpu_ctx {
     // CUDA graph of one tick
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_epoch = ~0ull;
+    uint32_t graph_ticks = 1;        // ticks held by the captured graph
+    uint32_t graph_ticks_wanted = 8; // RECS_GPU_GRAPH_TICKS: 1-2 us per tick less than one graph launch per tick at 5 000 .. 16 384 bodies
     bool capturing = false;
     bool graph_elided_pack = false;  // the captured tick found the mirror current and holds no pack kernel
 
@@ -1297,6 +1299,7 @@ int32_t recs_gpu_create(const recs_gpu_config* cfg, recs_gpu_ctx** out_ctx) {
         if (const char* g = getenv("RECS_GPU_GRAVITY_GRID")) c->grav_grid_forced = atoi(g);
         c->grav_no_heavy = getenv("RECS_GPU_GRAVITY_NO_LAST_SPLIT") != nullptr;
         if (const char* r = getenv("RECS_GPU_RESIDENT_MAX_ROWS")) c->resident_max_rows = (uint64_t)atoll(r);
+        if (const char* t = getenv("RECS_GPU_GRAPH_TICKS")) c->graph_ticks_wanted = (uint32_t)std::max(1, std::min(64, atoi(t)));
         if (c->resident_max_rows > (uint64_t)kResidentMaxTiles * kGravTile) c->resident_max_rows = (uint64_t)kResidentMaxTiles * kGravTile;
         if (const char* e = getenv("RECS_GPU_GRAVITY_EMULATE_RANK")) {
             int R = 0, r = 0;
@@ -1965,7 +1968,8 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
         // a captured tick that found the gravity mirror current holds no pack kernel: it is only valid while nothing
         // outside the chain (recs_gpu_run_system, an upload) has written the mirror's source columns since
         if (c->graph && c->graph_elided_pack && !posm_is_current(c)) drop_graph(c);
-        if (!c->graph || c->graph_epoch != c->epoch) {
+        const uint32_t per_graph = std::max(1u, std::min(c->graph_ticks_wanted, (n_ticks - 1) / 2));
+        if (!c->graph || c->graph_epoch != c->epoch || c->graph_ticks != per_graph) {
             drop_graph(c);
             // one eager tick sizes every workspace, then the same chain is captured
             int32_t st = run_tick_once(c);
@@ -1975,8 +1979,9 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
             cudaGraph_t g = nullptr;
             RECS_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
             c->capturing = true;
-            st = run_tick_once(c);
+            for (uint32_t k = 0; k < per_graph && st == RECS_OK; ++k) st = run_tick_once(c);
             c->capturing = false;
+            c->graph_ticks = per_graph;
             cudaError_t ce = cudaStreamEndCapture(c->stream, &g);
             if (st != RECS_OK) {
                 if (g) cudaGraphDestroy(g);
@@ -1988,7 +1993,7 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
             RECS_CUDA(c, ce);
             c->graph_epoch = epoch;
         }
-        for (; done < n_ticks; ++done) RECS_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
+        for (; done + c->graph_ticks <= n_ticks; done += c->graph_ticks) RECS_CUDA(c, cudaGraphLaunch(c->graph, c->stream));
     }
     for (; done < n_ticks; ++done) {
         int32_t st = run_tick_once(c);
