@@ -705,3 +705,63 @@ def test_drift_65536_bodies_100_ticks(nbody_oracle):
     e_ref = sum(nbody_oracle.total_energy(ref[0], start[1], ref[2]))
     print(f"energy drift 65536 x 100: gpu {abs(e_gpu - e0) / abs(e0):.3e}  reference order {abs(e_ref - e0) / abs(e0):.3e}")
     assert abs(e_gpu - e_ref) / abs(e0) <= 1e-6
+
+
+# ---- every scene the reference defines (crates/n-body/src/scenes.rs:10-47, 179-206) -----------------------------------
+def _reference_scenes():
+    from dataclasses import replace
+
+    one_heavy = lambda seed: tuple(np.concatenate([a, b]) for a, b in zip(          # the demo's set-up (n_body_demo.rs:28-52):
+        scenes.spawn_bodies(scenes.ONE_HEAVY_BODY, seed), scenes.spawn_bodies(scenes.EVERYTHING_LIGHT, seed + 1)))  # a sun among light bodies
+    return {
+        "EVERYTHING_HEAVY": lambda seed: scenes.spawn_bodies(scenes.EVERYTHING_HEAVY, seed),
+        "EVERYTHING_LIGHT": lambda seed: scenes.spawn_bodies(scenes.EVERYTHING_LIGHT, seed),
+        "ONE_HEAVY_BODY+LIGHT": one_heavy,
+        "SMALL_HEAVY_CLUSTERS": lambda seed: scenes.spawn_clusters(scenes.SMALL_HEAVY_CLUSTERS, seed),
+        "SMALL_LIGHT_CLUSTERS": lambda seed: scenes.spawn_clusters(scenes.SMALL_LIGHT_CLUSTERS, seed),
+        "HUGE_HEAVY_CLUSTERS": lambda seed: scenes.spawn_clusters(scenes.HUGE_HEAVY_CLUSTERS, seed),
+        "HUGE_LIGHT_CLUSTERS": lambda seed: scenes.spawn_clusters(scenes.HUGE_LIGHT_CLUSTERS, seed),
+        "HUGE_HEAVY_CLUSTERS x 6000": lambda seed: scenes.spawn_clusters(
+            replace(scenes.HUGE_HEAVY_CLUSTERS, scene=replace(scenes.HUGE_HEAVY_CLUSTERS.scene, body_count=6000)), seed),
+    }
+
+
+@pytest.mark.parametrize("name", list(_reference_scenes()))
+def test_every_reference_scene(nbody_oracle, name):
+    """The reference's own scenes -- uniform cubes heavy and light, one heavy body among light ones, four clusters 100 m and
+    1 km apart -- through (a) the hand-written tick: positions bit-exact after tick 1, accelerations within 1e-4 of the
+    reference-order sum, 20 ticks (one resident launch for the small ones) within the drift bound; (b) the generic
+    reference-order system: accelerations equal to the oracle bit for bit (its fast fold must cope with the light scenes'
+    tiny G*m and the clusters' range of distances)."""
+    from recs_b200 import GpuContext
+    from recs_b200.nbody import NBodyGpuApp, ReferenceOrderNBodyApp
+
+    start = _reference_scenes()[name](31)
+    n = start[0].shape[0]
+    want = [a.copy() for a in start]
+    nbody_oracle.run_sequential(want[0], want[1], want[2], want[3], 1)
+    for app_type in (NBodyGpuApp, ReferenceOrderNBodyApp):
+        cols = [a.copy() for a in start]
+        with GpuContext(device=0) as ctx:
+            app = app_type(ctx, *cols)
+            app.upload()
+            app.tick(1)
+            app.download()
+        assert np.array_equal(cols[0].view(np.uint32), want[0].view(np.uint32)), "positions after tick 1"
+        if app_type is ReferenceOrderNBodyApp:
+            assert np.array_equal(cols[3].view(np.uint32), want[3].view(np.uint32)), "reference-order accelerations"
+            assert np.array_equal(cols[2].view(np.uint32), want[2].view(np.uint32))
+        else:
+            assert rel_err_rows(cols[3], want[3]).max() <= ACC_TOL
+    ticks = 20
+    later = [a.copy() for a in start]
+    nbody_oracle.run_sequential(later[0], later[1], later[2], later[3], ticks)
+    cols = [a.copy() for a in start]
+    with GpuContext(device=0) as ctx:
+        app = NBodyGpuApp(ctx, *cols)
+        app.upload()
+        app.tick(ticks)
+        app.download()
+    assert rel_err_rows(cols[0], later[0], floor=1.0).max() <= 1e-4
+    assert rel_err_rows(cols[2], later[2], floor=1.0).max() <= 1e-4
+    assert n >= 1000
