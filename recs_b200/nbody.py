@@ -70,7 +70,7 @@ class NBodyGpuApp:
 
 # `gravity` as a GENERIC nested-query system (recs_gpu_system_create_pair_kernel): crates/n-body/src/lib.rs:104-135 one
 # expression per line.  Folded in query order with IEEE division / square root and no FMA contraction, it reproduces
-# the reference's sequential f32 sum bit for bit -- the exactness cross-check of the hand-written kernel (about 7x
+# the reference's sequential f32 sum bit for bit -- the exactness cross-check of the hand-written kernel (about 4.5x
 # slower than it).
 REFERENCE_ORDER_GRAVITY_SOURCE = """
 struct Position { float x, y, z; };
