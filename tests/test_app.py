@@ -326,3 +326,43 @@ def test_application_of_gpu_systems_only_hands_the_remaining_ticks_over_in_one_c
     assert launches[1] >= 2 * ticks
     if n <= 4096:
         assert launches[0] <= 6, launches  # pack, tick 1, tick 2 (first of the handed-over call), one launch for the rest
+
+
+@pytest.mark.gpu
+def test_hand_over_survives_structural_changes_between_runs(gpu_ctx, nbody_oracle):
+    """run(k) hands ticks 2..k to the context in one call; entities created and removed between run calls change the
+    archetype under it (columns move, the mirror grows and shrinks, the resident launch's second mirror buffer with it).
+    The same program tick by tick must give the same columns bit for bit."""
+    outs = []
+    for one_by_one in (False, True):
+        app = ecs.Application(gpu=gpu_ctx)
+        w = app.world
+        for c, dt, name in ((POS, F3, "Position"), (MASS, np.float32, "Mass"), (VEL, F3, "Velocity"), (ACC, F3, "Acceleration")):
+            w.register_component(c, dt, name)
+        app.add_gpu_system(_lib.SYS_NBODY_MOVEMENT, [POS, VEL], "movement")
+        app.add_gpu_system(_lib.SYS_NBODY_ACCELERATION, [VEL, ACC], "acceleration")
+        app.add_gpu_system(_lib.SYS_NBODY_GRAVITY, [POS, ACC, MASS], "gravity")
+        run = (lambda k: [app.run(1) for _ in range(k)]) if one_by_one else app.run
+        first = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(900), 6)
+        w.create_entities(900, {POS: first[0], MASS: first[1], VEL: first[2], ACC: first[3]})
+        run(7)
+        more = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(400), 7)   # 1 300 bodies: one more mirror tile
+        app.sync_to_host()
+        w.create_entities(400, {POS: more[0], MASS: more[1], VEL: more[2], ACC: more[3]})
+        run(6)
+        app.sync_to_host()
+        for k in (5, 17, 1200, 640):
+            app.command_remove(ecs.Entity(*w.archetype_entities(1)[k]))
+        run(1)   # playback removes them after this tick
+        run(9)
+        big = scenes.spawn_bodies(scenes.all_heavy_random_cube_with_bodies(4000), 8)   # 5 296 bodies: beyond the resident limit
+        app.sync_to_host()
+        w.create_entities(4000, {POS: big[0], MASS: big[1], VEL: big[2], ACC: big[3]})
+        run(4)
+        app.sync_to_host()
+        n = len(w.archetype_entities(1))
+        assert n == 900 + 400 - 4 + 4000
+        outs.append([w.column(1, c)[:n].copy() for c in (POS, VEL, ACC)])
+        app.close()
+    for a, b in zip(*outs):
+        assert np.all(np.isfinite(a)) and np.array_equal(a.view(np.uint32), b.view(np.uint32))
