@@ -678,8 +678,12 @@ def run_gpu_arm(args) -> None:
     if world > 1:
         kernel_by_rank = [None] * world
         dist.all_gather_object(kernel_by_rank, float(roofline["kernel_ms_per_step"]))
+        tail_by_rank = [None] * world
+        dist.all_gather_object(tail_by_rank, float(t["gravity_reduce_ms"]) / k_steps)
         comm = {
             "kernel_ms_per_step_by_rank": [round(x, 3) for x in kernel_by_rank],
+            # chunk sums + reduce + integration tail (with the peer push), CUDA events around those launches
+            "tail_ms_per_step_by_rank": [round(x, 3) for x in tail_by_rank],
             "exchange": exchange,
             "bytes_per_rank_per_step": int((re - rb) * 16 * (world if exchange == "peer-push" else 1)),
             "bytes_total_per_step": int(n * 16 * (world if exchange == "peer-push" else 1)),

@@ -547,11 +547,18 @@ __device__ __forceinline__ void push_begin(const PeerPush& p) {
 // After the CTA's stores: the last CTA of the grid raises this rank's flag on every peer.
 __device__ __forceinline__ void push_end(const PeerPush& p) {
     if (p.n == 0) return;
-    __threadfence_system();
-    if (!p.signal) return;  // a later launch of the same generation raises the flag (stream order)
+    if (!p.signal) {  // a later launch of the same generation raises the flag (stream order; its fence covers these stores
+        __threadfence_system();  // only if they are performed: fence here as well)
+        return;
+    }
+    // one system-scope fence per CTA: the CTA barrier orders every thread's remote stores before thread 0's fence
+    // (cumulativity), which orders them before the counter increment the last CTA's flag stores follow
     __syncthreads();
     __shared__ uint32_t is_last;
-    if (threadIdx.x == 0) is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        is_last = atomicAdd(p.done_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
     __syncthreads();
     if (is_last) {
         if (threadIdx.x == 0) *p.done_counter = 0;  // the next pushing kernel follows in stream order
