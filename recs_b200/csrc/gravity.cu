@@ -621,7 +621,8 @@ __device__ __forceinline__ void build_chunk_table(const GravityWork& w, uint32_t
     }
 }
 // One chunk sum of one row: the prefix fragment continued with the tile fragments other CTAs stored one by one, in tile
-// order (fetched eight at a time, added in order).
+// order (fetched kFragBatch at a time -- independent loads in flight -- and added in order).
+constexpr uint32_t kFragBatch = 8;
 __device__ __forceinline__ float4 chunk_sum(const GravityReduceArgs& a, const ChunkTable& t, uint32_t c, uint32_t idx, float4 pre) {
     const GravityWork& w = a.work;
     const uint32_t rows = a.iblock_rows, K = w.chunk_tiles;
@@ -634,14 +635,14 @@ __device__ __forceinline__ float4 chunk_sum(const GravityReduceArgs& a, const Ch
         Span sg = span_of(g, w.grid, units);
         while (u < t.ext_hi[c]) {
             while (u >= sg.begin + sg.count) sg = span_of(++g, w.grid, units);
-            const uint32_t n = min(min(t.ext_hi[c], sg.begin + sg.count) - u, 8u);  // consecutive slots of one CTA
+            const uint32_t n = min(min(t.ext_hi[c], sg.begin + sg.count) - u, kFragBatch);  // consecutive slots of one CTA
             const float4* src = a.frags + (static_cast<size_t>(P.tile_frag_base) + static_cast<size_t>(g) * (K - 1) + (u - sg.begin)) * rows + idx;
-            float4 f[8];
+            float4 f[kFragBatch];
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
+            for (uint32_t j = 0; j < kFragBatch; ++j)
                 if (j < n) f[j] = __ldcs(src + static_cast<size_t>(j) * rows);
 #pragma unroll
-            for (uint32_t j = 0; j < 8; ++j)
+            for (uint32_t j = 0; j < kFragBatch; ++j)
                 if (j < n) cx += f[j].x, cy += f[j].y, cz += f[j].z;
             u += n;
         }
