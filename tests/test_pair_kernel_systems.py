@@ -46,6 +46,29 @@ def test_pair_kernels_compile_without_a_gpu():
     assert st == 12 and "has no member" in log and "recs_system_body.cu" in log  # the user's own line numbers
 
 
+def test_fast_fold_is_generated_only_when_the_source_defines_it(tmp_path, monkeypatch):
+    """`bool <pair>_fast(...)` in the source switches the generated kernel to the speculative fold (fast body per tile, exact
+    redo from the saved accumulator); without it the exact body alone is folded; a fast body with other parameters than
+    `pair` is a compile error in the user's own source, not a silent fallback.  RECS_GPU_KERNEL_DUMP keeps source + cubin."""
+    monkeypatch.setenv("RECS_GPU_KERNEL_DUMP", str(tmp_path))
+    with_fast = GRAVITY + "\n// variant A\n"     # (distinct texts: compiled sources are cached per process)
+    i, j = GRAVITY.index("bool pair_fast("), GRAVITY.index("void finish(")
+    without = GRAVITY[:i] + GRAVITY[j:] + "\n// variant B\n"
+    wrong = GRAVITY.replace("bool pair_fast(Total& total, const Position& position,", "bool pair_fast(Total& total, const Mass& position,") + "\n// variant C\n"
+    st, log, cubin = compile_pair_kernel_system(with_fast, "Total", "pair", "finish", GRAVITY_PARAMS)
+    assert st == 0 and cubin > 1000, log
+    st, log, cubin = compile_pair_kernel_system(without, "Total", "pair", "finish", GRAVITY_PARAMS)
+    assert st == 0 and cubin > 1000, log
+    st, log, _ = compile_pair_kernel_system(wrong, "Total", "pair", "finish", GRAVITY_PARAMS)
+    assert st == 12 and "pair_fast" in log
+    dumped = sorted(tmp_path.glob("recs_generated_*.cu"))
+    assert len(dumped) == 3 and len(list(tmp_path.glob("recs_generated_*.cubin"))) == 2
+    texts = {("A" if "// variant A" in t else "B" if "// variant B" in t else "C"): t for t in (p.read_text() for p in dumped)}
+    generated = lambda t: t[t.index("recs_generated_kernel.cu"):]
+    assert "recs_ok = recs_ok & pair_fast(recs_acc0" in generated(texts["A"]) and "recs_acc0 = recs_saved" in generated(texts["A"])
+    assert "pair_fast" not in generated(texts["B"]) and "pair(recs_acc0" in generated(texts["B"])
+
+
 def _bind(ctx, arch, comp, array):
     ctx.bind_column(arch, comp, array)
     ctx.upload(arch, comp)
