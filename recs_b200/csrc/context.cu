@@ -1837,18 +1837,20 @@ int32_t recs_gpu_system_creates(recs_gpu_ctx* c, uint32_t id, void* out_records,
     RECS_CUDA(c, cudaMemcpy(raw.data(), k.create_buf + 16, raw.size(), cudaMemcpyDeviceToHost));
     c->d2h_bytes += raw.size();
     // playback order = the order a sequential run would have recorded them in: entity order, then call order
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; ++i) order[i] = i;
-    auto key = [&](uint32_t i) {
-        unsigned long long k64;
-        uint32_t call;
-        memcpy(&k64, raw.data() + (size_t)i * stride, 8);
-        memcpy(&call, raw.data() + (size_t)i * stride + 8, 4);
-        return std::make_pair(k64, call);
+    struct Key {
+        unsigned long long entity;
+        uint32_t call, slot;
+        bool operator<(const Key& o) const { return entity != o.entity ? entity < o.entity : call < o.call; }
     };
-    std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key(a) < key(b); });
+    std::vector<Key> order(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        memcpy(&order[i].entity, raw.data() + (size_t)i * stride, 8);
+        memcpy(&order[i].call, raw.data() + (size_t)i * stride + 8, 4);
+        order[i].slot = i;
+    }
+    if (!std::is_sorted(order.begin(), order.end())) std::sort(order.begin(), order.end());
     for (uint32_t i = 0; i < n && i < cap_records; ++i)
-        memcpy((unsigned char*)out_records + (size_t)i * k.create_bytes, raw.data() + (size_t)order[i] * stride + 16, k.create_bytes);
+        memcpy((unsigned char*)out_records + (size_t)i * k.create_bytes, raw.data() + (size_t)order[i].slot * stride + 16, k.create_bytes);
     return RECS_OK;
 }
 

@@ -14,6 +14,7 @@
 //     downloaded before a CPU system touches a column the device wrote.
 #include <string.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <functional>
@@ -22,6 +23,7 @@
 #include <mutex>
 #include <set>
 #include <thread>
+#include <unordered_set>
 
 #include "host.h"
 
@@ -158,6 +160,9 @@ struct CreateCommand {
     std::vector<uint64_t> ids;
     std::vector<std::vector<uint8_t>> values;
     uint32_t system = 0xffffffffu;  // index of the recording system (commands recorded outside a system come last)
+    // A batch: `count` entities of the same component set recorded by one GPU system in one run, component k of all of
+    // them contiguous in values[k] (count == 0: a single entity, values[k] = its component k)
+    uint64_t count = 0;
 };
 
 struct recs_app {
@@ -166,6 +171,8 @@ struct recs_app {
     std::vector<std::pair<uint32_t, std::vector<uint32_t>>> gpu_removal_sources;  // (system index, outer archetypes) run this tick
     std::vector<uint32_t> gpu_create_sources;  // generic GPU systems with a create() record run this tick
     uint64_t last_created = 0, last_removed = 0;
+    // RECS_APP_PROFILE: milliseconds by phase, summed over ticks
+    double prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // systems+flush, fetch removals, fetch creates, world creates, device appends, world removes, device moves+rebind, ticks
     recs_gpu_ctx* gpu = nullptr;
     recs_world* world = nullptr;
     std::vector<AppSystem> systems;
@@ -448,9 +455,19 @@ struct SwapRemoveFold {
 // logged-and-ignored removal errors).  Removal order here is record order (GPU systems: system order,
 // archetype order, ascending component index); the reference iterates a hash set, so the final row
 // ORDER inside an archetype after several removals in one playback is not pinned by it.
+// RECS_APP_PROFILE=1: where a tick's host time goes (printed by recs_app_destroy)
+struct PhaseClock {
+    double* slot;
+    std::chrono::steady_clock::time_point t0;
+    explicit PhaseClock(double* s) : slot(s), t0(std::chrono::steady_clock::now()) {}
+    ~PhaseClock() { *slot += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 int32_t playback_commands(recs_app* app) {
     app->last_created = app->last_removed = 0;
     std::vector<recs_entity> to_remove = app->removes;
+    {
+    PhaseClock pc(&app->prof[1]);
     for (auto& src : app->gpu_removal_sources) {
         AppSystem& s = app->systems[src.first];
         for (uint32_t arch : src.second) {
@@ -465,8 +482,10 @@ int32_t playback_commands(recs_app* app) {
                 if (r < a.entities.size()) to_remove.push_back(a.entities[r]);
         }
     }
+    }
     app->gpu_removal_sources.clear();
     app->removes.clear();
+    PhaseClock* pc2 = new PhaseClock(&app->prof[2]);
     // `Commands::create` calls of generic GPU systems: records fetched in sequential-run order, split into components
     for (uint32_t index : app->gpu_create_sources) {
         AppSystem& s = app->systems[index];
@@ -476,19 +495,23 @@ int32_t playback_commands(recs_app* app) {
         if (!n) continue;
         std::vector<uint8_t> records((size_t)n * bytes);
         if ((st = recs_gpu_system_creates(app->gpu, s.gpu_id, records.data(), n, &n, &bytes)) != RECS_OK) return gpu_fail(app, st);
-        for (uint32_t r = 0; r < n; ++r) {
-            CreateCommand cmd;
-            cmd.system = index;
-            size_t off = (size_t)r * bytes;
-            for (size_t k = 0; k < s.create_comps.size(); ++k) {
-                cmd.ids.push_back(s.create_comps[k]);
-                cmd.values.push_back(std::vector<uint8_t>(records.begin() + off, records.begin() + off + s.create_sizes[k]));
-                off += s.create_sizes[k];
-            }
-            app->creates.push_back(std::move(cmd));
+        // one batch per system and run: the records (array of structs) become one column per component
+        CreateCommand cmd;
+        cmd.system = index;
+        cmd.count = n;
+        size_t field = 0;
+        for (size_t k = 0; k < s.create_comps.size(); ++k) {
+            const size_t elem = s.create_sizes[k];
+            cmd.ids.push_back(s.create_comps[k]);
+            std::vector<uint8_t> column((size_t)n * elem);
+            for (uint32_t r = 0; r < n; ++r) memcpy(column.data() + (size_t)r * elem, records.data() + (size_t)r * bytes + field, elem);
+            cmd.values.push_back(std::move(column));
+            field += elem;
         }
+        app->creates.push_back(std::move(cmd));
     }
     app->gpu_create_sources.clear();
+    delete pc2;
     // command buffers are drained system by system, in registration order (crates/ecs/src/lib.rs:325-336)
     std::stable_sort(app->creates.begin(), app->creates.end(),
                      [](const CreateCommand& a, const CreateCommand& b) { return a.system < b.system; });
@@ -517,16 +540,24 @@ int32_t playback_commands(recs_app* app) {
     int32_t st;
     const uint32_t archetypes_before = (uint32_t)w->archetypes.size();
     for (uint32_t a = 0; a < archetypes_before; ++a) touch(a);  // cheap: a handful of archetypes
+    PhaseClock* pc3 = new PhaseClock(&app->prof[3]);
     for (CreateCommand& cmd : app->creates) {
         std::vector<const void*> ptrs(cmd.ids.size());
         for (size_t i = 0; i < cmd.ids.size(); ++i) ptrs[i] = cmd.values[i].empty() ? nullptr : cmd.values[i].data();
-        st = recs_world_create_entity(w, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
+        if (cmd.count) {
+            st = recs_world_create_entities(w, cmd.count, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
+            app->last_created += st == RECS_OK ? cmd.count : 0;
+        } else {
+            st = recs_world_create_entity(w, cmd.ids.data(), ptrs.data(), (uint32_t)cmd.ids.size(), nullptr);
+            app->last_created += st == RECS_OK ? 1 : 0;
+        }
         if (st != RECS_OK) return app->fail(st, recs_world_last_error(w));
-        app->last_created++;
     }
     app->creates.clear();
+    delete pc3;
     // resident columns of grown archetypes: upload the new rows only
     std::set<ColKey> resident;  // columns kept in step on the device during this playback
+    PhaseClock* pc4 = new PhaseClock(&app->prof[4]);
     if (app->gpu)
         for (auto& kv : touched) {
             const uint32_t arch = kv.first;
@@ -543,7 +574,10 @@ int32_t playback_commands(recs_app* app) {
                 }
             }
         }
-    std::set<uint64_t> seen;
+    delete pc4;
+    PhaseClock* pc5 = new PhaseClock(&app->prof[5]);
+    std::unordered_set<uint64_t> seen;
+    seen.reserve(to_remove.size() * 2);
     for (recs_entity e : to_remove) {
         if (!seen.insert(entity_key(e)).second) continue;
         uint32_t arch = 0;
@@ -558,6 +592,8 @@ int32_t playback_commands(recs_app* app) {
         t.removed = true;
         t.fold.remove((uint32_t)row, last);
     }
+    delete pc5;
+    PhaseClock pc6(&app->prof[6]);
     if (app->gpu)
         for (auto& kv : touched) {
             const uint32_t arch = kv.first;
@@ -616,6 +652,11 @@ int32_t recs_app_create(recs_gpu_ctx* gpu, recs_app** out) {
 
 int32_t recs_app_destroy(recs_app* app) {
     if (!app) return RECS_ERR_INVALID_ARGUMENT;
+    if (getenv("RECS_APP_PROFILE") && app->prof[7] > 0)
+        fprintf(stderr, "recs_app profile over %.0f ticks (ms per tick): systems+flush %.4f | fetch removals %.4f | fetch creates %.4f | "
+                "world creates %.4f | device appends %.4f | world removes %.4f | device moves+rebind %.4f\n", app->prof[7],
+                app->prof[0] / app->prof[7], app->prof[1] / app->prof[7], app->prof[2] / app->prof[7], app->prof[3] / app->prof[7],
+                app->prof[4] / app->prof[7], app->prof[5] / app->prof[7], app->prof[6] / app->prof[7]);
     if (app->schedule) recs_schedule_destroy(app->schedule);
     recs_world_destroy(app->world);
     delete app;
@@ -884,6 +925,8 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
         app->last_order.clear();
         app->last_batch.clear();
         uint32_t batch_no = 0;
+        app->prof[7] += 1;
+        PhaseClock* pc0 = new PhaseClock(&app->prof[0]);
         for (;;) {  // Executor::execute_once
             uint32_t got = 0;
             st = recs_schedule_next_batch(app->schedule, RECS_REACTION_RETURN_ERROR, batch.data(), (uint32_t)batch.size(), &got);
@@ -928,7 +971,9 @@ int32_t recs_app_run(recs_app* app, uint32_t n_ticks, int32_t ordered) {
             for (uint32_t i = 0; i < got; ++i) recs_schedule_complete(app->schedule, batch[i]);
             ++batch_no;
         }
-        if ((st = flush_gpu_chain(app)) != RECS_OK) return st;
+        st = flush_gpu_chain(app);
+        delete pc0;
+        if (st != RECS_OK) return st;
         // loop { runner.tick(); runner.playback_commands(); } (lib.rs:321-323)
         if ((st = playback_commands(app)) != RECS_OK) return st;
         // A tick that was ONE chain of GPU systems holding every system of the application, none of which can record a

@@ -138,7 +138,9 @@ int32_t check_registered(recs_world& w, const uint64_t* ids, uint32_t n) {
     return RECS_OK;
 }
 
-int32_t create_empty_entity(recs_world& w, recs_entity* out) {
+// The id half of World::create_empty_entity (lib.rs:701-718): reuse the most recently deleted id with its generation
+// bumped, else the next fresh one.
+int32_t allocate_entity(recs_world& w, recs_entity* out) {
     if (w.archetypes.empty()) w.archetypes.push_back(Archetype());  // the "empty entity archetype"
     recs_entity e;
     if (!w.deleted_entities.empty()) {
@@ -160,8 +162,16 @@ int32_t create_empty_entity(recs_world& w, recs_entity* out) {
         slot.entity = e;
         w.entities.push_back(slot);
     }
+    *out = e;
+    return RECS_OK;
+}
+
+int32_t create_empty_entity(recs_world& w, recs_entity* out) {
+    recs_entity e;
+    int32_t st = allocate_entity(w, &e);
+    if (st != RECS_OK) return st;
     // store_entity_in_archetype(new_entity, EMPTY_ENTITY_ARCHETYPE_INDEX)
-    int32_t st = store_entity(w, w.archetypes[0], e);
+    st = store_entity(w, w.archetypes[0], e);
     if (st != RECS_OK) return st;
     w.entity_to_archetype_index[entity_key(e)] = 0;
     *out = e;
@@ -359,7 +369,54 @@ int32_t recs_world_create_entities(recs_world* w, uint64_t count, const uint64_t
     std::vector<const void*> values(n);
     std::vector<uint32_t> elem(n);
     for (uint32_t i = 0; i < n; ++i) elem[i] = w->registry.at(ids[i]).elem;
+    bool distinct = n > 0;
+    for (uint32_t i = 0; i < n; ++i)
+        for (uint32_t j = 0; j < i; ++j) distinct = distinct && ids[i] != ids[j];
+    const std::vector<uint64_t> id_set(ids, ids + n);
     for (uint64_t k = 0; k < count; ++k) {
+        // Batch path, once the archetype of exactly this component set exists (the first entity of a new set creates it the
+        // long way).  Entity by entity the reference stores the new entity in the empty-entity archetype and moves it out
+        // again (lib.rs:720-726, archetypes.rs:556-651): there it is pushed last and swap-removed as the last element, which
+        // leaves that archetype as it was.  What remains per entity is the id allocation, its row in the target archetype and
+        // the two index maps; the component values of all remaining entities are appended column by column.  Same end state
+        // (tests/test_world.py::test_batch_create_equals_single_creates).
+        uint32_t target = 0;
+        if (distinct && exactly_matching(*w, id_set, &target) && target != 0) {
+            const uint64_t m = count - k;
+            {
+                Archetype& t = w->archetypes[target];
+                t.entities.reserve(t.entities.size() + m);
+                t.entity_to_component_index.reserve(t.entity_to_component_index.size() + m);
+            }
+            for (uint64_t r = 0; r < m; ++r) {
+                recs_entity e;
+                st = allocate_entity(*w, &e);
+                if (st != RECS_OK) return st;
+                Archetype& t = w->archetypes[target];
+                const uint64_t index = t.entity_to_component_index.size();
+                if (!t.entity_to_component_index.insert(std::make_pair(entity_key(e), index)).second)
+                    return w->fail(RECS_ERR_WORLD, "archetype already contains entity: " + entity_str(e));
+                t.entities.push_back(e);
+                w->entity_to_archetype_index[entity_key(e)] = target;
+                if (out) out[k + r] = e;
+            }
+            Archetype& t = w->archetypes[target];
+            for (uint32_t i = 0; i < n; ++i) {
+                ColumnStore& col = t.columns.at(ids[i]);
+                if (col.elem) {
+                    const size_t old = col.data.size();
+                    col.data.resize(old + (size_t)m * col.elem);
+                    if (columns && columns[i])
+                        memcpy(col.data.data() + old, static_cast<const uint8_t*>(columns[i]) + k * elem[i], (size_t)m * col.elem);
+                    else
+                        memset(col.data.data() + old, 0, (size_t)m * col.elem);
+                }
+                col.len += m;
+            }
+            w->archetypes[0].version += 3 * m;  // store, move out, update_after_entity_removal -- per entity
+            t.version += 3 * m;                 // move in, store, add_components
+            return RECS_OK;
+        }
         for (uint32_t i = 0; i < n; ++i)
             values[i] = columns && columns[i] ? static_cast<const uint8_t*>(columns[i]) + k * elem[i] : nullptr;
         recs_entity e;

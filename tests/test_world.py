@@ -468,3 +468,65 @@ def test_fold_swap_removes_rejects_rows_out_of_range():
     with pytest.raises(EcsError):
         fold_swap_removes(1, [0, 0])
     assert fold_swap_removes(4, [3, 2]) == ([], [], 2)  # removing from the end moves nothing
+
+
+def test_batch_create_equals_single_creates():
+    """recs_world_create_entities takes a batch path once the archetype of the component set exists (no stop in the
+    empty-entity archetype per entity).  The end state must be the one the reference's entity-by-entity creation produces:
+    entity ids and generations (deleted ids are reused most-recent first), archetype indices, row order, component
+    indices, column bytes -- through random interleavings of batch creates over several component sets, single creates and
+    deletions."""
+    from recs_b200 import ecs
+
+    A, B, Cc, Z = 1, 2, 3, 4
+    dtypes = {A: np.dtype((np.float32, 3)), B: np.float32, Cc: np.dtype((np.uint8, 6)), Z: np.dtype((np.uint8, 0))}
+    sets = [(A,), (B, A), (A, B, Cc), (Cc,), (Z, A)]
+    rng = np.random.default_rng(77)
+    worlds = [ecs.World(), ecs.World()]
+    for w in worlds:
+        for c, dt in dtypes.items():
+            w.register_component(c, dt, f"c{c}")
+
+    def columns(ids, m):
+        out = {}
+        for c in ids:
+            dt = np.dtype(dtypes[c])
+            shape = (m,) + dt.shape
+            base = dt.base
+            if base == np.float32:
+                out[c] = rng.standard_normal(shape).astype(np.float32)
+            else:
+                out[c] = rng.integers(0, 255, shape).astype(np.uint8) if dt.shape != (0,) else np.zeros((m, 0), np.uint8)
+        return out
+
+    def state(w):
+        snap = {"slots": w.entity_slots(), "archetypes": []}
+        for a in range(w.archetype_count()):
+            ents = w.archetype_entities(a)
+            comps = w.archetype_components(a)
+            snap["archetypes"].append((ents, comps, [w.column(a, c).tobytes() for c in comps],
+                                       [w.entity_component_index(ecs.Entity(*e)) for e in ents]))
+        return snap
+
+    for step in range(60):
+        op = rng.choice(["batch", "batch", "single", "delete"])
+        if op == "batch":
+            ids = sets[rng.integers(len(sets))]
+            m = int(rng.integers(1, 40))
+            cols = columns(ids, m)
+            worlds[0].create_entities(m, cols)
+            for k in range(m):
+                worlds[1].create_entity({c: cols[c][k] for c in ids})
+        elif op == "single":
+            ids = sets[rng.integers(len(sets))]
+            cols = columns(ids, 1)
+            for w in worlds:
+                w.create_entity({c: cols[c][0] for c in ids})
+        else:
+            alive = [e for e in worlds[0].entity_slots() if e is not None]
+            for e in rng.permutation(len(alive))[: int(rng.integers(0, 12))]:
+                for w in worlds:
+                    w.delete_entity(ecs.Entity(*alive[e]))
+        assert state(worlds[0]) == state(worlds[1]), step
+    assert worlds[0].archetype_count() == len(sets) + 1
+    assert any(gen > 0 for slot in worlds[0].entity_slots() if slot for gen in [slot[1]])  # ids were reused
