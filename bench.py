@@ -955,6 +955,31 @@ def streaming_extras(ctx, traffic) -> dict:
     }
     out["clocks"] = sampler.stop()
     out["rain_16Mi_fused"]["parity"] = rain_parity(ctx, ARCH2, VEL, POS, vel, pos, 3 + 20)
+    # the reference's rain_simulation benchmark as it registers it -- all seven systems, drops spawned (Commands::create) and
+    # removed (ground_collision) every tick -- with the whole tick on the device and the host World playing the commands back
+    from recs_b200.rain import rain_application
+
+    app = rain_application(ctx, 16384)
+    app.run(100)  # steady state: drops are landing
+    ctx.synchronize()
+    t0 = time.perf_counter()
+    created = removed = 0
+    for _ in range(50):
+        app.run(1)
+        c, r = app.last_playback()
+        created, removed = created + c, removed + r
+    ctx.synchronize()
+    sec = time.perf_counter() - t0
+    out["rain_benchmark_full_tick_16384_clouds"] = {
+        "ms_per_tick": sec / 50 * 1e3,
+        "drops_alive": len(app.world.archetype_entities(2)),
+        "created_per_tick": created / 50,
+        "removed_per_tick": removed / 50,
+        "how": "wall clock per tick (host + device) over 50 ticks after 100 warm-up ticks; crates/ecs_bench_suite/src/recs/rain_simulation.rs "
+               "system set, create_evenly_interspersed_clouds(16384); entity ids and columns of this set-up are checked against the oracle "
+               "tick by tick in tests/test_gpu_playback.py::test_full_rain_tick_through_application",
+    }
+    app.close()
     out["hbm_peak_GBps"] = peak
     return out
 
