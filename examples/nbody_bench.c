@@ -53,9 +53,19 @@ static double now_ms(void) {
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+/* `benchmark_system` of the reference's bench (crates/ecs_bench_suite/src/recs/n_body.rs:36-52): a parameterless CPU system that
+ * counts the ticks.  With it in the schedule every tick passes through the host scheduler (a CPU system may record
+ * commands), so recs_app_run cannot hand the remaining ticks to the context in one call. */
+static void benchmark_system(void* user, uint32_t archetype, uint64_t count, void* const* columns, uint32_t n_columns) {
+    (void)archetype, (void)count, (void)columns, (void)n_columns;
+    ++*(uint64_t*)user;
+}
+
 int main(int argc, char** argv) {
     const uint64_t n = argc > 1 ? strtoull(argv[1], NULL, 10) : 65536;
     const uint32_t ticks = argc > 2 ? (uint32_t)atoi(argv[2]) : 10;
+    const int with_benchmark_system = argc > 3 && strcmp(argv[3], "benchmark_system") == 0;
+    uint64_t ticks_counted = 0;
     recs_gpu_ctx* ctx = NULL;
     recs_gpu_config cfg;
     recs_gpu_default_config(&cfg);
@@ -75,6 +85,10 @@ int main(int argc, char** argv) {
     CHECK_APP(recs_app_add_gpu_system(app, RECS_SYS_NBODY_MOVEMENT, movement_ids, 2, &movement));
     CHECK_APP(recs_app_add_gpu_system(app, RECS_SYS_NBODY_ACCELERATION, acceleration_ids, 2, &acceleration));
     CHECK_APP(recs_app_add_gpu_system(app, RECS_SYS_NBODY_GRAVITY, gravity_ids, 3, &gravity));
+    if (with_benchmark_system) {
+        uint32_t index;
+        CHECK_APP(recs_app_add_cpu_system(app, "benchmark_system", NULL, 0, benchmark_system, &ticks_counted, &index));
+    }
 
     /* EVERYTHING_HEAVY (crates/n-body/src/scenes.rs:10-21), per body: position xyz, mass, velocity xyz, acceleration xyz */
     float* pos = malloc(n * 12);
@@ -101,8 +115,11 @@ int main(int argc, char** argv) {
     CHECK_GPU(recs_gpu_synchronize(ctx));
     const double ms = (now_ms() - t0) / ticks;
 
-    uint32_t order[8], batch[8], n_order = 0;
-    CHECK_APP(recs_app_last_tick_order(app, order, batch, 8, &n_order));
+    uint32_t order_all[8], batch[8], n_order = 0, order[8], n_gpu = 0;
+    CHECK_APP(recs_app_last_tick_order(app, order_all, batch, 8, &n_order));
+    for (uint32_t i = 0; i < n_order && i < 8; ++i)
+        if (order_all[i] < 3) order[n_gpu++] = order_all[i]; /* (benchmark_system, if registered, is system 3) */
+    if (with_benchmark_system && ticks_counted != (uint64_t)ticks + 1) return 1;
     const char* names[3];
     names[movement] = "movement";
     names[acceleration] = "acceleration";
