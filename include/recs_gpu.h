@@ -327,10 +327,10 @@ int32_t recs_gpu_set_tick_order(recs_gpu_ctx* ctx, const uint32_t* system_ids, u
 /* `Executor::execute_once` x n_ticks (crates/scheduler/src/executor/mod.rs:191-236) for a chain
  * made only of GPU systems: one stream-ordered chain (a CUDA graph when enabled).
  * When the chain is exactly gravity -> movement -> acceleration over one body archetype of at most
- * 4 096 rows (the reference's own benchmark size, crates/ecs_bench_suite/benches/n_body.rs) and
- * n_ticks >= 3, all ticks after the first run in ONE cooperative launch that keeps the position
- * mirror in shared memory and the rows in registers (one grid barrier per tick); columns come out
- * bit-identical to the tick-by-tick chain.  RECS_GPU_RESIDENT_MAX_ROWS=0 (environment) switches
+ * 4 096 rows (the reference's own benchmark size, crates/ecs_bench_suite/benches/n_body.rs), the
+ * ticks of a call run in ONE cooperative launch that keeps the position mirror in shared memory and
+ * the rows in registers (one grid barrier per tick; preceded by one tick of the ordinary chain when
+ * the mirror has to be packed first); columns come out bit-identical to the tick-by-tick chain.  RECS_GPU_RESIDENT_MAX_ROWS=0 (environment) switches
  * that path off. */
 int32_t recs_gpu_tick(recs_gpu_ctx* ctx, uint32_t n_ticks);
 

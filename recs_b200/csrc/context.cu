@@ -139,6 +139,9 @@ struct recs_gpu_ctx {
     float* posm_alt = nullptr;
     size_t posm_alt_cap = 0;
     uint32_t* resident_barrier = nullptr;
+    uint32_t resident_barrier_count = 0;  // arrivals counted so far (the counter only grows: no reset between launches)
+    uint64_t posm_pack_serial = 0;        // bumped by every pack of the mirror
+    uint64_t posm_alt_serial = ~0ull;     // pack whose G*m entries and null bodies the second buffer holds
     uint64_t resident_max_rows = 4096;  // RECS_GPU_RESIDENT_MAX_ROWS (0 switches the path off)
     uint64_t resident_launches = 0;
     uint64_t posm_bodies = 0;  // padded body count currently laid out
@@ -475,6 +478,7 @@ int32_t run_gravity(recs_gpu_ctx* c, System& sys, System* movement = nullptr, Sy
         c->posm_sources = sources;
         c->posm_bodies = n_jpad;
         c->posm_scaled = scaled;
+        c->posm_pack_serial++;
     } else if (c->capturing) {
         c->graph_elided_pack = true;
     }
@@ -1889,6 +1893,18 @@ bool resident_ticks_apply(recs_gpu_ctx* c) {
     return p && p->count >= 1 && p->count <= c->resident_max_rows && p->count <= kGravSmallRows;
 }
 
+// The mirror holds exactly this archetype's bodies, unscaled, and no source column was written since it was refreshed.
+bool resident_mirror_ready(recs_gpu_ctx* c) {
+    System& g = c->systems[c->order[0]];
+    const uint32_t arch = g.archs[0];
+    const Column* p = find_column(c, arch, g.comp[0]);
+    if (!p || !c->posm || c->posm_scaled) return false;
+    const uint64_t n_pad = (p->count + kGravTile - 1) / kGravTile * kGravTile;
+    if (c->posm_bodies != n_pad || c->posm_sources.size() != 2) return false;
+    if (c->posm_sources[0].first != ColKey(arch, g.comp[0]) || c->posm_sources[1].first != ColKey(arch, g.comp[2])) return false;
+    return posm_is_current(c);
+}
+
 int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
     *launched = true;
     System& g = c->systems[c->order[0]];
@@ -1904,10 +1920,20 @@ int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
     const uint64_t n_pad = (n + kGravTile - 1) / kGravTile * kGravTile;
     if (c->posm_bodies != n_pad || c->posm_scaled || !posm_is_current(c))
         return fail(c, RECS_ERR_UNSUPPORTED, "resident ticks need the current unscaled mirror of the archetype");
+    const float* alt_before = c->posm_alt;
     if ((st = ensure(c, &c->posm_alt, &c->posm_alt_cap, n_pad * 16)) != RECS_OK) return st;
-    if (!c->resident_barrier) RECS_CUDA(c, cudaMalloc((void**)&c->resident_barrier, 256));
-    RECS_CUDA(c, cudaMemsetAsync(c->resident_barrier, 0, 4, c->stream));
-    RECS_CUDA(c, cudaMemcpyAsync(c->posm_alt, c->posm, n_pad * 16, cudaMemcpyDeviceToDevice, c->stream));  // G*m and the null bodies
+    if (c->posm_alt != alt_before) c->posm_alt_serial = ~0ull;
+    if (!c->resident_barrier) {
+        RECS_CUDA(c, cudaMalloc((void**)&c->resident_barrier, 256));
+        RECS_CUDA(c, cudaMemsetAsync(c->resident_barrier, 0, 256, c->stream));
+        c->resident_barrier_count = 0;
+    }
+    if (c->posm_alt_serial != c->posm_pack_serial) {
+        // G*m and the null bodies of the second buffer: the kernel refreshes positions only, so once both buffers carry the
+        // same pack they stay interchangeable until the next one
+        RECS_CUDA(c, cudaMemcpyAsync(c->posm_alt, c->posm, n_pad * 16, cudaMemcpyDeviceToDevice, c->stream));
+        c->posm_alt_serial = c->posm_pack_serial;
+    }
     ResidentTicksArgs ra;
     memset(&ra, 0, sizeof ra);
     ra.posm[0] = c->posm;
@@ -1921,6 +1947,7 @@ int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
     ra.dt = c->cfg.nbody_dt;
     ra.eps = c->cfg.nbody_epsilon;
     ra.barrier = c->resident_barrier;
+    ra.barrier_base = c->resident_barrier_count;
     ra.error = c->dev_error;
     {
         NvtxRange range("resident ticks");
@@ -1936,8 +1963,11 @@ int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
     c->kernel_launches++;
     c->gravity_launches++;
     c->resident_launches++;
-    if (n_ticks & 1)  // the last tick refreshed the second buffer
-        RECS_CUDA(c, cudaMemcpyAsync(c->posm, c->posm_alt, n_pad * 16, cudaMemcpyDeviceToDevice, c->stream));
+    c->resident_barrier_count += (n_ticks - 1) * ((ra.n_rows + 31) / 32);  // one arrival per CTA and tick but the last
+    if (n_ticks & 1) {  // the last tick refreshed the second buffer: it is the mirror now
+        std::swap(c->posm, c->posm_alt);
+        std::swap(c->posm_cap, c->posm_alt_cap);
+    }
     pos->version += n_ticks;
     vel->version += n_ticks;
     acc->version += n_ticks;
@@ -1948,15 +1978,20 @@ int32_t run_resident_ticks(recs_gpu_ctx* c, uint32_t n_ticks, bool* launched) {
 int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
     RECS_ENTER(c);
     if (n_ticks == 0 || c->order.empty()) return RECS_OK;
-    if (n_ticks >= 3 && !c->capturing && resident_ticks_apply(c)) {
-        // the first tick through the ordinary chain (binds, sizes, packs the mirror if a column changed), the rest in one launch
-        int32_t st = run_tick_once(c);
-        if (st != RECS_OK) return st;
-        bool launched = false;
-        st = run_resident_ticks(c, n_ticks - 1, &launched);
-        if (st != RECS_OK || launched) return st;
-        c->resident_max_rows = 0;  // not on this device: the chain below, now and from here on
-        --n_ticks;
+    if (!c->capturing && resident_ticks_apply(c)) {
+        // with the mirror of exactly this archetype current, every tick of the call is in ONE launch; else the first tick goes
+        // through the ordinary chain (binds, sizes, packs the mirror) and the rest follows in one launch
+        if (!resident_mirror_ready(c)) {
+            int32_t st = run_tick_once(c);
+            if (st != RECS_OK) return st;
+            if (--n_ticks == 0) return RECS_OK;
+        }
+        if (resident_mirror_ready(c)) {
+            bool launched = false;
+            int32_t st = run_resident_ticks(c, n_ticks, &launched);
+            if (st != RECS_OK || launched) return st;
+            c->resident_max_rows = 0;  // not on this device: the chain below, now and from here on
+        }
     }
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (c->timing) {

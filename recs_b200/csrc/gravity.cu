@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(512, 1) nbody_resident_ticks_kernel(const Resi
             if (threadIdx.x == 0) {
                 // bounded: a grid that is not co-resident (never the case for a cooperative launch) ends in an error, not a hang
                 // (every CTA waits for the same count, so all of them give up at the same tick)
-                if (!ptx::grid_barrier(a.barrier, (k + 1u) * gridDim.x, a.error)) stop = 1;
+                if (!ptx::grid_barrier(a.barrier, a.barrier_base + (k + 1u) * gridDim.x, a.error)) stop = 1;
             }
             __syncthreads();
             if (stop) break;

@@ -190,7 +190,8 @@ struct ResidentTicksArgs {
     uint32_t n_ticks;
     float dt;
     float eps;
-    uint32_t* barrier; // zero before the launch
+    uint32_t* barrier; // arrival counter of the grid barrier; holds barrier_base at launch
+    uint32_t barrier_base;
     uint32_t* error;   // raised if the grid barrier times out
 };
 cudaError_t launch_resident_ticks(const ResidentTicksArgs& a, cudaStream_t s);
