@@ -1987,9 +1987,15 @@ int32_t recs_gpu_tick(recs_gpu_ctx* c, uint32_t n_ticks) {
             if (--n_ticks == 0) return RECS_OK;
         }
         if (resident_mirror_ready(c)) {
-            bool launched = false;
-            int32_t st = run_resident_ticks(c, n_ticks, &launched);
-            if (st != RECS_OK || launched) return st;
+            // (at most 2^20 ticks per launch: the barrier counter is compared through a signed 32-bit difference)
+            bool launched = true;
+            while (n_ticks && launched) {
+                const uint32_t chunk = std::min<uint32_t>(n_ticks, 1u << 20);
+                int32_t st = run_resident_ticks(c, chunk, &launched);
+                if (st != RECS_OK) return st;
+                if (launched) n_ticks -= chunk;
+            }
+            if (n_ticks == 0) return RECS_OK;
             c->resident_max_rows = 0;  // not on this device: the chain below, now and from here on
         }
     }
